@@ -1,0 +1,227 @@
+"""ctypes view of libcvvp_cuda.so (include/cvvp.h).
+
+This is what tests/ and bench.py call: every GPU test goes through the C ABI exactly as the
+reference-side binding in INTEGRATION.md would.  There is no CPU fallback here: if the library is
+missing or no B200 is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libcvvp_cuda.so"
+HEADER = PKG_DIR.parent / "include" / "cvvp.h"
+
+_lib = None
+
+
+class CvvpError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"cvvp error {code}: {message}")
+        self.code = code
+
+
+def declared_symbols() -> list[str]:
+    """Every function name include/cvvp.h declares (used by the symbol-export test)."""
+    text = HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cvvp_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the CUDA path)"
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, sz, u32 = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_uint32
+    sigs = {
+        "cvvp_abi_version": (i32, []),
+        "cvvp_ctx_create": (i32, [i32, C.POINTER(vp)]),
+        "cvvp_ctx_destroy": (None, [vp]),
+        "cvvp_last_error": (C.c_char_p, [vp]),
+        "cvvp_ctx_synchronize": (i32, [vp]),
+        "cvvp_ctx_stream": (vp, [vp]),
+        "cvvp_ctx_device": (i32, [vp]),
+        "cvvp_ctx_sm_count": (i32, [vp]),
+        "cvvp_ctx_launch_count": (i64, [vp]),
+        "cvvp_host_alloc": (i32, [sz, C.POINTER(vp)]),
+        "cvvp_host_free": (i32, [vp]),
+        "cvvp_median_begin": (i32, [vp, sz, i64]),
+        "cvvp_median_push": (i32, [vp, vp, i64, sz]),
+        "cvvp_median_count": (i64, [vp]),
+        "cvvp_median_finish": (i32, [vp, vp]),
+        "cvvp_median_abort": (i32, [vp]),
+        "cvvp_median_device": (i32, [vp, vp, i64, sz, sz, vp, vp]),
+        "cvvp_median_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
+        "cvvp_synth_frames_device": (i32, [vp, vp, sz, i32, i32, i32, i32, i64, i64, u32, i32, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class PinnedBuffer:
+    """Page-locked host memory from cvvp_host_alloc, exposed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        lib = load()
+        p = C.c_void_p()
+        rc = lib.cvvp_host_alloc(nbytes, C.byref(p))
+        if rc != 0:
+            raise CvvpError(rc, (lib.cvvp_last_error(None) or b"").decode())
+        self._ptr = p
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    def close(self):
+        if self._ptr is not None:
+            self.array = None
+            load().cvvp_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One cvvp_ctx (one CUDA device)."""
+
+    def __init__(self, device: int = -1):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.cvvp_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise CvvpError(rc, (self._lib.cvvp_last_error(None) or b"").decode())
+        self._h = h
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise CvvpError(rc, (self._lib.cvvp_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.cvvp_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.cvvp_ctx_stream(self._h) or 0)
+
+    @property
+    def device(self) -> int:
+        return self._lib.cvvp_ctx_device(self._h)
+
+    @property
+    def sm_count(self) -> int:
+        return self._lib.cvvp_ctx_sm_count(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.cvvp_ctx_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self._lib.cvvp_ctx_synchronize(self._h))
+
+    # -- median ---------------------------------------------------------------------------
+    def median_begin(self, nelem: int, nframes_hint: int = -1):
+        self._check(self._lib.cvvp_median_begin(self._h, nelem, nframes_hint))
+
+    def median_push(self, frames: np.ndarray):
+        """frames: uint8 array (n, ...) whose trailing dims are one frame; frame bytes must be contiguous."""
+        if frames.dtype != np.uint8 or frames.ndim < 2:
+            raise TypeError("frames must be a uint8 array of shape (n, ...)")
+        n = frames.shape[0]
+        if n == 0:
+            return
+        nelem = int(np.prod(frames.shape[1:]))
+        one = frames[0]
+        if not one.flags.c_contiguous:
+            frames = np.ascontiguousarray(frames)
+        stride = frames.strides[0] if n > 1 else nelem
+        if stride < nelem:
+            frames = np.ascontiguousarray(frames)
+            stride = nelem
+        self._check(self._lib.cvvp_median_push(self._h, frames.ctypes.data, n, stride))
+        self._keepalive = frames
+
+    def median_push_raw(self, ptr: int, n: int, stride: int):
+        self._check(self._lib.cvvp_median_push(self._h, ptr, n, stride))
+
+    def median_count(self) -> int:
+        return int(self._lib.cvvp_median_count(self._h))
+
+    def median_finish(self, out: np.ndarray | None = None, nelem: int | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(nelem, np.uint8)
+        if out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise TypeError("out must be a contiguous uint8 array")
+        self._check(self._lib.cvvp_median_finish(self._h, out.ctypes.data))
+        self._keepalive = None
+        return out
+
+    def median_abort(self):
+        self._check(self._lib.cvvp_median_abort(self._h))
+
+    def median(self, frames: np.ndarray, chunk: int = 64) -> np.ndarray:
+        """Whole job through the streaming host interface: begin, push in chunks, finish."""
+        n = frames.shape[0]
+        nelem = int(np.prod(frames.shape[1:]))
+        self.median_begin(nelem, n)
+        try:
+            for i in range(0, n, chunk):
+                self.median_push(frames[i : i + chunk])
+        except Exception:
+            self.median_abort()
+            raise
+        return self.median_finish(nelem=nelem).reshape(frames.shape[1:])
+
+    def median_device(self, d_frames: int, nframes: int, nelem: int, frame_stride: int, d_out: int, stream: int = 0):
+        self._check(self._lib.cvvp_median_device(self._h, d_frames, nframes, nelem, frame_stride, d_out, stream or None))
+
+    def median_last_kernel_ms(self) -> float:
+        v = C.c_float()
+        self._check(self._lib.cvvp_median_last_kernel_ms(self._h, C.byref(v)))
+        return float(v.value)
+
+    # -- synthetic frames -----------------------------------------------------------------
+    def synth_frames_device(self, d_frames: int, frame_stride: int, width: int, height: int, first_frame: int,
+                            nframes: int, seed: int, ndisks: int, row0: int = 0, nrows: int | None = None,
+                            stream: int = 0):
+        if nrows is None:
+            nrows = height - row0
+        self._check(
+            self._lib.cvvp_synth_frames_device(self._h, d_frames, frame_stride, width, height, row0, nrows, first_frame,
+                                               nframes, seed, ndisks, stream or None)
+        )

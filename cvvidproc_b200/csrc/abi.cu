@@ -1,0 +1,478 @@
+// extern "C" entry points of libcvvp_cuda.so (include/cvvp.h): context management, the streaming
+// (host-buffer) median job with pinned staging and stream/event pipelining, and the
+// device-resident forms used by the benchmark.  No C++ exception leaves this file.
+#include "context.hpp"
+
+#include <cstring>
+#include <new>
+
+namespace cvvp
+{
+namespace
+{
+thread_local std::string g_err;
+constexpr size_t kStagingBytes = size_t(32) << 20; // per pinned staging buffer
+constexpr int kStagingBufs = 3;
+
+size_t round_up(size_t v, size_t a)
+{
+    return (v + a - 1) / a * a;
+}
+} // namespace
+
+void set_global_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+const char *global_error()
+{
+    return g_err.c_str();
+}
+
+int fail(cvvp_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_err = buf;
+    return code;
+}
+
+namespace
+{
+void release_median(cvvp_ctx *ctx)
+{
+    MedianJob &m = ctx->med;
+    m.active = false;
+    m.count = 0;
+    // device buffers are kept for reuse by the next job of the same context
+}
+
+int ensure_stack(cvvp_ctx *ctx, long long frames_needed)
+{
+    MedianJob &m = ctx->med;
+    if (frames_needed <= m.capacity)
+        return CVVP_OK;
+    long long new_cap = m.capacity > 0 ? m.capacity : 64;
+    while (new_cap < frames_needed)
+        new_cap *= 2;
+    const size_t bytes = size_t(new_cap) * m.stride;
+    if (bytes > m.d_stack_bytes) {
+        uint8_t *fresh = nullptr;
+        if (cudaMalloc(&fresh, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, CVVP_ERR_NOMEM, "median: cudaMalloc of %zu bytes for the frame stack failed", bytes);
+        }
+        if (m.d_stack && m.count > 0) {
+            CVVP_CUDA_OK(ctx, cudaMemcpyAsync(fresh, m.d_stack, size_t(m.count) * m.stride, cudaMemcpyDeviceToDevice, ctx->copy));
+            CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy));
+        }
+        if (m.d_stack)
+            cudaFree(m.d_stack);
+        m.d_stack = fresh;
+        m.d_stack_bytes = bytes;
+    }
+    m.capacity = new_cap;
+    return CVVP_OK;
+}
+
+int ensure_staging(cvvp_ctx *ctx)
+{
+    if (!ctx->staging.empty())
+        return CVVP_OK;
+    ctx->staging.resize(kStagingBufs);
+    for (auto &b : ctx->staging) {
+        if (cudaMallocHost(&b.host, kStagingBytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, CVVP_ERR_NOMEM, "pinned staging allocation failed");
+        }
+        b.bytes = kStagingBytes;
+        CVVP_CUDA_OK(ctx, cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+    }
+    return CVVP_OK;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+} // namespace
+} // namespace cvvp
+
+using namespace cvvp;
+
+extern "C" {
+
+int cvvp_abi_version(void)
+{
+    return CVVP_ABI_VERSION;
+}
+
+int cvvp_ctx_create(int device, cvvp_ctx **out_ctx)
+{
+    if (!out_ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "cvvp_ctx_create: out_ctx is NULL");
+    *out_ctx = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, CVVP_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess)
+            device = 0;
+    }
+    if (device >= ndev)
+        return fail(nullptr, CVVP_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    cvvp_ctx *ctx = new (std::nothrow) cvvp_ctx();
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop{};
+    int rc = CVVP_OK;
+    auto bail = [&](const char *what, cudaError_t err) {
+        rc = fail(nullptr, CVVP_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(err));
+        cvvp_ctx_destroy(ctx);
+        return rc;
+    };
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return bail("cudaGetDeviceProperties", e);
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (prop.major != 10) {
+        fail(nullptr, CVVP_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+             prop.major, prop.minor);
+        cvvp_ctx_destroy(ctx);
+        return CVVP_ERR_UNSUPPORTED;
+    }
+    if ((e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_start)) != cudaSuccess)
+        return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_stop)) != cudaSuccess)
+        return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess)
+        return bail("cudaEventCreate", e);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres{};
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        fail(nullptr, CVVP_ERR_CUDA, "cuTensorMapEncodeTiled is not exported by this driver");
+        cvvp_ctx_destroy(ctx);
+        return CVVP_ERR_CUDA;
+    }
+    ctx->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    *out_ctx = ctx;
+    return CVVP_OK;
+}
+
+void cvvp_ctx_destroy(cvvp_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    DeviceGuard guard(ctx->device);
+    if (ctx->compute)
+        cudaStreamSynchronize(ctx->compute);
+    if (ctx->copy)
+        cudaStreamSynchronize(ctx->copy);
+    for (auto &b : ctx->staging) {
+        if (b.done)
+            cudaEventDestroy(b.done);
+        if (b.host)
+            cudaFreeHost(b.host);
+    }
+    if (ctx->med.d_stack)
+        cudaFree(ctx->med.d_stack);
+    if (ctx->med.d_out)
+        cudaFree(ctx->med.d_out);
+    if (ctx->ev_start)
+        cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop)
+        cudaEventDestroy(ctx->ev_stop);
+    if (ctx->ev_copy)
+        cudaEventDestroy(ctx->ev_copy);
+    if (ctx->compute)
+        cudaStreamDestroy(ctx->compute);
+    if (ctx->copy)
+        cudaStreamDestroy(ctx->copy);
+    cudaGetLastError();
+    delete ctx;
+}
+
+const char *cvvp_last_error(const cvvp_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : global_error();
+}
+
+int cvvp_ctx_synchronize(cvvp_ctx *ctx)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy));
+    CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->compute));
+    for (auto &b : ctx->staging)
+        b.in_flight = false;
+    return CVVP_OK;
+}
+
+void *cvvp_ctx_stream(cvvp_ctx *ctx)
+{
+    return ctx ? static_cast<void *>(ctx->compute) : nullptr;
+}
+
+int cvvp_ctx_device(const cvvp_ctx *ctx)
+{
+    return ctx ? ctx->device : -1;
+}
+
+int cvvp_ctx_sm_count(const cvvp_ctx *ctx)
+{
+    return ctx ? ctx->sm_count : 0;
+}
+
+long long cvvp_ctx_launch_count(const cvvp_ctx *ctx)
+{
+    return ctx ? ctx->launches : 0;
+}
+
+int cvvp_host_alloc(size_t bytes, void **out_ptr)
+{
+    if (!out_ptr || bytes == 0)
+        return fail(nullptr, CVVP_ERR_INVALID, "cvvp_host_alloc: bad arguments");
+    *out_ptr = nullptr;
+    cudaError_t e = cudaMallocHost(out_ptr, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, CVVP_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return CVVP_OK;
+}
+
+int cvvp_host_free(void *ptr)
+{
+    if (!ptr)
+        return CVVP_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, CVVP_ERR_CUDA, "cudaFreeHost failed: %s", cudaGetErrorString(e));
+    }
+    return CVVP_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* median                                                                                      */
+/* ------------------------------------------------------------------------------------------- */
+
+int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    if (ctx->med.active)
+        return fail(ctx, CVVP_ERR_STATE, "median: a job is already running on this context");
+    if (nelem == 0 || nelem >= (1ull << 31))
+        return fail(ctx, CVVP_ERR_INVALID, "median: nelem must be in [1, 2^31)");
+    DeviceGuard guard(ctx->device);
+    MedianJob &m = ctx->med;
+    const size_t stride = round_up(nelem, 128);
+    if (stride != m.stride) {
+        // geometry changed: the old stack cannot be reused as is
+        if (m.d_stack)
+            cudaFree(m.d_stack);
+        m.d_stack = nullptr;
+        m.d_stack_bytes = 0;
+    }
+    m.capacity = 0;
+    m.nelem = nelem;
+    m.stride = stride;
+    m.count = 0;
+    if (m.d_out_bytes < stride) {
+        if (m.d_out)
+            cudaFree(m.d_out);
+        m.d_out = nullptr;
+        m.d_out_bytes = 0;
+        if (cudaMalloc(&m.d_out, stride) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, CVVP_ERR_NOMEM, "median: cudaMalloc of the result buffer failed");
+        }
+        m.d_out_bytes = stride;
+    }
+    if (m.d_stack_bytes >= stride)
+        m.capacity = (long long)(m.d_stack_bytes / stride);
+    const int rc = ensure_stack(ctx, nframes_hint > 0 ? nframes_hint : 64);
+    if (rc != CVVP_OK)
+        return rc;
+    m.active = true;
+    return CVVP_OK;
+}
+
+int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    MedianJob &m = ctx->med;
+    if (!m.active)
+        return fail(ctx, CVVP_ERR_STATE, "median: push without begin");
+    if (n == 0)
+        return CVVP_OK;
+    if (!frames || n < 0 || frame_stride < m.nelem)
+        return fail(ctx, CVVP_ERR_INVALID, "median: bad push arguments");
+    DeviceGuard guard(ctx->device);
+    int rc = ensure_stack(ctx, m.count + n);
+    if (rc != CVVP_OK)
+        return rc;
+    uint8_t *dst = m.d_stack + size_t(m.count) * m.stride;
+    if (is_pinned(frames)) {
+        // DMA straight from the caller's pinned buffer
+        if (frame_stride == m.stride && m.stride == m.nelem) {
+            CVVP_CUDA_OK(ctx, cudaMemcpyAsync(dst, frames, size_t(n) * m.stride, cudaMemcpyHostToDevice, ctx->copy));
+        } else {
+            CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst, m.stride, frames, frame_stride, m.nelem, size_t(n),
+                                                cudaMemcpyHostToDevice, ctx->copy));
+        }
+    } else {
+        // pageable source: stage through the pinned ring, copies overlap the next memcpy
+        rc = ensure_staging(ctx);
+        if (rc != CVVP_OK)
+            return rc;
+        const long long per_buf = (long long)(kStagingBytes / m.nelem);
+        if (per_buf == 0)
+            return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: frame larger than the staging buffer; pass pinned memory");
+        for (long long done = 0; done < n;) {
+            const long long chunk = (n - done) < per_buf ? (n - done) : per_buf;
+            StagingBuf &b = ctx->staging[ctx->staging_next];
+            ctx->staging_next = (ctx->staging_next + 1) % ctx->staging.size();
+            if (b.in_flight) {
+                CVVP_CUDA_OK(ctx, cudaEventSynchronize(b.done));
+                b.in_flight = false;
+            }
+            for (long long i = 0; i < chunk; ++i)
+                std::memcpy(b.host + size_t(i) * m.nelem, frames + size_t(done + i) * frame_stride, m.nelem);
+            CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst + size_t(done) * m.stride, m.stride, b.host, m.nelem, m.nelem,
+                                                size_t(chunk), cudaMemcpyHostToDevice, ctx->copy));
+            CVVP_CUDA_OK(ctx, cudaEventRecord(b.done, ctx->copy));
+            b.in_flight = true;
+            done += chunk;
+        }
+    }
+    m.count += n;
+    return CVVP_OK;
+}
+
+long long cvvp_median_count(const cvvp_ctx *ctx)
+{
+    return ctx ? ctx->med.count : 0;
+}
+
+int cvvp_median_finish(cvvp_ctx *ctx, uint8_t *out)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    MedianJob &m = ctx->med;
+    if (!m.active)
+        return fail(ctx, CVVP_ERR_STATE, "median: finish without begin");
+    if (!out) {
+        release_median(ctx);
+        return fail(ctx, CVVP_ERR_INVALID, "median: out is NULL");
+    }
+    if (m.count == 0) {
+        // the reference publishes an empty Mat when no token was inserted; report it as a state error
+        release_median(ctx);
+        return fail(ctx, CVVP_ERR_STATE, "median: no frames were pushed");
+    }
+    DeviceGuard guard(ctx->device);
+    int rc = CVVP_OK;
+    do {
+        cudaError_t e;
+        if ((e = cudaEventRecord(ctx->ev_copy, ctx->copy)) != cudaSuccess ||
+            (e = cudaStreamWaitEvent(ctx->compute, ctx->ev_copy, 0)) != cudaSuccess ||
+            (e = cudaEventRecord(ctx->ev_start, ctx->compute)) != cudaSuccess) {
+            rc = fail(ctx, CVVP_ERR_CUDA, "median: stream setup failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        rc = median_launch(ctx, m.d_stack, m.count, m.nelem, m.stride, m.d_out, ctx->compute);
+        if (rc != CVVP_OK)
+            break;
+        if ((e = cudaEventRecord(ctx->ev_stop, ctx->compute)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(out, m.d_out, m.nelem, cudaMemcpyDeviceToHost, ctx->compute)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(ctx->compute)) != cudaSuccess) {
+            rc = fail(ctx, CVVP_ERR_CUDA, "median: kernel or result copy failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        ctx->have_kernel_time = true;
+    } while (false);
+    for (auto &b : ctx->staging)
+        b.in_flight = false;
+    release_median(ctx);
+    return rc;
+}
+
+int cvvp_median_abort(cvvp_ctx *ctx)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->copy);
+    for (auto &b : ctx->staging)
+        b.in_flight = false;
+    release_median(ctx);
+    return CVVP_OK;
+}
+
+int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
+                       uint8_t *d_out, void *stream)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->compute;
+    return median_launch(ctx, d_frames, nframes, nelem, frame_stride, d_out, s);
+}
+
+int cvvp_median_last_kernel_ms(cvvp_ctx *ctx, float *out_ms)
+{
+    if (!ctx || !out_ms)
+        return fail(ctx, CVVP_ERR_INVALID, "bad arguments");
+    if (!ctx->have_kernel_time)
+        return fail(ctx, CVVP_ERR_STATE, "no median kernel has been timed on this context");
+    DeviceGuard guard(ctx->device);
+    CVVP_CUDA_OK(ctx, cudaEventElapsedTime(out_ms, ctx->ev_start, ctx->ev_stop));
+    return CVVP_OK;
+}
+
+int cvvp_synth_frames_device(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width, int height, int row0,
+                             int nrows, long long first_frame, long long nframes, uint32_t seed, int ndisks, void *stream)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->compute;
+    return synth_launch(ctx, d_frames, frame_stride, width, height, row0, nrows, first_frame, nframes, seed, ndisks, s);
+}
+
+} // extern "C"

@@ -1,0 +1,101 @@
+// Opaque context behind the C ABI (include/cvvp.h): one CUDA device, its streams/events, the
+// device frame stack of the running median job and the pinned staging ring.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/cvvp.h"
+
+namespace cvvp
+{
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct StagingBuf {
+    uint8_t *host{nullptr};
+    size_t bytes{0};
+    cudaEvent_t done{nullptr};
+    bool in_flight{false};
+};
+
+struct MedianJob {
+    bool active{false};
+    size_t nelem{0};
+    size_t stride{0}; // device frame pitch in bytes (multiple of 128)
+    long long capacity{0};
+    long long count{0};
+    uint8_t *d_stack{nullptr};
+    uint8_t *d_out{nullptr};
+    size_t d_out_bytes{0};
+    size_t d_stack_bytes{0};
+};
+} // namespace cvvp
+
+struct cvvp_ctx {
+    int device{0};
+    int sm_count{0};
+    int cc_major{0};
+    int cc_minor{0};
+    size_t smem_optin{0};
+    cudaStream_t compute{nullptr};
+    cudaStream_t copy{nullptr};
+    cudaEvent_t ev_start{nullptr};
+    cudaEvent_t ev_stop{nullptr};
+    cudaEvent_t ev_copy{nullptr};
+    bool have_kernel_time{false};
+    long long launches{0};
+    std::string err;
+    cvvp::EncodeTiledFn encode_tiled{nullptr};
+    cvvp::MedianJob med;
+    std::vector<cvvp::StagingBuf> staging;
+    size_t staging_next{0};
+};
+
+namespace cvvp
+{
+void set_global_error(const char *fmt, ...);
+const char *global_error();
+
+int fail(cvvp_ctx *ctx, int code, const char *fmt, ...);
+
+#define CVVP_CUDA_OK(ctx, expr)                                                                                       \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+            return ::cvvp::fail((ctx), CVVP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),          \
+                                __FILE__, __LINE__);                                                                   \
+    } while (0)
+
+// RAII device switch: every ABI call makes its context's device current and restores the caller's.
+struct DeviceGuard {
+    int prev{-1};
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess)
+            prev = -1;
+        if (prev != dev)
+            cudaSetDevice(dev);
+        else
+            prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+// median.cu
+int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
+                  uint8_t *d_out, cudaStream_t stream);
+// synth.cu
+int synth_launch(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width, int height, int row0, int nrows,
+                 long long first_frame, long long nframes, uint32_t seed, int ndisks, cudaStream_t stream);
+} // namespace cvvp

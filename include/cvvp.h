@@ -1,0 +1,123 @@
+/*
+ * cvvp.h -- C ABI of libcvvp_cuda.so, the B200 (sm_100a) implementation of CvVidProc's
+ * data-parallel hot path: the per-pixel temporal-median background model and the per-frame
+ * highlight stage.
+ *
+ * Boundary rules
+ *   - plain pointers and sizes only; no C++ types, no exceptions cross this boundary;
+ *   - every function returns 0 on success or a negative cvvp_status; the text of the last
+ *     failure of a context is available from cvvp_last_error(ctx) (ctx == NULL: the last
+ *     failure of a call that had no context, thread-local);
+ *   - the caller owns every host buffer; the library owns device memory, streams, events and
+ *     pinned staging inside the opaque context; a context is bound to ONE CUDA device (one
+ *     process per GPU, as torch.distributed launches them) and is not thread-safe;
+ *   - there is no CPU fallback: every entry point fails with CVVP_ERR_CUDA if no sm_100 device
+ *     is usable.
+ *
+ * Each entry point cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef CVVP_H
+#define CVVP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVVP_ABI_VERSION 1
+
+typedef enum cvvp_status {
+    CVVP_OK = 0,
+    CVVP_ERR_INVALID = -1, /* bad argument / call order                                   */
+    CVVP_ERR_CUDA = -2,    /* CUDA runtime/driver failure (text in cvvp_last_error)       */
+    CVVP_ERR_NOMEM = -3,   /* host or device allocation failed                            */
+    CVVP_ERR_STATE = -4,   /* object is in the wrong state for this call                  */
+    CVVP_ERR_UNSUPPORTED = -5
+} cvvp_status;
+
+typedef struct cvvp_ctx cvvp_ctx;
+
+/* ---------------------------------------------------------------------------------------------
+ * context
+ * ------------------------------------------------------------------------------------------- */
+int cvvp_abi_version(void);
+/* device: CUDA ordinal, or -1 for the current device. */
+int cvvp_ctx_create(int device, cvvp_ctx **out_ctx);
+void cvvp_ctx_destroy(cvvp_ctx *ctx);
+const char *cvvp_last_error(const cvvp_ctx *ctx);
+/* block until all work queued on the context's streams is complete */
+int cvvp_ctx_synchronize(cvvp_ctx *ctx);
+/* the context's compute stream as a cudaStream_t (void* to keep CUDA types out of the ABI) */
+void *cvvp_ctx_stream(cvvp_ctx *ctx);
+int cvvp_ctx_device(const cvvp_ctx *ctx);
+int cvvp_ctx_sm_count(const cvvp_ctx *ctx);
+
+/* pinned (page-locked) host memory for callers that want zero-staging H2D/D2H.
+ * Replaces nothing in the reference (its tokens are pageable cv::Mat); it is the "frames are
+ * batched into pinned buffers" part of BASELINE.json:north_star. */
+int cvvp_host_alloc(size_t bytes, void **out_ptr);
+int cvvp_host_free(void *ptr);
+
+/* ---------------------------------------------------------------------------------------------
+ * temporal median -- replaces HistogramMedianAlgo<T>
+ *   Sources/ProcessorAlgos/histogram_median_algo.h
+ *     Insert :66-87 / ConsumeVector :116-141        -> cvvp_median_push
+ *     NotifyNoMoreTokens :101-108 / MedianFromHistograms :144-193 / TryGetResult :90-98
+ *                                                   -> cvvp_median_finish
+ *   bin-width choice (cv_vid_bg_helpers.cpp:232-253) has no equivalent: the device path is an
+ *   exact rank selection, i.e. the result the reference computes whenever its counters do not
+ *   saturate, which GetVideoBackground's choice guarantees.
+ *
+ * An "element" is one byte of a frame (rows*cols*channels of them, cv_util.cpp:251-254); the
+ * median is taken per element over all pushed frames and is the UPPER median sorted[N/2]
+ * (histogram_median_algo.h:160-166).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Start a median job on frames of `nelem` bytes.  nframes_hint > 0 pre-sizes the device stack
+ * (it grows if more frames are pushed). */
+int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint);
+/* Append n frames from HOST memory; frame i starts at frames + i*frame_stride and holds nelem
+ * contiguous bytes.  The copy is asynchronous when `frames` is pinned (cvvp_host_alloc or
+ * cudaHostRegister'ed); the buffer must then stay valid until cvvp_median_finish or
+ * cvvp_ctx_synchronize returns.  Pageable memory is staged through the context's pinned ring
+ * and may be reused as soon as the call returns. */
+int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride);
+/* Number of frames pushed so far. */
+long long cvvp_median_count(const cvvp_ctx *ctx);
+/* Run the select over everything pushed and copy the nelem result bytes to HOST memory `out`
+ * (synchronous: the result is valid on return).  Ends the job. */
+int cvvp_median_finish(cvvp_ctx *ctx, uint8_t *out);
+/* Drop a job without computing. */
+int cvvp_median_abort(cvvp_ctx *ctx);
+
+/* Device-resident form: d_frames is a DEVICE pointer to nframes frames, frame f at
+ * d_frames + f*frame_stride (frame_stride % 16 == 0 and d_frames 16-byte aligned, the TMA
+ * tensor-map constraints), d_out a DEVICE pointer to nelem bytes.  Runs on `stream`
+ * (a cudaStream_t, NULL = the context's compute stream) and does not synchronize. */
+int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem,
+                       size_t frame_stride, uint8_t *d_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * synthetic input: deterministic integer-hash frames generated directly in
+ * device memory, bit-identical to cvvidproc_b200/synth.py on the host.
+ * frames first_frame .. first_frame+nframes-1 of the stream (seed, K disks) are written to
+ * d_frames + i*frame_stride, rows [row0, row0+nrows) of each (a row band for row-sharded jobs).
+ * ------------------------------------------------------------------------------------------- */
+int cvvp_synth_frames_device(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width,
+                             int height, int row0, int nrows, long long first_frame,
+                             long long nframes, uint32_t seed, int ndisks, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * timing of the last median kernel (CUDA events on the launching stream), for the
+ * print_timing_report equivalent (Sources/AsyncTokens/async_token_process.h:273-414).
+ * ------------------------------------------------------------------------------------------- */
+int cvvp_median_last_kernel_ms(cvvp_ctx *ctx, float *out_ms);
+/* how many kernels of this library the context has launched so far */
+long long cvvp_ctx_launch_count(const cvvp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVVP_H */
