@@ -17,6 +17,7 @@ LIB_PATH = PKG_DIR / "libcvvp_cuda.so"
 HEADER = PKG_DIR.parent / "include" / "cvvp.h"
 
 _lib = None
+BOUND_SYMBOLS: list[str] = []
 
 
 class CvvpError(RuntimeError):
@@ -64,6 +65,8 @@ def load():
         "cvvp_median_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "cvvp_synth_frames_device": (i32, [vp, vp, sz, i32, i32, i32, i32, i64, i64, u32, i32, vp]),
     }
+    global BOUND_SYMBOLS
+    BOUND_SYMBOLS = sorted(sigs)
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -33,8 +33,10 @@ constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32; // + 1 producer warp
 constexpr int kStageBytes = 4096;
 constexpr int kStageWords = kStageBytes / 4;
-constexpr int kMaxStagesPerTile = 48; // planes of one tile: nst * 4 KB
-constexpr int kMinRing = 6;
+constexpr int kMaxStagesPerTile = 40; // planes of one tile: nst * 4 KB
+// The ring must hold at least one stage per consumer warp: warp w waits for stage w of a tile right
+// away, and an mbarrier parity wait is only sound if the previous fill of that slot has completed.
+constexpr int kMinRing = kConsumerWarps;
 constexpr int kJMax = kMaxStagesPerTile / 4;
 
 // In-register transpose of a 32x32 bit matrix: afterwards r[j] bit i == (old r[i]) bit j.

@@ -35,18 +35,40 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
+    uint32_t ok;
     asm volatile("{\n"
                  ".reg .pred P1;\n"
-                 "LAB_WAIT:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-                 "@P1 bra DONE;\n"
-                 "bra LAB_WAIT;\n"
-                 "DONE:\n"
-                 "}" ::"r"(smem_u32(bar)),
-                 "r"(parity)
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, P1;\n"
+                 "}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Wait for the phase with the given parity.  NOTE (parity aliasing): a waiter may only start waiting
+// for fill q of a slot once fill q-1 of that slot has completed, otherwise the test passes early.
+// A watchdog turns any protocol bug into a trap (sticky CUDA error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity))
+        return;
+    const uint64_t t0 = global_timer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > 2000000000ull)
+            __trap();
+    }
 }
 
 // L2 eviction-priority policies (createpolicy.fractional encodings used by cp.async.bulk .L2::cache_hint)

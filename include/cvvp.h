@@ -28,6 +28,12 @@ extern "C" {
 
 #define CVVP_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define CVVP_API __attribute__((visibility("default")))
+#else
+#define CVVP_API
+#endif
+
 typedef enum cvvp_status {
     CVVP_OK = 0,
     CVVP_ERR_INVALID = -1, /* bad argument / call order                                   */
@@ -42,23 +48,23 @@ typedef struct cvvp_ctx cvvp_ctx;
 /* ---------------------------------------------------------------------------------------------
  * context
  * ------------------------------------------------------------------------------------------- */
-int cvvp_abi_version(void);
+CVVP_API int cvvp_abi_version(void);
 /* device: CUDA ordinal, or -1 for the current device. */
-int cvvp_ctx_create(int device, cvvp_ctx **out_ctx);
-void cvvp_ctx_destroy(cvvp_ctx *ctx);
-const char *cvvp_last_error(const cvvp_ctx *ctx);
+CVVP_API int cvvp_ctx_create(int device, cvvp_ctx **out_ctx);
+CVVP_API void cvvp_ctx_destroy(cvvp_ctx *ctx);
+CVVP_API const char *cvvp_last_error(const cvvp_ctx *ctx);
 /* block until all work queued on the context's streams is complete */
-int cvvp_ctx_synchronize(cvvp_ctx *ctx);
+CVVP_API int cvvp_ctx_synchronize(cvvp_ctx *ctx);
 /* the context's compute stream as a cudaStream_t (void* to keep CUDA types out of the ABI) */
-void *cvvp_ctx_stream(cvvp_ctx *ctx);
-int cvvp_ctx_device(const cvvp_ctx *ctx);
-int cvvp_ctx_sm_count(const cvvp_ctx *ctx);
+CVVP_API void *cvvp_ctx_stream(cvvp_ctx *ctx);
+CVVP_API int cvvp_ctx_device(const cvvp_ctx *ctx);
+CVVP_API int cvvp_ctx_sm_count(const cvvp_ctx *ctx);
 
 /* pinned (page-locked) host memory for callers that want zero-staging H2D/D2H.
  * Replaces nothing in the reference (its tokens are pageable cv::Mat); it is the "frames are
  * batched into pinned buffers" part of BASELINE.json:north_star. */
-int cvvp_host_alloc(size_t bytes, void **out_ptr);
-int cvvp_host_free(void *ptr);
+CVVP_API int cvvp_host_alloc(size_t bytes, void **out_ptr);
+CVVP_API int cvvp_host_free(void *ptr);
 
 /* ---------------------------------------------------------------------------------------------
  * temporal median -- replaces HistogramMedianAlgo<T>
@@ -77,26 +83,26 @@ int cvvp_host_free(void *ptr);
 
 /* Start a median job on frames of `nelem` bytes.  nframes_hint > 0 pre-sizes the device stack
  * (it grows if more frames are pushed). */
-int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint);
+CVVP_API int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint);
 /* Append n frames from HOST memory; frame i starts at frames + i*frame_stride and holds nelem
  * contiguous bytes.  The copy is asynchronous when `frames` is pinned (cvvp_host_alloc or
  * cudaHostRegister'ed); the buffer must then stay valid until cvvp_median_finish or
  * cvvp_ctx_synchronize returns.  Pageable memory is staged through the context's pinned ring
  * and may be reused as soon as the call returns. */
-int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride);
+CVVP_API int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride);
 /* Number of frames pushed so far. */
-long long cvvp_median_count(const cvvp_ctx *ctx);
+CVVP_API long long cvvp_median_count(const cvvp_ctx *ctx);
 /* Run the select over everything pushed and copy the nelem result bytes to HOST memory `out`
  * (synchronous: the result is valid on return).  Ends the job. */
-int cvvp_median_finish(cvvp_ctx *ctx, uint8_t *out);
+CVVP_API int cvvp_median_finish(cvvp_ctx *ctx, uint8_t *out);
 /* Drop a job without computing. */
-int cvvp_median_abort(cvvp_ctx *ctx);
+CVVP_API int cvvp_median_abort(cvvp_ctx *ctx);
 
 /* Device-resident form: d_frames is a DEVICE pointer to nframes frames, frame f at
  * d_frames + f*frame_stride (frame_stride % 16 == 0 and d_frames 16-byte aligned, the TMA
  * tensor-map constraints), d_out a DEVICE pointer to nelem bytes.  Runs on `stream`
  * (a cudaStream_t, NULL = the context's compute stream) and does not synchronize. */
-int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem,
+CVVP_API int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem,
                        size_t frame_stride, uint8_t *d_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -105,7 +111,7 @@ int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes
  * frames first_frame .. first_frame+nframes-1 of the stream (seed, K disks) are written to
  * d_frames + i*frame_stride, rows [row0, row0+nrows) of each (a row band for row-sharded jobs).
  * ------------------------------------------------------------------------------------------- */
-int cvvp_synth_frames_device(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width,
+CVVP_API int cvvp_synth_frames_device(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width,
                              int height, int row0, int nrows, long long first_frame,
                              long long nframes, uint32_t seed, int ndisks, void *stream);
 
@@ -113,9 +119,9 @@ int cvvp_synth_frames_device(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stri
  * timing of the last median kernel (CUDA events on the launching stream), for the
  * print_timing_report equivalent (Sources/AsyncTokens/async_token_process.h:273-414).
  * ------------------------------------------------------------------------------------------- */
-int cvvp_median_last_kernel_ms(cvvp_ctx *ctx, float *out_ms);
+CVVP_API int cvvp_median_last_kernel_ms(cvvp_ctx *ctx, float *out_ms);
 /* how many kernels of this library the context has launched so far */
-long long cvvp_ctx_launch_count(const cvvp_ctx *ctx);
+CVVP_API long long cvvp_ctx_launch_count(const cvvp_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -31,8 +31,8 @@ def test_ragged_geometry(gpu_ctx, oracle_median, shape):
     assert np.array_equal(gpu_ctx.median(frames), oracle_median(frames))
 
 
-# every tile variant: P=128 (N<=1536), 64 (<=3072), 32 (<=6144), 16 (<=12288)
-@pytest.mark.parametrize("n", [1536, 1537, 2000, 3072, 3073, 5000, 6145, 9000])
+# every tile variant: P=128 (N<=1280), 64 (<=2560), 32 (<=5120), 16 (<=10240)
+@pytest.mark.parametrize("n", [1280, 1281, 2000, 2560, 2561, 5000, 5121, 9000, 10240])
 def test_large_frame_counts(gpu_ctx, oracle_median, n):
     rng = np.random.default_rng(n)
     frames = _rand(rng, n, 5, 77, 90, 140)
@@ -147,3 +147,15 @@ def test_device_resident_full_size_property(gpu_ctx):
     gpu_ctx.median_device(rev.data_ptr(), n, nelem, nelem, out2.data_ptr())
     gpu_ctx.synchronize()
     assert torch.equal(out, out2)
+
+
+def test_too_many_frames_is_a_loud_error(gpu_ctx):
+    import torch
+    from cvvidproc_b200 import _cabi
+
+    n, nelem = 10241, 256
+    stack = torch.zeros((n, nelem), dtype=torch.uint8, device="cuda:0")
+    out = torch.zeros(nelem, dtype=torch.uint8, device="cuda:0")
+    with pytest.raises(_cabi.CvvpError) as ei:
+        gpu_ctx.median_device(stack.data_ptr(), n, nelem, nelem, out.data_ptr())
+    assert ei.value.code == -5
