@@ -37,7 +37,15 @@ constexpr int kMaxStagesPerTile = 40; // planes of one tile: nst * 4 KB
 // The ring must hold at least one stage per consumer warp: warp w waits for stage w of a tile right
 // away, and an mbarrier parity wait is only sound if the previous fill of that slot has completed.
 constexpr int kMinRing = kConsumerWarps;
-constexpr int kJMax = kMaxStagesPerTile / 4;
+static_assert(kMaxStagesPerTile == 40, "dispatch_jt covers JT = 1..10");
+
+// bitwise select: (a & m) | (b & ~m) as ONE LOP3 (ptxas does not fuse the two-mask C expression)
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
 
 // In-register transpose of a 32x32 bit matrix: afterwards r[j] bit i == (old r[i]) bit j.
 __device__ __forceinline__ void transpose32(uint32_t (&r)[32])
@@ -62,8 +70,8 @@ __device__ __forceinline__ void transpose32(uint32_t (&r)[32])
 #pragma unroll
         for (int i = h; i < h + 4; ++i) {
             const uint32_t a = r[i], b = r[i + 4];
-            r[i] = (a & 0x0F0F0F0Fu) | ((b << 4) & 0xF0F0F0F0u);
-            r[i + 4] = ((a >> 4) & 0x0F0F0F0Fu) | (b & 0xF0F0F0F0u);
+            r[i] = bitsel(a, b << 4, 0x0F0F0F0Fu);
+            r[i + 4] = bitsel(a >> 4, b, 0x0F0F0F0Fu);
         }
     }
 #pragma unroll
@@ -71,22 +79,24 @@ __device__ __forceinline__ void transpose32(uint32_t (&r)[32])
 #pragma unroll
         for (int i = h; i < h + 2; ++i) {
             const uint32_t a = r[i], b = r[i + 2];
-            r[i] = (a & 0x33333333u) | ((b << 2) & 0xCCCCCCCCu);
-            r[i + 2] = ((a >> 2) & 0x33333333u) | (b & 0xCCCCCCCCu);
+            r[i] = bitsel(a, b << 2, 0x33333333u);
+            r[i + 2] = bitsel(a >> 2, b, 0x33333333u);
         }
     }
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
         const uint32_t a = r[i], b = r[i + 1];
-        r[i] = (a & 0x55555555u) | ((b << 1) & 0xAAAAAAAAu);
-        r[i + 1] = ((a >> 1) & 0x55555555u) | (b & 0xAAAAAAAAu);
+        r[i] = bitsel(a, b << 1, 0x55555555u);
+        r[i + 1] = bitsel(a >> 1, b, 0x55555555u);
     }
 }
 
 // LOG2S: log2 of the number of 32-frame sub-blocks one 4 KB stage holds per element.
 //   P (elements per tile)   = 128 >> LOG2S
 //   frame slots per stage   = 32 << LOG2S
-template <int LOG2S>
+// JT   : stages per select thread = ceil(nst / 4), a compile-time constant so that the per-thread
+//        alive[]/plane-word arrays live in registers with no guards.
+template <int LOG2S, int JT>
 __global__ void __launch_bounds__(kThreads, 1)
     median_bitslice_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ out, const uint32_t nelem,
                            const uint32_t nframes, const uint32_t nst, const uint32_t nring, const uint32_t ntiles)
@@ -98,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem);                           // nring x 4 KB
-    const uint32_t nst4 = (nst + 3u) & ~3u; // plane rows are padded to a multiple of 4 stages
+    constexpr uint32_t nst4 = 4u * JT; // plane rows are padded to a multiple of 4 stages
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + size_t(nring) * kStageBytes); // [8][nst4][4][32] words
     uint8_t *outstage = smem + size_t(nring + nst4) * kStageBytes;                 // 128 B
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(outstage + 128);             // nring
@@ -158,8 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t s_elem = 4u * s_c + s_p; // element index inside the tile
     const bool s_writer = (s_g == 0u) && ((s_low3 & (S - 1u)) == 0u);
 
-    const uint32_t J = (nst + 3u) >> 2;
-    const uint32_t plane_stride = nst4 * 128u; // words per bit plane
+    constexpr uint32_t plane_stride = nst4 * 128u; // words per bit plane
     const uint32_t k0 = nframes / 2u + (nst * kSlotsPerStage - nframes); // rank incl. zero pad slots
 
     uint32_t iter = 0; // tiles done by this CTA
@@ -193,11 +202,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ---- select phase: this thread owns stages st = 4*j + g of element s_elem, sub-block s
         {
             const uint32_t *base = planes + s_g * 128u + s_p * 32u + s_col;
-            uint32_t alive[kJMax];
-            uint32_t w[kJMax];
+            uint32_t alive[JT];
+            uint32_t w[JT];
 #pragma unroll
-            for (int j = 0; j < kJMax; ++j)
-                alive[j] = (uint32_t(j) < J && (4u * j + s_g) < nst) ? 0xFFFFFFFFu : 0u;
+            for (int j = 0; j < JT; ++j)
+                alive[j] = (4u * j + s_g) < nst ? 0xFFFFFFFFu : 0u;
             uint32_t k = k0;
             uint32_t med = 0;
 #pragma unroll 1
@@ -205,11 +214,9 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const uint32_t *pb = base + uint32_t(b) * plane_stride;
                 uint32_t cnt = 0;
 #pragma unroll
-                for (int j = 0; j < kJMax; ++j) {
-                    if (uint32_t(j) < J) {
-                        w[j] = pb[j * 512]; // rows >= nst hold garbage; alive[j] == 0 masks them
-                        cnt += __popc(alive[j] & ~w[j]);
-                    }
+                for (int j = 0; j < JT; ++j) {
+                    w[j] = pb[j * 512]; // rows >= nst hold garbage; alive[j] == 0 masks them
+                    cnt += __popc(alive[j] & ~w[j]);
                 }
                 if (LOG2S >= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
                 if (LOG2S >= 2) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
@@ -223,10 +230,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
                 const uint32_t flip = one ? 0u : 0xFFFFFFFFu;
 #pragma unroll
-                for (int j = 0; j < kJMax; ++j) {
-                    if (uint32_t(j) < J)
-                        alive[j] &= (w[j] ^ flip);
-                }
+                for (int j = 0; j < JT; ++j)
+                    alive[j] &= (w[j] ^ flip);
             }
             if (s_writer)
                 outstage[s_elem] = uint8_t(med);
@@ -248,28 +253,50 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
 }
 
-template <int LOG2S>
+template <int LOG2S, int JT>
 int launch_variant(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes,
                    uint32_t nst, cudaStream_t stream)
 {
     constexpr int P = 128 >> LOG2S;
+    constexpr uint32_t nst4 = 4u * JT;
     const uint32_t ntiles = (nelem + P - 1) / P;
     const size_t fixed = 128 + 1024 /*alignment slack*/;
     const size_t avail_stages = (ctx->smem_optin - fixed) / (kStageBytes + 16);
-    const uint32_t nst4 = (nst + 3u) & ~3u;
     if (avail_stages < nst4 + kMinRing)
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: tile does not fit shared memory");
     uint32_t nring = uint32_t(avail_stages - nst4);
     if (nring > 32)
         nring = 32;
     const size_t smem_bytes = size_t(nring + nst4) * kStageBytes + 128 + size_t(nring) * 16;
-    auto kern = median_bitslice_kernel<LOG2S>;
+    auto kern = median_bitslice_kernel<LOG2S, JT>;
     CVVP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
     const uint32_t grid = ntiles < uint32_t(ctx->sm_count) ? ntiles : uint32_t(ctx->sm_count);
     kern<<<grid, kThreads, smem_bytes, stream>>>(tmap, d_out, nelem, nframes, nst, nring, ntiles);
     CVVP_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches++;
     return CVVP_OK;
+}
+
+template <int LOG2S>
+int dispatch_jt(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes, uint32_t nst,
+                cudaStream_t stream)
+{
+    switch ((nst + 3u) / 4u) {
+#define CVVP_JT_CASE(J) \
+    case J: return launch_variant<LOG2S, J>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+        CVVP_JT_CASE(1)
+        CVVP_JT_CASE(2)
+        CVVP_JT_CASE(3)
+        CVVP_JT_CASE(4)
+        CVVP_JT_CASE(5)
+        CVVP_JT_CASE(6)
+        CVVP_JT_CASE(7)
+        CVVP_JT_CASE(8)
+        CVVP_JT_CASE(9)
+        CVVP_JT_CASE(10)
+#undef CVVP_JT_CASE
+    default: return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: unsupported stage count %u", nst);
+    }
 }
 } // namespace
 
@@ -312,10 +339,10 @@ int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, siz
         return fail(ctx, CVVP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(cr));
 
     switch (log2s) {
-    case 0: return launch_variant<0>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
-    case 1: return launch_variant<1>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
-    case 2: return launch_variant<2>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
-    default: return launch_variant<3>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
+    case 0: return dispatch_jt<0>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
+    case 1: return dispatch_jt<1>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
+    case 2: return dispatch_jt<2>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
+    default: return dispatch_jt<3>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
     }
 }
 } // namespace cvvp
