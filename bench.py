@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json): temporal-median background over a uint8 frame stack.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                           # the reference's CPU path
+
+One "step" = one pass of the hot path over one batch = the median of the whole synthetic
+1920x1080 x 1000-frame stack (BASELINE.json configs[1]; SURVEY.md 8d seeds).  `value` is
+megapixel-frames/s with the stack already resident in HBM (CUDA events on the launching stream,
+max over ranks); `e2e` is the same metric through the C ABI's host-buffer interface
+(cvvp_median_begin/push/finish) with the frames in pinned host memory, H2D and D2H inside the
+timed region.  The stack (2.07 GB per GPU) is ~16x larger than L2, so no L2 flush is needed
+between timed iterations.
+
+N > 1 (one process per GPU under torchrun): see shard_plan() -- the work is partitioned with no
+collective on the data path; the result bands are gathered with one NCCL all_gather per step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+WORKLOAD = dict(name="C2: 1920x1080 uint8 x 1000 frames, temporal median (BASELINE.json configs[1])",
+                width=1920, height=1080, nframes=1000, seed=2, ndisks=30)
+METRIC = "megapixel-frames/sec (temporal-median background, 1080p x 1000-frame stack)"
+UNIT = "Mpx-frames/s"
+FALLBACK_HBM_GBS = 6650.0
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per launch of the median kernel from the committed ncu --set full capture."""
+    p = REPO / "profiles" / "median_ncu_summary.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+        except Exception:
+            pass
+    return None
+
+
+class ClockSampler:
+    """Polls NVML for SM clock and throttle reasons while a timed region is active."""
+
+    def __init__(self, device_index: int):
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.active = False
+        self._stop = False
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = None
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            except Exception:
+                pass
+            self.h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        self.h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        try:
+                            self.h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                            break
+                        except Exception:
+                            continue
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    _REASONS = {
+        "hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+        "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2,
+        "display_clock_setting": 0x100,
+    }
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop:
+            if self.active:
+                try:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.samples.append(mhz)
+                    for name, bit in self._REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv is None:
+            return
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop = True
+        if self._thread:
+            self._thread.join(timeout=1.0)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def shard_plan(height: int, rank: int, world: int):
+    """Row-band partition (the reference's own spatial sharding, cv_vid_frames_generator_algo.h:159-164, with
+    horizontal bands instead of vertical strips so that every band is contiguous in memory).  The median is
+    element-wise, so bands are independent: no collective on the data path."""
+    base = height // world
+    row0 = base * rank
+    nrows = base if rank < world - 1 else height - row0
+    return row0, nrows
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (reference implementation timed on host cores)
+# ------------------------------------------------------------------------------------------------
+def cpu_median_fn():
+    """oracle/_ref (the reference's own class, kind='reference') when it was built, else the C port."""
+    ref = REPO / "oracle" / "_ref" / "libcvvp_median_ref.so"
+    port = REPO / "oracle" / "_build" / "libcvvp_oracle.so"
+    if ref.exists():
+        lib, name, kind = ctypes.CDLL(str(ref)), "cvvp_ref_median", "reference"
+    elif port.exists():
+        lib, name, kind = ctypes.CDLL(str(port)), "cvvp_oracle_median", "port"
+    else:
+        raise RuntimeError("neither oracle/_ref nor oracle/_build is built; run __graft_entry__.build()")
+    fn = getattr(lib, name)
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                   ctypes.c_void_p]
+    fn.restype = ctypes.c_int
+
+    def run(frames: np.ndarray, nthreads: int) -> np.ndarray:
+        n = frames.shape[0]
+        nelem = int(np.prod(frames.shape[1:]))
+        out = np.empty(nelem, np.uint8)
+        rc = fn(frames.ctypes.data, n, nelem, frames.strides[0], 0, nthreads, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"{name} failed: {rc}")
+        return out
+
+    return run, kind
+
+
+def host_sample_frames(rows: int) -> np.ndarray:
+    """Rows [0, rows) of every frame of the workload, generated on the host (cvvidproc_b200/synth.py)."""
+    from cvvidproc_b200 import synth
+
+    w = WORKLOAD
+    return synth.synth_frames(0, w["nframes"], w["width"], w["height"], w["seed"], w["ndisks"], row0=0, nrows=rows)
+
+
+def run_reference_arm(args, rank: int, world: int):
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    w = WORKLOAD
+    cores = os.cpu_count() or 1
+    run, kind = cpu_median_fn()
+    # bounded sample: a band of rows of the SAME stack (all 1000 frames), sized from a calibration band so that
+    # the whole run stays within ~2.5 minutes
+    calib_rows = 8
+    frames = host_sample_frames(calib_rows)
+    t0 = time.perf_counter()
+    run(frames, cores)
+    t_cal = max(time.perf_counter() - t0, 1e-4)
+    per_row = t_cal / calib_rows
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    rows = int(min(w["height"], max(calib_rows, budget / per_row)))
+    rows = min(rows, 270)  # generation of the sample on the host is itself ~0.1 s per row
+    frames = host_sample_frames(rows)
+    for _ in range(args.warmup):
+        run(frames, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(frames, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    mpxf = rows * w["width"] * w["nframes"] / 1e6
+    value = mpxf / dt
+    sample = f"rows [0,{rows}) of all {w['nframes']} frames ({mpxf:.1f} Mpx-frames per step)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": w["name"], "width": w["width"], "height": w["height"], "nframes": w["nframes"],
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, rank: int, local_rank: int, world: int):
+    import torch
+
+    from cvvidproc_b200 import _cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = WORKLOAD
+    W, H, N = w["width"], w["height"], w["nframes"]
+    row0, nrows = shard_plan(H, rank, world)
+    nelem = nrows * W
+    stride = (nelem + 127) // 128 * 128
+    ctx = _cabi.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    # resident input: this rank's band of every frame, generated on the device
+    stack = torch.empty((N, stride), dtype=torch.uint8, device=f"cuda:{local_rank}")
+    out = torch.empty(stride, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    ctx.synth_frames_device(stack.data_ptr(), stride, W, H, 0, N, w["seed"], w["ndisks"], row0=row0, nrows=nrows)
+    ctx.synchronize()
+    gathered = None
+    if world > 1:
+        band_max = (H - (H // world) * (world - 1)) * W
+        out_pad = torch.zeros(band_max, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        gathered = torch.empty(world * band_max, dtype=torch.uint8, device=f"cuda:{local_rank}")
+
+    def step():
+        ctx.median_device(stack.data_ptr(), N, nelem, stride, out.data_ptr())
+        if world > 1:
+            out_pad[:nelem].copy_(out[:nelem], non_blocking=True)
+            dist.all_gather_into_tensor(gathered, out_pad)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        launches0 = ctx.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kern_evs = []
+        sampler.active = True
+        ev0.record(stream)
+        for _ in range(args.steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            ctx.median_device(stack.data_ptr(), N, nelem, stride, out.data_ptr())
+            b.record(stream)
+            kern_evs.append((a, b))
+            if world > 1:
+                out_pad[:nelem].copy_(out[:nelem], non_blocking=True)
+                dist.all_gather_into_tensor(gathered, out_pad)
+        ev1.record(stream)
+        barrier()
+        sampler.active = False
+        launches = ctx.launch_count - launches0
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_evs]))
+    t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms_max = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    job_mpxf = W * H * N / 1e6  # whole job, all ranks
+    value = job_mpxf / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI: pinned host frames -> result in host memory
+    pinned = _cabi.PinnedBuffer(N * nelem)
+    host_frames = pinned.array.reshape(N, nelem)
+    chunk = 50
+    for i in range(0, N, chunk):  # fill the pinned buffer once (outside every timed region)
+        host_frames[i : i + chunk] = stack[i : i + chunk, :nelem].cpu().numpy()
+    host_out = np.empty(nelem, np.uint8)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        ctx.median_begin(nelem, N)
+        for i in range(0, N, 125):
+            ctx.median_push_raw(host_frames[i].ctypes.data, min(125, N - i), nelem)
+        ctx.median_finish(host_out)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    sampler.active = True
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    sampler.active = False
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    e2e_value = job_mpxf / e2e_s
+    sampler.stop()
+    clocks = sampler.summary()
+    # parity spot check of what was timed (cheap, outside the timed regions): e2e result == resident result
+    same = bool(np.array_equal(host_out, out[:nelem].cpu().numpy()))
+
+    # ---- roofline of the dominant (only) kernel
+    peak, peak_src = load_peaks()
+    algo_bytes = float(N) * nelem + nelem  # bytes one launch must move: every input byte once + the result
+    achieved = algo_bytes / (kern_ms_max * 1e-3) / 1e9
+    traffic = load_traffic() if world == 1 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "median_bitslice_kernel",
+                "kernel_ms": kern_ms_max, "algorithmic_bytes_per_launch": algo_bytes}
+
+    # ---- CPU baseline on rank 0 at N=1 only (bounded sample; reported, not the target)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            run, kind = cpu_median_fn()
+            cores = os.cpu_count() or 1
+            rows = 120
+            sample_frames = np.ascontiguousarray(host_frames[:, : rows * W]).reshape(N, rows, W)
+            want = run(sample_frames, cores)  # warm-up + parity of the sample against the GPU result
+            same = same and bool(np.array_equal(want, host_out[: rows * W]))
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                run(sample_frames, cores)
+            dt = (time.perf_counter() - t0) / reps
+            cpu_baseline = {"value": rows * W * N / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                            "sample": f"rows [0,{rows}) of all {N} frames, {reps} repetitions, all host threads"}
+        except Exception as exc:  # the baseline must never take the GPU number down with it
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "unavailable",
+                            "sample": f"failed: {exc}"}
+    pinned.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": w["name"], "width": W, "height": H, "nframes": N, "seed": w["seed"],
+                       "ndisks": w["ndisks"], "sharding": "single GPU" if world == 1 else f"row bands x{world}, no data-path collective",
+                       "l2": "input stack (2.07 GB / n_gpus) exceeds the 126 MB L2; no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(N * nelem),
+                    "d2h_bytes_per_step": int(nelem), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "parity_spot_check": same,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "cuda":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        print(f"bench.py: --gpus {args.gpus} needs torchrun (one process per GPU); running the single-GPU job",
+              file=sys.stderr)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+    else:
+        run_gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
