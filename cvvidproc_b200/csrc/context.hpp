@@ -95,6 +95,10 @@ struct DeviceGuard {
 // median.cu
 int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
                   uint8_t *d_out, cudaStream_t stream);
+// median_pipe.cu
+long long median_pipe_max_frames();
+int median_pipe_launch(cvvp_ctx *ctx, const CUtensorMap &tmap, int log2s, uint8_t *d_out, uint32_t nelem, uint32_t nframes,
+                       uint32_t nst, cudaStream_t stream);
 // synth.cu
 int synth_launch(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width, int height, int row0, int nrows,
                  long long first_frame, long long nframes, uint32_t seed, int ndisks, cudaStream_t stream);

@@ -22,7 +22,10 @@
 // frames are accounted for by raising the wanted rank by the number of pad slots, so no masks
 // are needed.  HBM traffic is the algorithmic minimum: every input byte is read exactly once.
 #include "context.hpp"
+
+#include <cstdlib>
 #include "ptx_helpers.cuh"
+#include "median_common.cuh"
 
 namespace cvvp
 {
@@ -34,62 +37,10 @@ constexpr int kThreads = kConsumerThreads + 32; // + 1 producer warp
 constexpr int kStageBytes = 4096;
 constexpr int kStageWords = kStageBytes / 4;
 constexpr int kMaxStagesPerTile = 40; // planes of one tile: nst * 4 KB
-// The ring must hold at least one stage per consumer warp: warp w waits for stage w of a tile right
-// away, and an mbarrier parity wait is only sound if the previous fill of that slot has completed.
+// An mbarrier parity wait is only sound if the previous fill of that slot has completed, so every ring slot is
+// private to one consumer warp (1 or 2 slots per warp).
 constexpr int kMinRing = kConsumerWarps;
 static_assert(kMaxStagesPerTile == 40, "dispatch_jt covers JT = 1..10");
-
-// bitwise select: (a & m) | (b & ~m) as ONE LOP3 (ptxas does not fuse the two-mask C expression)
-__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m)
-{
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
-    return d;
-}
-
-// In-register transpose of a 32x32 bit matrix: afterwards r[j] bit i == (old r[i]) bit j.
-__device__ __forceinline__ void transpose32(uint32_t (&r)[32])
-{
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const uint32_t a = r[i], b = r[i + 16];
-        r[i] = __byte_perm(a, b, 0x5410);
-        r[i + 16] = __byte_perm(a, b, 0x7632);
-    }
-#pragma unroll
-    for (int h = 0; h < 32; h += 16) {
-#pragma unroll
-        for (int i = h; i < h + 8; ++i) {
-            const uint32_t a = r[i], b = r[i + 8];
-            r[i] = __byte_perm(a, b, 0x6240);
-            r[i + 8] = __byte_perm(a, b, 0x7351);
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < 32; h += 8) {
-#pragma unroll
-        for (int i = h; i < h + 4; ++i) {
-            const uint32_t a = r[i], b = r[i + 4];
-            r[i] = bitsel(a, b << 4, 0x0F0F0F0Fu);
-            r[i + 4] = bitsel(a >> 4, b, 0x0F0F0F0Fu);
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < 32; h += 4) {
-#pragma unroll
-        for (int i = h; i < h + 2; ++i) {
-            const uint32_t a = r[i], b = r[i + 2];
-            r[i] = bitsel(a, b << 2, 0x33333333u);
-            r[i + 2] = bitsel(a >> 2, b, 0x33333333u);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-        const uint32_t a = r[i], b = r[i + 1];
-        r[i] = bitsel(a, b << 1, 0x55555555u);
-        r[i + 1] = bitsel(a >> 1, b, 0x55555555u);
-    }
-}
 
 // LOG2S: log2 of the number of 32-frame sub-blocks one 4 KB stage holds per element.
 //   P (elements per tile)   = 128 >> LOG2S
@@ -132,18 +83,31 @@ __global__ void __launch_bounds__(kThreads, 1)
         // ===== TMA producer: one thread, runs ahead of the consumers by up to nring stages,
         // including across tile boundaries (the next tile streams in during the select phase).
         if (lane == 0) {
-            uint32_t slot = 0, phase = 0;
+            // each consumer warp owns R = nring/16 PRIVATE ring slots (slot = w + 16*(k % R) for its k-th stage):
+            // TMA completions are unordered across slots, so a slot shared between warps could alias a parity wait
+            const uint32_t R = nring / kConsumerWarps;
+            uint32_t seq[kConsumerWarps];
+#pragma unroll
+            for (int i = 0; i < kConsumerWarps; ++i)
+                seq[i] = 0;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int32_t x = int32_t(tile * P);
                 for (uint32_t st = 0; st < nst; ++st) {
-                    mbar_wait(&empty_bar[slot], phase ^ 1u);
+                    const uint32_t w = st % kConsumerWarps;
+                    uint32_t k = 0;
+#pragma unroll
+                    for (int i = 0; i < kConsumerWarps; ++i) {
+                        if (uint32_t(i) == w) {
+                            k = seq[i];
+                            seq[i] = k + 1;
+                        }
+                    }
+                    const uint32_t slot = w + kConsumerWarps * (k % R);
+                    const uint32_t fill = k / R;
+                    mbar_wait(&empty_bar[slot], (fill & 1u) ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[slot], kStageBytes);
                     tma_load_2d(ring + size_t(slot) * kStageWords, &tmap, &full_bar[slot], x,
                                 int32_t(st * kSlotsPerStage), kL2EvictFirst);
-                    if (++slot == nring) {
-                        slot = 0;
-                        phase ^= 1u;
-                    }
                 }
             }
         }
@@ -171,13 +135,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     constexpr uint32_t plane_stride = nst4 * 128u; // words per bit plane
     const uint32_t k0 = nframes / 2u + (nst * kSlotsPerStage - nframes); // rank incl. zero pad slots
 
-    uint32_t iter = 0; // tiles done by this CTA
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+    const uint32_t R = nring / kConsumerWarps;
+    uint32_t kseq = 0; // stages consumed by this warp
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- transpose phase: warp w takes stages w, w+16, ...
-        for (uint32_t st = warp; st < nst; st += kConsumerWarps) {
-            const uint32_t it = iter * nst + st;
-            const uint32_t slot = it % nring;
-            const uint32_t phase = (it / nring) & 1u;
+        for (uint32_t st = warp; st < nst; st += kConsumerWarps, ++kseq) {
+            const uint32_t slot = warp + kConsumerWarps * (kseq % R);
+            const uint32_t phase = (kseq / R) & 1u;
             mbar_wait(&full_bar[slot], phase);
             const uint32_t *src = ring + size_t(slot) * kStageWords + lane;
             uint32_t r[32];
@@ -264,9 +228,8 @@ int launch_variant(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint3
     const size_t avail_stages = (ctx->smem_optin - fixed) / (kStageBytes + 16);
     if (avail_stages < nst4 + kMinRing)
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: tile does not fit shared memory");
-    uint32_t nring = uint32_t(avail_stages - nst4);
-    if (nring > 32)
-        nring = 32;
+    // a multiple of the consumer-warp count: every ring slot is private to one warp
+    const uint32_t nring = (avail_stages - nst4) >= 2u * kConsumerWarps ? 2u * kConsumerWarps : uint32_t(kConsumerWarps);
     const size_t smem_bytes = size_t(nring + nst4) * kStageBytes + 128 + size_t(nring) * 16;
     auto kern = median_bitslice_kernel<LOG2S, JT>;
     CVVP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
@@ -298,6 +261,12 @@ int dispatch_jt(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t
     default: return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: unsupported stage count %u", nst);
     }
 }
+bool force_single_buffer()
+{
+    // development switch: CVVP_MEDIAN_KERNEL=single forces the single-buffer kernel for every frame count
+    const char *e = getenv("CVVP_MEDIAN_KERNEL");
+    return e && e[0] == 's';
+}
 } // namespace
 
 int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
@@ -311,13 +280,16 @@ int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, siz
     if (nelem >= (1ull << 31) || nframes >= (1ll << 31))
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: stack dimensions exceed the tensor-map limits");
 
-    // smallest LOG2S (widest tile) whose planes fit on chip
+    // smallest LOG2S (widest tile) whose planes fit on chip; the pipelined kernel (double-buffered planes,
+    // <= 16 stages per tile) is preferred, the single-buffer kernel takes the larger frame counts
+    const bool pipelined = nframes <= median_pipe_max_frames() && !force_single_buffer();
+    const long long max_stages = pipelined ? 16 : kMaxStagesPerTile;
     int log2s = -1;
     uint32_t nst = 0;
     for (int l = 0; l <= 3; ++l) {
         const long long slots = 32ll << l;
         const long long need = (nframes + slots - 1) / slots;
-        if (need <= kMaxStagesPerTile) {
+        if (need <= max_stages) {
             log2s = l;
             nst = uint32_t(need);
             break;
@@ -338,6 +310,8 @@ int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, siz
     if (cr != CUDA_SUCCESS)
         return fail(ctx, CVVP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(cr));
 
+    if (pipelined)
+        return median_pipe_launch(ctx, tmap, log2s, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
     switch (log2s) {
     case 0: return dispatch_jt<0>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
     case 1: return dispatch_jt<1>(ctx, tmap, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);

@@ -1,0 +1,58 @@
+// Shared device helpers of the median kernels: single-LOP3 bit select and the in-register 32x32 bit transpose.
+#pragma once
+#include <cstdint>
+
+namespace cvvp
+{
+// bitwise select: (a & m) | (b & ~m) as ONE LOP3 (ptxas does not fuse the two-mask C expression)
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+
+// In-register transpose of a 32x32 bit matrix: afterwards r[j] bit i == (old r[i]) bit j.
+__device__ __forceinline__ void transpose32(uint32_t (&r)[32])
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t a = r[i], b = r[i + 16];
+        r[i] = __byte_perm(a, b, 0x5410);
+        r[i + 16] = __byte_perm(a, b, 0x7632);
+    }
+#pragma unroll
+    for (int h = 0; h < 32; h += 16) {
+#pragma unroll
+        for (int i = h; i < h + 8; ++i) {
+            const uint32_t a = r[i], b = r[i + 8];
+            r[i] = __byte_perm(a, b, 0x6240);
+            r[i + 8] = __byte_perm(a, b, 0x7351);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 32; h += 8) {
+#pragma unroll
+        for (int i = h; i < h + 4; ++i) {
+            const uint32_t a = r[i], b = r[i + 4];
+            r[i] = bitsel(a, b << 4, 0x0F0F0F0Fu);
+            r[i + 4] = bitsel(a >> 4, b, 0x0F0F0F0Fu);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 32; h += 4) {
+#pragma unroll
+        for (int i = h; i < h + 2; ++i) {
+            const uint32_t a = r[i], b = r[i + 2];
+            r[i] = bitsel(a, b << 2, 0x33333333u);
+            r[i + 2] = bitsel(a >> 2, b, 0x33333333u);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        const uint32_t a = r[i], b = r[i + 1];
+        r[i] = bitsel(a, b << 1, 0x55555555u);
+        r[i + 1] = bitsel(a >> 1, b, 0x55555555u);
+    }
+}
+} // namespace cvvp

@@ -74,6 +74,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // L2 eviction-priority policies (createpolicy.fractional encodings used by cp.async.bulk .L2::cache_hint)
 constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
 
 // 2-D tiled TMA load global -> shared, completion signalled on an mbarrier (complete_tx::bytes).
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, uint64_t *bar, int32_t x, int32_t y,
