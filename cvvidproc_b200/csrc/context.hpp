@@ -96,7 +96,7 @@ struct DeviceGuard {
 int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
                   uint8_t *d_out, cudaStream_t stream);
 // median_pipe.cu
-long long median_pipe_max_frames();
+long long median_max_frames();
 int median_pipe_launch(cvvp_ctx *ctx, const CUtensorMap &tmap, int log2s, uint8_t *d_out, uint32_t nelem, uint32_t nframes,
                        uint32_t nst, cudaStream_t stream);
 // synth.cu

@@ -1,26 +1,37 @@
-// Pipelined temporal-median kernel (the fast path for N <= 4096 frames) -- same bit-sliced radix select as
-// median.cu, restructured so that HBM streaming, bit transposition and rank selection all run concurrently on
-// every SM instead of in alternating phases:
+// Temporal-median kernel: on-chip bit-sliced radix select with warp-specialised streaming.
+// (Algorithm and reference citations: see median.cu.)
 //
-//   warp  0..7   SELECT     (256 threads: 4..32 threads per element) -- tile t   , plane buffer t & 1
-//   warp  8..19  TRANSPOSE  (12 warps, one 4 KB stage at a time)     -- tile t+1 , plane buffer (t+1) & 1
-//   warp  20     PRODUCER   (one thread issuing TMA boxes, up to 24 stages ahead, across tiles)
+//   SELECT warps     (8 or 16)  tile t      : 8 MSB-first passes of popc over bit planes held in shared memory
+//   TRANSPOSE warps  (12)       tile t+1    : wait for a 4 KB TMA stage, 32x32 bit-transpose it in registers, store
+//                                             the planes, and immediately RE-ISSUE the TMA load of their own next
+//                                             stage into the slot they just drained
 //
-// Shared memory: 24-stage TMA ring (96 KB) + 2 plane buffers of up to 16 stages (2 x 64 KB).
+// There is no producer warp: a single thread issuing every TMA box costs ~290 cycles per stage (dependent
+// try_wait -> expect_tx -> issue chain) and caps the whole chip near 4 TB/s.  With 12 self-service warps the issue
+// work is spread out and the ring needs no "empty" barriers at all: each transposer warp owns two PRIVATE slots
+// (stage g of the CTA's global stage sequence goes to warp g % 12, slot g % 24), refills a slot only after its own
+// lanes have read it, and therefore always waits for the direct successor of a fill it consumed itself -- the
+// condition under which an mbarrier parity wait cannot alias (TMA completions are unordered across slots).
 //
-// Synchronisation is all mbarrier based and every parity wait is provably at most one phase away:
-//   * each transposer warp owns two PRIVATE ring slots (slot = warp + 12*(k&1) for its k-th stage), so the fill it
-//     waits for is always the direct successor of a fill it consumed itself (TMA completions are unordered across
-//     slots, which makes shared slots unsafe);
-//   * every transposer warp and every select warp walks through EVERY tile of its CTA in order (warps without a
-//     stage in a tile still do the buffer handshake), so planes_full/planes_empty waits are one phase away by
-//     induction.
+// Two buffering modes, chosen by the stage count per tile (nst):
+//   nst <= 16 : two plane buffers, 8 select warps  (stages split by parity, JT = ceil(nst/2) <= 8 per thread)
+//   nst <= 32 : one plane buffer, 16 select warps  (stages split mod 4,      JT = ceil(nst/4) <= 8 per thread);
+//               the buffer is released as soon as the low-nibble planes are in registers, so the last four
+//               passes overlap the next tile's transposition; the 24 ring slots keep HBM streaming meanwhile.
 //
-// Plane layout per buffer: [stage][byte p][nibble bh][column phi][4 words = bits 4bh..4bh+3], so a transposer lane
-// stores uint4 and a select thread loads the four planes of a nibble with one LDS.128.  phi = (transposer lane id)
-// ^ (stage & 1): the select thread that owns stages of parity g for logical lane L reads column L ^ g, which equals
-// (its own lane id) ^ (warp & 1).  Both patterns touch 8 distinct 16-byte columns per quarter-warp: conflict free.
+// Plane layout per buffer: [stage][byte p][nibble bh][column phi][4 words = bits 4bh..4bh+3]: a transposer lane
+// stores uint4, a select thread loads the four planes of a nibble with one LDS.128.  phi = lane ^ (stage % G)
+// (G = 2 or 4 stage classes); the select thread for logical lane L and stage class g reads column L ^ g, which is
+// its own lane id ^ (low column bits held in its warp id).  Both patterns touch 8 distinct 16-byte columns per
+// quarter-warp: bank-conflict free.
+//
+// Selectors walk through every tile in order, so their planes_full waits are one phase away by induction.  A
+// transposer can reach a buffer two fills ahead when tiles are tiny, so before its planes_empty parity wait it
+// checks a monotonic shared counter of completed selects; after that the parity wait is at most one phase away.
 #include "context.hpp"
+
+#include <cstdlib>
+
 #include "median_common.cuh"
 #include "ptx_helpers.cuh"
 
@@ -28,36 +39,37 @@ namespace cvvp
 {
 namespace
 {
-constexpr int kSelWarps = 8;
 constexpr int kTrWarps = 12;
-constexpr int kSelThreads = kSelWarps * 32;
-constexpr int kPipeThreads = (kSelWarps + kTrWarps + 1) * 32;
 constexpr int kStageBytes = 4096;
 constexpr int kStageWords = kStageBytes / 4;
 constexpr int kRing = 2 * kTrWarps; // two private slots per transposer warp
-constexpr int kMaxStages = 16;      // stages per tile (per plane buffer)
 
-// LOG2S: log2(32-frame sub-blocks per stage per element); P = 128 >> LOG2S elements per tile, 32 << LOG2S frame
-//        slots per stage.   JT: stages per select thread = ceil(nst / 2) (compile time).
-template <int LOG2S, int JT>
-__global__ void __launch_bounds__(kPipeThreads, 1)
+// LOG2S : log2(32-frame sub-blocks per stage per element); P = 128 >> LOG2S elements per tile
+// JT    : stages per select thread (compile time)
+// NSELW : select warps, 8 (two stage classes, two plane buffers) or 16 (four stage classes, one plane buffer)
+template <int LOG2S, int JT, int NSELW>
+__global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     median_pipe_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ out, const uint32_t nelem,
                        const uint32_t nframes, const uint32_t nst, const uint32_t ntiles, const uint64_t l2_policy)
 {
     constexpr int S = 1 << LOG2S;
     constexpr int P = 128 >> LOG2S;
     constexpr int kSlotsPerStage = 32 * S;
-    constexpr int kColBits = 5 - LOG2S;             // word-column bits of a transposer lane id (the rest: sub-block)
-    constexpr uint32_t kBufWords = 2u * JT * 1024u; // one plane buffer: 2*JT stages x 4 KB
+    constexpr int kColBits = 5 - LOG2S;            // word-column bits of a transposer lane id (the rest: sub-block)
+    constexpr uint32_t G = NSELW / 4;              // stage classes (st % G) = select threads per (element, sub-block)
+    constexpr uint32_t NBUF = (NSELW == 8) ? 2 : 1;
+    constexpr uint32_t kBufWords = G * JT * 1024u; // one plane buffer: G*JT stages x 4 KB
+    static_assert(G == 2 || G == 4, "8 or 16 select warps");
+    static_assert((1 << kColBits) >= int(G), "stage classes are encoded in the low column bits");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem);                         // kRing x 4 KB
-    uint32_t *planes = reinterpret_cast<uint32_t *>(smem + kRing * kStageBytes); // 2 buffers
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRing * kStageBytes + 2u * kBufWords * 4u);
-    uint64_t *ring_full = bars;
-    uint64_t *ring_empty = bars + kRing;
-    uint64_t *planes_full = bars + 2 * kRing;
-    uint64_t *planes_empty = planes_full + 2;
+    uint32_t *planes = reinterpret_cast<uint32_t *>(smem + kRing * kStageBytes); // NBUF buffers
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRing * kStageBytes + NBUF * kBufWords * 4u);
+    uint64_t *ring_full = bars;                // [kRing]
+    uint64_t *planes_full = bars + kRing;      // [2]
+    uint64_t *planes_empty = bars + kRing + 2; // [2]
+    volatile uint32_t *sel_done = reinterpret_cast<volatile uint32_t *>(bars + kRing + 4); // [2] selects completed
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
@@ -65,124 +77,115 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 
     if (tid == 0) {
         prefetch_tmap(&tmap);
-        for (int i = 0; i < kRing; ++i) {
+        for (int i = 0; i < kRing; ++i)
             mbar_init(&ring_full[i], 1);
-            mbar_init(&ring_empty[i], 1);
-        }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&planes_full[i], kTrWarps);
-            mbar_init(&planes_empty[i], kSelWarps);
+            mbar_init(&planes_full[i], nst); // one arrival per transposed stage
+            mbar_init(&planes_empty[i], NSELW);
+            sel_done[i] = 0;
         }
         fence_mbar_init();
     }
     __syncthreads();
 
-    // tiles of this CTA: adjacent tile PAIRS (2m, 2m+1), so that for P < 128 both halves of a 128-byte line are
-    // requested by the same SM back to back (the second one hits L2)
-    const uint32_t npairs = (ntiles + 1) / 2;
-    const uint32_t my_pairs = blockIdx.x < npairs ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t my_tiles = 2 * my_pairs; // the odd tail tile (>= ntiles) is skipped below
-    auto tile_of = [&](uint32_t it) { return 2u * (blockIdx.x + (it >> 1) * gridDim.x) + (it & 1u); };
+    // tiles of this CTA, in the order every role walks them
+    const uint32_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp == kSelWarps + kTrWarps) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t seq[kTrWarps]; // stages issued so far per transposer warp
-#pragma unroll
-            for (int i = 0; i < kTrWarps; ++i)
-                seq[i] = 0;
-            for (uint32_t it = 0; it < my_tiles; ++it) {
-                const uint32_t tile = tile_of(it);
-                if (tile >= ntiles)
-                    continue;
-                const int32_t x = int32_t(tile * P);
-                for (uint32_t st = 0; st < nst; ++st) {
-                    const uint32_t w = st % kTrWarps;
-                    uint32_t k = 0;
-#pragma unroll
-                    for (int i = 0; i < kTrWarps; ++i) { // register array with a dynamic index: select by compare
-                        if (uint32_t(i) == w) {
-                            k = seq[i];
-                            seq[i] = k + 1;
-                        }
-                    }
-                    const uint32_t slot = w + kTrWarps * (k & 1u);
-                    const uint32_t fill = k >> 1;
-                    mbar_wait(&ring_empty[slot], (fill & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&ring_full[slot], kStageBytes);
-                    tma_load_2d(ring + size_t(slot) * kStageWords, &tmap, &ring_full[slot], x,
-                                int32_t(st * kSlotsPerStage), l2_policy);
-                }
+    if (warp >= NSELW) {
+        // ===================== transposers (self-service TMA) =====================
+        const uint32_t w = warp - NSELW;
+        const uint32_t total_stages = my_tiles * nst; // global stage sequence of this CTA
+        // issue the TMA load of the stage at (tile iteration t, stage s) into this warp's slot for its k-th stage
+        auto issue = [&](uint32_t k, uint32_t t, uint32_t s) {
+            const uint32_t slot = w + kTrWarps * (k & 1u);
+            const uint32_t tile = blockIdx.x + t * gridDim.x;
+            mbar_arrive_expect_tx(&ring_full[slot], kStageBytes);
+            tma_load_2d(ring + size_t(slot) * kStageWords, &tmap, &ring_full[slot], int32_t(tile * P),
+                        int32_t(s * kSlotsPerStage), l2_policy);
+        };
+        auto advance = [&](uint32_t &t, uint32_t &s) { // next stage of this warp: global stage number += 12
+            s += kTrWarps;
+            while (s >= nst) {
+                s -= nst;
+                ++t;
             }
+        };
+        // position of this warp's k-th stage: gs = w + 12k -> (ti, st) = (gs / nst, gs % nst), kept incrementally
+        uint32_t ti = 0, st = w;
+        while (st >= nst) {
+            st -= nst;
+            ++ti;
         }
-        return;
-    }
+        uint32_t ti2 = ti, st2 = st; // look-ahead cursor: the stage that is (re)issued next
+        if (lane == 0 && w < total_stages)
+            issue(0, ti2, st2);
+        advance(ti2, st2);
+        if (lane == 0 && w + kTrWarps < total_stages)
+            issue(1, ti2, st2);
+        advance(ti2, st2);
 
-    if (warp >= kSelWarps) {
-        // ===================== transposers =====================
-        const uint32_t w = warp - kSelWarps;
-        // lane L of a stage holds word column c = L & (W-1) of the P-byte row and sub-block s = L >> kColBits
-        uint32_t k = 0; // stages consumed by this warp
-        for (uint32_t it = 0; it < my_tiles; ++it) {
-            if (tile_of(it) >= ntiles)
-                continue;
-            const uint32_t buf = it & 1u;
-            const uint32_t q = it >> 1;
-            mbar_wait(&planes_empty[buf], (q & 1u) ^ 1u); // selectors are done with the previous tile in this buffer
-            uint32_t *pbuf = planes + buf * kBufWords;
-            for (uint32_t st = w; st < nst; st += kTrWarps, ++k) {
-                const uint32_t slot = w + kTrWarps * (k & 1u);
-                mbar_wait(&ring_full[slot], (k >> 1) & 1u);
-                const uint32_t *src = ring + size_t(slot) * kStageWords + lane;
-                uint32_t r[32];
+        uint32_t k = 0;
+        for (uint32_t gs = w; gs < total_stages; gs += kTrWarps, ++k) {
+            const uint32_t buf = (NBUF == 2) ? (ti & 1u) : 0u;
+            const uint32_t q = (NBUF == 2) ? (ti >> 1) : ti; // fill number of this buffer
+            const uint32_t slot = w + kTrWarps * (k & 1u);
+            mbar_wait(&ring_full[slot], (k >> 1) & 1u);
+            const uint32_t *src = ring + size_t(slot) * kStageWords + lane;
+            uint32_t r[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    r[i] = src[i * 32];
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive(&ring_empty[slot]);
-                transpose32(r);
-                // r[8*p + b] = bit plane b of element 4*c+p over this lane's 32 frame slots
-                const uint32_t col = lane ^ (st & 1u);
-                uint4 *dst = reinterpret_cast<uint4 *>(pbuf + st * 1024u) + col;
+            for (int i = 0; i < 32; ++i)
+                r[i] = src[i * 32];
+            __syncwarp(); // every lane has read the slot: refill it with this warp's stage k+2 (same slot)
+            if (lane == 0 && gs + 2 * kTrWarps < total_stages)
+                issue(k, ti2, st2);
+            advance(ti2, st2);
+            transpose32(r);
+            // r[8*p + b] = bit plane b of element 4*c+p over this lane's 32 frame slots.
+            // Selectors must be done with the previous fill of this buffer.  Pre-check (almost always already
+            // true): the fill before that one is finished, which makes the parity wait at most one phase away.
+            if (q >= 2u) {
+                while (sel_done[buf] < NSELW * (q - 1u))
+                    __nanosleep(64);
+            }
+            mbar_wait(&planes_empty[buf], (q & 1u) ^ 1u);
+            const uint32_t col = lane ^ (st & (G - 1u));
+            uint4 *dst = reinterpret_cast<uint4 *>(planes + buf * kBufWords + st * 1024u) + col;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    dst[(p * 2 + 0) * 32] = make_uint4(r[8 * p + 0], r[8 * p + 1], r[8 * p + 2], r[8 * p + 3]);
-                    dst[(p * 2 + 1) * 32] = make_uint4(r[8 * p + 4], r[8 * p + 5], r[8 * p + 6], r[8 * p + 7]);
-                }
+            for (int p = 0; p < 4; ++p) {
+                dst[(p * 2 + 0) * 32] = make_uint4(r[8 * p + 0], r[8 * p + 1], r[8 * p + 2], r[8 * p + 3]);
+                dst[(p * 2 + 1) * 32] = make_uint4(r[8 * p + 4], r[8 * p + 5], r[8 * p + 6], r[8 * p + 7]);
             }
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&planes_full[buf]);
+            advance(ti, st);
         }
         return;
     }
 
     // ===================== selectors =====================
-    // warp = (byte p of the word, cx = lowest column bit); lane = logical transposer lane id with bit 0 replaced
-    // by g; this thread owns stages st = 2j + g of element 4c + p, sub-block s
-    const uint32_t s_p = warp >> 1;
-    const uint32_t s_cx = warp & 1u;
-    const uint32_t s_g = lane & 1u;
+    // warp = (byte p of the word, cx = low column bits); lane = logical transposer lane id with its low log2(G)
+    // bits replaced by the stage class g; this thread owns stages st = G*j + g of element 4c + p, sub-block s
+    const uint32_t s_p = warp / G;
+    const uint32_t s_cx = warp % G;
+    const uint32_t s_g = lane & (G - 1u);
     const uint32_t s_col = lane ^ s_cx;
-    const uint32_t s_L = (lane & ~1u) | s_cx;
+    const uint32_t s_L = (lane & ~(G - 1u)) | s_cx;
     const uint32_t s_c = s_L & ((32u >> LOG2S) - 1u);
     const uint32_t s_elem = 4u * s_c + s_p;
     const bool s_writer = (s_g == 0u) && ((lane >> kColBits) == 0u);
     const uint32_t k0 = nframes / 2u + (nst * kSlotsPerStage - nframes); // wanted rank incl. zero pad slots
 
     for (uint32_t it = 0; it < my_tiles; ++it) {
-        const uint32_t tile = tile_of(it);
-        if (tile >= ntiles)
-            continue;
-        const uint32_t buf = it & 1u;
-        const uint32_t q = it >> 1;
+        const uint32_t tile = blockIdx.x + it * gridDim.x;
+        const uint32_t buf = (NBUF == 2) ? (it & 1u) : 0u;
+        const uint32_t q = (NBUF == 2) ? (it >> 1) : it;
         mbar_wait(&planes_full[buf], q & 1u);
         const uint4 *base = reinterpret_cast<const uint4 *>(planes + buf * kBufWords + s_g * 1024u) + s_p * 64u + s_col;
         uint32_t alive[JT];
 #pragma unroll
         for (int j = 0; j < JT; ++j)
-            alive[j] = (2u * j + s_g) < nst ? 0xFFFFFFFFu : 0u; // rows >= nst hold garbage; alive == 0 masks them
+            alive[j] = (G * j + s_g) < nst ? 0xFFFFFFFFu : 0u; // rows >= nst hold garbage; alive == 0 masks them
         uint32_t k = k0;
         uint32_t med = 0;
 #pragma unroll
@@ -190,7 +193,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
             uint4 w4[JT];
 #pragma unroll
             for (int j = 0; j < JT; ++j)
-                w4[j] = base[j * 512 + bh * 32]; // stage 2j+g, nibble bh: 4 planes in one LDS.128
+                w4[j] = base[j * (G * 256) + bh * 32]; // stage G*j+g, nibble bh: 4 planes in one LDS.128
+            if (bh == 0) {
+                // every plane word this thread needs is now in registers: hand the buffer back to the transposers
+                __syncwarp();
+                if (lane == 0) {
+                    atomicAdd(const_cast<uint32_t *>(sel_done) + buf, 1u);
+                    mbar_arrive(&planes_empty[buf]);
+                }
+            }
 #pragma unroll
             for (int bl = 3; bl >= 0; --bl) {
                 uint32_t cnt = 0;
@@ -199,7 +210,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
                     const uint32_t wv = bl == 0 ? w4[j].x : bl == 1 ? w4[j].y : bl == 2 ? w4[j].z : w4[j].w;
                     cnt += __popc(alive[j] & ~wv);
                 }
-                cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1); // the two stage parities
+                cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1); // stage classes
+                if (G == 4) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
                 if (LOG2S >= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 16); // sub-blocks
                 if (LOG2S >= 2) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 8);
                 if (LOG2S >= 3) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 4);
@@ -216,43 +228,43 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0)
-            mbar_arrive(&planes_empty[buf]);
         const size_t e = size_t(tile) * P + s_elem;
         if (s_writer && e < nelem)
             out[e] = uint8_t(med);
     }
 }
 
-template <int LOG2S, int JT>
+template <int LOG2S, int JT, int NSELW>
 int launch_pipe_variant(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes,
                         uint32_t nst, cudaStream_t stream)
 {
     constexpr int P = 128 >> LOG2S;
+    constexpr uint32_t G = NSELW / 4;
+    constexpr uint32_t NBUF = (NSELW == 8) ? 2 : 1;
     const uint32_t ntiles = (nelem + P - 1) / P;
-    const size_t smem_bytes = size_t(kRing) * kStageBytes + 2u * (2u * JT * 4096u) + size_t(2 * kRing + 4) * 8;
+    const size_t smem_bytes = size_t(kRing) * kStageBytes + size_t(NBUF) * (G * JT * 4096u) + size_t(kRing + 4) * 8 + 16;
     if (smem_bytes > ctx->smem_optin)
-        return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: pipelined tile does not fit shared memory");
-    auto kern = median_pipe_kernel<LOG2S, JT>;
+        return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: tile does not fit shared memory");
+    auto kern = median_pipe_kernel<LOG2S, JT, NSELW>;
     CVVP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
-    const uint32_t npairs = (ntiles + 1) / 2;
-    const uint32_t grid = npairs < uint32_t(ctx->sm_count) ? npairs : uint32_t(ctx->sm_count);
-    // P == 128: every line is read once -> evict-first.  P < 128: the sibling tile re-reads the line from L2.
+    const uint32_t grid = ntiles < uint32_t(ctx->sm_count) ? ntiles : uint32_t(ctx->sm_count);
+    // P == 128: every line is read exactly once -> evict-first.  P < 128: the neighbouring CTA reads the other part
+    // of the line at about the same time and should hit L2.
     const uint64_t policy = (LOG2S == 0) ? kL2EvictFirst : kL2EvictNormal;
-    kern<<<grid, kPipeThreads, smem_bytes, stream>>>(tmap, d_out, nelem, nframes, nst, ntiles, policy);
+    kern<<<grid, (NSELW + kTrWarps) * 32, smem_bytes, stream>>>(tmap, d_out, nelem, nframes, nst, ntiles, policy);
     CVVP_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches++;
     return CVVP_OK;
 }
 
-template <int LOG2S>
-int dispatch_pipe(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes, uint32_t nst,
-                  cudaStream_t stream)
+template <int LOG2S, int NSELW>
+int dispatch_jt(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes, uint32_t nst,
+                cudaStream_t stream)
 {
-    switch ((nst + 1u) / 2u) {
+    constexpr uint32_t G = NSELW / 4;
+    switch ((nst + G - 1u) / G) {
 #define CVVP_JT_CASE(J) \
-    case J: return launch_pipe_variant<LOG2S, J>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+    case J: return launch_pipe_variant<LOG2S, J, NSELW>(ctx, tmap, d_out, nelem, nframes, nst, stream);
         CVVP_JT_CASE(1)
         CVVP_JT_CASE(2)
         CVVP_JT_CASE(3)
@@ -265,24 +277,35 @@ int dispatch_pipe(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32
     default: return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: unsupported stage count %u", nst);
     }
 }
+
+template <int LOG2S>
+int dispatch_mode(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes, uint32_t nst,
+                  cudaStream_t stream)
+{
+    const char *e = getenv("CVVP_MEDIAN_BUFFERS"); // development switch: "1" forces the single-buffer mode
+    const bool force_single = e && e[0] == '1';
+    if (nst <= 16 && !force_single)
+        return dispatch_jt<LOG2S, 8>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+    return dispatch_jt<LOG2S, 16>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+}
 } // namespace
 
-// Largest frame count the pipelined kernel takes (16 stages x 256 frame slots at P = 16).
-long long median_pipe_max_frames()
+// Largest frame count the kernel takes: 32 stages x 256 frame slots at P = 16.
+long long median_max_frames()
 {
-    return 16ll * 256ll;
+    return 32ll * 256ll;
 }
 
 int median_pipe_launch(cvvp_ctx *ctx, const CUtensorMap &tmap, int log2s, uint8_t *d_out, uint32_t nelem,
                        uint32_t nframes, uint32_t nst, cudaStream_t stream)
 {
-    if (nst == 0 || nst > kMaxStages)
-        return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: %u stages exceed the pipelined kernel's plane buffers", nst);
+    if (nst == 0 || nst > 32)
+        return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: %u stages exceed the plane buffer", nst);
     switch (log2s) {
-    case 0: return dispatch_pipe<0>(ctx, tmap, d_out, nelem, nframes, nst, stream);
-    case 1: return dispatch_pipe<1>(ctx, tmap, d_out, nelem, nframes, nst, stream);
-    case 2: return dispatch_pipe<2>(ctx, tmap, d_out, nelem, nframes, nst, stream);
-    case 3: return dispatch_pipe<3>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+    case 0: return dispatch_mode<0>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+    case 1: return dispatch_mode<1>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+    case 2: return dispatch_mode<2>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+    case 3: return dispatch_mode<3>(ctx, tmap, d_out, nelem, nframes, nst, stream);
     default: return fail(ctx, CVVP_ERR_INVALID, "median: bad tile variant");
     }
 }

@@ -86,6 +86,13 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
                  : "memory");
 }
 
+// Bulk prefetch of a contiguous global range into L2 (a hint: no destination, no completion to wait for).
+// addr and bytes must be multiples of 16.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tmap)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

@@ -31,19 +31,19 @@ def test_ragged_geometry(gpu_ctx, oracle_median, shape):
     assert np.array_equal(gpu_ctx.median(frames), oracle_median(frames))
 
 
-# every tile variant of both kernels.  Pipelined kernel: P=128 (N<=512), 64 (<=1024), 32 (<=2048), 16 (<=4096);
-# single-buffer kernel above that: P=32 (<=5120), 16 (<=10240).
-@pytest.mark.parametrize("n", [512, 513, 1024, 1025, 2048, 2049, 3000, 4096, 4097, 5000, 5121, 9000, 10240])
+# every tile variant and both buffering modes.  P=128: N<=512 (two plane buffers) / <=1024 (one buffer); P=64: <=1024
+# / <=2048; P=32: <=2048 / <=4096; P=16: <=4096 / <=8192.
+@pytest.mark.parametrize("n", [512, 513, 1024, 1025, 2048, 2049, 3000, 4096, 4097, 5000, 8191, 8192])
 def test_large_frame_counts(gpu_ctx, oracle_median, n):
     rng = np.random.default_rng(n)
     frames = _rand(rng, n, 5, 77, 90, 140)
     assert np.array_equal(gpu_ctx.median(frames, chunk=512), oracle_median(frames))
 
 
-@pytest.mark.parametrize("n", [1, 33, 100, 512, 1000, 1280, 1281, 2560, 2561])
-def test_single_buffer_kernel_forced(gpu_ctx, oracle_median, n, monkeypatch):
-    """CVVP_MEDIAN_KERNEL=single routes every frame count through the single-buffer kernel (P=128 <= 1280, 64 <= 2560)."""
-    monkeypatch.setenv("CVVP_MEDIAN_KERNEL", "single")
+@pytest.mark.parametrize("n", [1, 2, 33, 100, 129, 500, 512])
+def test_single_buffer_mode_forced(gpu_ctx, oracle_median, n, monkeypatch):
+    """CVVP_MEDIAN_BUFFERS=1 routes small frame counts through the one-buffer / 16-select-warp mode as well."""
+    monkeypatch.setenv("CVVP_MEDIAN_BUFFERS", "1")
     rng = np.random.default_rng(n + 7)
     frames = _rand(rng, n, 9, 131)
     assert np.array_equal(gpu_ctx.median(frames, chunk=512), oracle_median(frames))
@@ -51,7 +51,7 @@ def test_single_buffer_kernel_forced(gpu_ctx, oracle_median, n, monkeypatch):
 
 @pytest.mark.parametrize("shape", [(2, 64), (2, 65), (3, 128), (1, 300), (7, 1000)])
 def test_tile_pair_tails(gpu_ctx, oracle_median, shape):
-    """element counts around the tile-pair boundaries of the pipelined kernel (odd tile counts, partial last tile)"""
+    """element counts around tile boundaries (fewer tiles than SMs, partial last tile)"""
     rng = np.random.default_rng(shape[1])
     for n in (5, 600, 1500):
         frames = _rand(rng, n, *shape)
@@ -172,7 +172,7 @@ def test_too_many_frames_is_a_loud_error(gpu_ctx):
     import torch
     from cvvidproc_b200 import _cabi
 
-    n, nelem = 10241, 256
+    n, nelem = 8193, 256
     stack = torch.zeros((n, nelem), dtype=torch.uint8, device="cuda:0")
     out = torch.zeros(nelem, dtype=torch.uint8, device="cuda:0")
     with pytest.raises(_cabi.CvvpError) as ei:
