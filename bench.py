@@ -359,7 +359,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     achieved = algo_bytes / (kern_ms_max * 1e-3) / 1e9
     traffic = load_traffic() if world == 1 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "median_bitslice_kernel",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "median_pipe_kernel",
                 "kernel_ms": kern_ms_max, "algorithmic_bytes_per_launch": algo_bytes}
 
     # ---- CPU baseline on rank 0 at N=1 only (bounded sample; reported, not the target)
