@@ -1,0 +1,79 @@
+"""CPU tests of the highlight oracles: the cv2 restatement of highlight_objects_algo.cpp (oracle/highlight_oracle.py)
+against the independent label-based model (oracle/highlight_model.py), stage by stage, on random and adversarial
+images, and against the committed golden hashes."""
+import hashlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import hl_cases
+from oracle import highlight_model as hm
+from oracle import highlight_oracle as ho
+
+STAGES = ["diff", "a_thresh", "a_open", "a_rso", "a_fill", "b_hyst", "b_open", "b_rso", "b_fill"]
+
+
+def _run_both(frame, p):
+    so, sm = {}, {}
+    a = ho.highlight_objects(frame.copy(), p, so)
+    b = hm.highlight_objects(frame, p.background, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi,
+                             p.min_size_hyst, p.min_size_threshold, sm)
+    return a, b, so, sm
+
+
+@pytest.mark.parametrize("t", range(120))
+def test_model_matches_cv2_random(t):
+    frame, p = hl_cases.random_case(t)
+    a, b, so, sm = _run_both(frame, p)
+    for k in STAGES:
+        assert np.array_equal(so[k], sm[k]), f"stage {k}"
+    assert np.array_equal(a, b)
+
+
+ADV = hl_cases.adversarial_cases()
+
+
+@pytest.mark.parametrize("case", ADV, ids=[c[0] for c in ADV])
+def test_model_matches_cv2_adversarial(case):
+    _, frame, p = case
+    a, b, so, sm = _run_both(frame, p)
+    for k in STAGES:
+        assert np.array_equal(so[k], sm[k]), f"stage {k}"
+    assert np.array_equal(a, b)
+
+
+def test_quirks_are_reproduced():
+    """the three places where the code differs from the prose"""
+    by = {c[0]: c for c in ADV}
+    # Q1: saturating bg - frame: a frame brighter than the background highlights nothing
+    _, f, p = by["brighter_everywhere"]
+    assert not ho.highlight_objects(f.copy(), p).any()
+    # Q4: an object covering pixel (0,0) turns the whole frame white
+    _, f, p = by["covers_origin"]
+    assert (ho.highlight_objects(f.copy(), p) == 255).all()
+    _, f, p = by["covers_bottom_right"]
+    assert (ho.highlight_objects(f.copy(), p) == 255).all()
+
+
+def test_synthetic_stream_case():
+    frame, p = hl_cases.synthetic_case()
+    a, b, so, sm = _run_both(frame, p)
+    assert np.array_equal(a, b)
+    assert 0 < (a == 255).mean() < 0.5
+
+
+def test_golden_hashes():
+    golden = json.loads((Path(__file__).parent / "golden" / "highlight_golden.json").read_text())
+    by = {c[0]: c for c in ADV}
+    for g in golden:
+        if g["kind"] == "adversarial":
+            _, frame, p = by[g["name"]]
+        elif g["kind"] == "random":
+            frame, p = hl_cases.random_case(g["t"])
+        else:
+            frame, p = hl_cases.synthetic_case(g["cfg"], g["frame_index"], g["scale"])
+        assert hashlib.sha256(frame.tobytes()).hexdigest() == g["input_sha256"], g["name"]
+        out = ho.highlight_objects(frame.copy(), p)
+        assert hashlib.sha256(out.tobytes()).hexdigest() == g["output_sha256"], g["name"]
