@@ -63,6 +63,10 @@ def load():
         "cvvp_median_abort": (i32, [vp]),
         "cvvp_median_device": (i32, [vp, vp, i64, sz, sz, vp, vp]),
         "cvvp_median_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
+        "cvvp_highlight_begin": (i32, [vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32]),
+        "cvvp_highlight_frames": (i32, [vp, vp, i64, sz, vp, sz]),
+        "cvvp_highlight_device": (i32, [vp, vp, i64, sz, vp, sz, vp]),
+        "cvvp_highlight_end": (i32, [vp]),
         "cvvp_synth_frames_device": (i32, [vp, vp, sz, i32, i32, i32, i32, i64, i64, u32, i32, vp]),
     }
     global BOUND_SYMBOLS
@@ -217,6 +221,39 @@ class Context:
         v = C.c_float()
         self._check(self._lib.cvvp_median_last_kernel_ms(self._h, C.byref(v)))
         return float(v.value)
+
+    # -- highlight ------------------------------------------------------------------------
+    def highlight_begin(self, background: np.ndarray, struct_element: np.ndarray, threshold: int, threshold_lo: int,
+                        threshold_hi: int, min_size_hyst: int, min_size_threshold: int, width_border: int = 0):
+        bg = np.ascontiguousarray(background)
+        se = np.ascontiguousarray(struct_element)
+        if bg.dtype != np.uint8 or bg.ndim != 2:
+            raise TypeError("background must be a 2-D uint8 array")
+        if se.dtype != np.uint8 or se.ndim != 2:
+            raise TypeError("struct_element must be a 2-D uint8 array (cv::morphologyEx asserts CV_8U)")
+        h, w = bg.shape
+        kh, kw = se.shape
+        self._check(self._lib.cvvp_highlight_begin(self._h, bg.ctypes.data, w, h, se.ctypes.data, kw, kh, threshold,
+                                                   threshold_lo, threshold_hi, min_size_hyst, min_size_threshold,
+                                                   width_border))
+        self._hl_shape = (h, w)
+
+    def highlight_frames(self, frames: np.ndarray) -> np.ndarray:
+        """frames: uint8 (n, H, W) -> masks uint8 (n, H, W) of 0/255"""
+        frames = np.ascontiguousarray(frames)
+        if frames.dtype != np.uint8 or frames.ndim != 3 or frames.shape[1:] != self._hl_shape:
+            raise TypeError("frames must be uint8 of shape (n, H, W) matching the background")
+        n = frames.shape[0]
+        npix = frames.shape[1] * frames.shape[2]
+        out = np.empty_like(frames)
+        self._check(self._lib.cvvp_highlight_frames(self._h, frames.ctypes.data, n, npix, out.ctypes.data, npix))
+        return out
+
+    def highlight_device(self, d_frames: int, n: int, frame_stride: int, d_out: int, out_stride: int, stream: int = 0):
+        self._check(self._lib.cvvp_highlight_device(self._h, d_frames, n, frame_stride, d_out, out_stride, stream or None))
+
+    def highlight_end(self):
+        self._check(self._lib.cvvp_highlight_end(self._h))
 
     # -- synthetic frames -----------------------------------------------------------------
     def synth_frames_device(self, d_frames: int, frame_stride: int, width: int, height: int, first_frame: int,

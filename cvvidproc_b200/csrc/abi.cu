@@ -205,6 +205,7 @@ void cvvp_ctx_destroy(cvvp_ctx *ctx)
         if (b.host)
             cudaFreeHost(b.host);
     }
+    highlight_release(ctx);
     if (ctx->med.d_stack)
         cudaFree(ctx->med.d_stack);
     if (ctx->med.d_out)
@@ -462,6 +463,52 @@ int cvvp_median_last_kernel_ms(cvvp_ctx *ctx, float *out_ms)
         return fail(ctx, CVVP_ERR_STATE, "no median kernel has been timed on this context");
     DeviceGuard guard(ctx->device);
     CVVP_CUDA_OK(ctx, cudaEventElapsedTime(out_ms, ctx->ev_start, ctx->ev_stop));
+    return CVVP_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* highlight                                                                                   */
+/* ------------------------------------------------------------------------------------------- */
+
+int cvvp_highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, int height, const uint8_t *struct_element,
+                         int kw, int kh, int threshold, int threshold_lo, int threshold_hi, int min_size_hyst,
+                         int min_size_threshold, int width_border)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    (void)width_border; // accepted and unused, exactly like the reference (FrameAndFill is dead code, :68-71)
+    DeviceGuard guard(ctx->device);
+    return highlight_begin(ctx, background, width, height, struct_element, kw, kh, threshold, threshold_lo, threshold_hi,
+                           min_size_hyst, min_size_threshold);
+}
+
+int cvvp_highlight_frames(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, uint8_t *masks_out,
+                          size_t out_stride)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    return highlight_frames_host(ctx, frames, n, frame_stride, masks_out, out_stride);
+}
+
+int cvvp_highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride, uint8_t *d_out,
+                          size_t out_stride, void *stream)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->compute;
+    return highlight_device(ctx, d_frames, n, frame_stride, d_out, out_stride, s);
+}
+
+int cvvp_highlight_end(cvvp_ctx *ctx)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->copy);
+    cudaStreamSynchronize(ctx->compute);
+    highlight_release(ctx);
     return CVVP_OK;
 }
 

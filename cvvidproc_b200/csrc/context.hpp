@@ -36,6 +36,7 @@ struct MedianJob {
     size_t d_out_bytes{0};
     size_t d_stack_bytes{0};
 };
+struct HighlightState; // highlight.cu
 } // namespace cvvp
 
 struct cvvp_ctx {
@@ -54,6 +55,7 @@ struct cvvp_ctx {
     std::string err;
     cvvp::EncodeTiledFn encode_tiled{nullptr};
     cvvp::MedianJob med;
+    cvvp::HighlightState *hl{nullptr};
     std::vector<cvvp::StagingBuf> staging;
     size_t staging_next{0};
 };
@@ -99,6 +101,14 @@ int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, siz
 long long median_max_frames();
 int median_pipe_launch(cvvp_ctx *ctx, const CUtensorMap &tmap, int log2s, uint8_t *d_out, uint32_t nelem, uint32_t nframes,
                        uint32_t nst, cudaStream_t stream);
+// highlight.cu
+void highlight_release(cvvp_ctx *ctx);
+int highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, int height, const uint8_t *selem, int kw, int kh,
+                    int threshold, int threshold_lo, int threshold_hi, int min_size_hyst, int min_size_threshold);
+int highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride, uint8_t *d_out,
+                     size_t out_stride, cudaStream_t stream);
+int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, uint8_t *masks_out,
+                          size_t out_stride);
 // synth.cu
 int synth_launch(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width, int height, int row0, int nrows,
                  long long first_frame, long long nframes, uint32_t seed, int ndisks, cudaStream_t stream);

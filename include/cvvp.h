@@ -106,6 +106,33 @@ CVVP_API int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long lon
                        size_t frame_stride, uint8_t *d_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * per-frame highlight -- replaces HighlightObjectsAlgo
+ *   Sources/ProcessorAlgos/highlight_objects_algo.h
+ *     TokenProcessorPack<HighlightObjectsAlgo> :21-32   -> cvvp_highlight_begin (parameters, moved in once)
+ *     Insert :60-69 / TryGetResult :72-79               -> cvvp_highlight_frames (batch of tokens in, masks out,
+ *                                                          same order; the reference mutates each token in place)
+ *   Sources/ProcessorAlgos/highlight_objects_algo.cpp
+ *     HighlightObjects :17-78 and its helpers :81-221   -> the device kernels (csrc/highlight.cu)
+ *
+ * Frames and the background are 8-bit single channel, width*height contiguous bytes (findContours requires
+ * 8UC1).  Output masks are 0 / 255.  The structuring element is kh x kw bytes, any non-zero entry is set
+ * (cv::morphologyEx asserts CV_8U), anchor (kw/2, kh/2).  threshold == -1 selects Otsu (:89-95).
+ * width_border is accepted and ignored, like the reference (:68-71).
+ * ------------------------------------------------------------------------------------------- */
+CVVP_API int cvvp_highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, int height,
+                                  const uint8_t *struct_element, int kw, int kh, int threshold, int threshold_lo,
+                                  int threshold_hi, int min_size_hyst, int min_size_threshold, int width_border);
+/* n frames from HOST memory (frame i at frames + i*frame_stride) -> n masks in HOST memory (mask i at
+ * masks_out + i*out_stride); synchronous; H2D, kernels and D2H of consecutive chunks overlap internally.
+ * masks_out may alias frames (in-place, like the reference's tokens) when the strides are equal. */
+CVVP_API int cvvp_highlight_frames(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride,
+                                   uint8_t *masks_out, size_t out_stride);
+/* device-resident form; runs on `stream` (NULL = the context's compute stream), does not synchronize */
+CVVP_API int cvvp_highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride,
+                                   uint8_t *d_out, size_t out_stride, void *stream);
+CVVP_API int cvvp_highlight_end(cvvp_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------
  * synthetic input: deterministic integer-hash frames generated directly in
  * device memory, bit-identical to cvvidproc_b200/synth.py on the host.
  * frames first_frame .. first_frame+nframes-1 of the stream (seed, K disks) are written to
