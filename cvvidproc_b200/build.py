@@ -77,12 +77,14 @@ def build_core_module(force: bool = False, verbose: bool = False) -> Path | None
     deps = [src] + sorted((CSRC / "host").glob("*.hpp")) + [REPO / "include" / "cvvp.h"]
     if not force and _newer_than(out, deps) and _newer_than(out, [LIB_PATH]):
         return out
-    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    # the system compiler links libstdc++ dynamically; the image's /opt/gcc wrapper (often in $CXX) links a STATIC
+    # libstdc++ whose exported symbols then clash with the copy every other extension (cv2, torch) uses
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else (os.environ.get("CXX") or shutil.which("g++") or "g++")
     cmd = [
         cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",
         "-I", str(REPO / "include"), "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
         str(src), "-o", str(out),
-        "-L", str(PKG_DIR), "-lcvvp_cuda", "-Wl,-rpath,$ORIGIN",
+        "-L", str(PKG_DIR), "-lcvvp_cuda", "-Wl,-rpath,$ORIGIN", "-Wl,--exclude-libs,ALL",
     ]
     _run(cmd, "core.log", verbose)
     return out

@@ -1,0 +1,385 @@
+// pybind11 module `_core`: the reference's Python surface (Sources/py_bindings.cpp:26-131) on top of the C++ host
+// operators (gpu_algos.hpp) and the C ABI.  Same class names, argument names, order and defaults; same observable
+// behaviour of the two entry points:
+//
+//   GetVideoBackground(pack) -> ndarray | None     Sources/cv_vid_bg_helpers.cpp:197-264
+//   TrackObjects(pack)       -> dict               Sources/cv_vid_objecttrack_helpers.cpp:153-210
+//
+// OpenCV C++ is not part of this build, so the numpy<->cv::Mat caster (Sources/Utility/ndarray_converter.*) is replaced
+// by py::array_t<uint8_t>, and video decode goes through the Python `cv2` module (the only decoder in the image),
+// reproducing CvVidFramesGeneratorAlgo::GetTokenSet (ProcessorTokenHandlers/cv_vid_frames_generator_algo.h:120-185):
+// crop, then channel 0 (vid_is_grayscale) or RGB2GRAY (grayscale) or the frame as is.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstdint>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <string>
+
+#include "gpu_algos.hpp"
+
+namespace py = pybind11;
+using namespace cvvp_host;
+
+namespace
+{
+using u8array = py::array_t<std::uint8_t, py::array::c_style | py::array::forcecast>;
+
+// ---- packs (plain data, only __init__ is exposed, like the reference) -------------------------------------------------
+struct VidBgPack { // cv_vid_bg_helpers.h:30-60
+    std::string vid_path;
+    std::string bg_algo;
+    int max_threads;
+    long long frame_limit;
+    bool grayscale;
+    bool vid_is_grayscale;
+    int crop_x, crop_y, crop_width, crop_height;
+    int token_storage_limit;
+    bool print_timing_report;
+};
+
+struct HighlightObjectsPack { // highlight_objects_algo.h:21-32
+    py::array background;
+    py::array struct_element;
+    int threshold, threshold_lo, threshold_hi, min_size_hyst, min_size_threshold, width_border;
+};
+
+struct AssignObjectsPack { // assign_objects_algo.h:28-44
+    py::function function;
+    py::dict kwargs;
+};
+
+struct VidObjectTrackPack { // cv_vid_objecttrack_helpers.h:23-60
+    std::string vid_path;
+    HighlightObjectsPack highlight_objects_pack;
+    AssignObjectsPack assign_objects_pack;
+    int max_threads;
+    long long start_frame;
+    long long frame_limit;
+    bool grayscale;
+    bool vid_is_grayscale;
+    int crop_x, crop_y, crop_width, crop_height;
+    int token_storage_limit;
+    bool print_timing_report;
+};
+
+struct Rect {
+    int x, y, width, height;
+};
+
+// cv_vid_bg_helpers.cpp:39-60 -- including its quirk: the height clamp compares against hor_pixels (:56)
+Rect GetCroppedFrameDims(int x, int y, int width, int height, int hor_pixels, int vert_pixels)
+{
+    CVVP_ASSERT(x >= 0);
+    CVVP_ASSERT(y >= 0);
+    CVVP_ASSERT(width >= 0);
+    CVVP_ASSERT(height >= 0);
+    CVVP_ASSERT_MSG(hor_pixels > 0, "frame must have horizontal size");
+    CVVP_ASSERT_MSG(vert_pixels > 0, "frame must have verical size");
+    CVVP_ASSERT_MSG(x < hor_pixels, "start of crop window can't be outside frame");
+    CVVP_ASSERT_MSG(y < vert_pixels, "start of crop window can't be outside frame");
+    if (width == 0 || width + x > hor_pixels)
+        width = hor_pixels - x;
+    if (height == 0 || height + y > hor_pixels)
+        height = vert_pixels - y;
+    return Rect{x, y, width, height};
+}
+
+// One decoded, cropped, channel-reduced frame as a contiguous uint8 array (H, W) or (H, W, C).
+// Mirrors CvVidFramesGeneratorAlgo::GetTokenSet (:137-156).  Returns an empty object at end of stream.
+class FrameSource
+{
+public:
+    FrameSource(const std::string &path, bool grayscale, bool vid_is_grayscale)
+        : m_cv2{py::module_::import("cv2")}, m_np{py::module_::import("numpy")}, m_gray{grayscale}, m_is_gray{vid_is_grayscale}
+    {
+        m_vid = m_cv2.attr("VideoCapture")(path);
+    }
+    bool opened() const { return m_vid.attr("isOpened")().cast<bool>(); }
+    double get(const char *prop) const { return m_vid.attr("get")(m_cv2.attr(prop)).cast<double>(); }
+    void set(const char *prop, double v) { m_vid.attr("set")(m_cv2.attr(prop), v); }
+    void set_crop(Rect r) { m_crop = r; }
+    void configure()
+    {
+        // :103-105 interpret frames as RGB for consistency unless the video is declared grayscale
+        if (!m_is_gray)
+            set("CAP_PROP_CONVERT_RGB", 1.0);
+    }
+    py::object next()
+    {
+        py::tuple res = m_vid.attr("read")().cast<py::tuple>();
+        if (!res[0].cast<bool>() || res[1].is_none())
+            return py::none();
+        py::object frame = res[1];
+        // :141 crop
+        frame = frame[py::make_tuple(py::slice(m_crop.y, m_crop.y + m_crop.height, 1),
+                                     py::slice(m_crop.x, m_crop.x + m_crop.width, 1))];
+        const int ndim = frame.attr("ndim").cast<int>();
+        if (m_is_gray) {
+            if (ndim == 3)
+                frame = m_cv2.attr("extractChannel")(frame, 0); // :149-151
+        } else if (m_gray) {
+            if (ndim == 3)
+                frame = m_cv2.attr("cvtColor")(frame, m_cv2.attr("COLOR_RGB2GRAY")); // :152-154
+        }
+        return m_np.attr("ascontiguousarray")(frame, py::arg("dtype") = m_np.attr("uint8"));
+    }
+
+private:
+    py::module_ m_cv2, m_np;
+    py::object m_vid;
+    bool m_gray, m_is_gray;
+    Rect m_crop{0, 0, 0, 0};
+};
+
+void array_geometry(const py::array &a, int &rows, int &cols, int &channels)
+{
+    CVVP_ASSERT_MSG(a.ndim() == 2 || a.ndim() == 3, "frames must be 2-D or 3-D uint8 arrays");
+    rows = int(a.shape(0));
+    cols = int(a.shape(1));
+    channels = a.ndim() == 3 ? int(a.shape(2)) : 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GetVideoBackground  (cv_vid_bg_helpers.cpp:197-264)
+// ---------------------------------------------------------------------------------------------------------------------
+py::object GetVideoBackground(const VidBgPack &pack)
+{
+    FrameSource vid{pack.vid_path, pack.grayscale, pack.vid_is_grayscale};
+    if (!vid.opened()) {
+        std::cerr << "Video file not detected: " << pack.vid_path << '\n';
+        return py::none(); // the reference returns an empty Mat, which its caster turns into None
+    }
+    const long long total_frames = static_cast<long long>(vid.get("CAP_PROP_FRAME_COUNT"));
+    const double fw = vid.get("CAP_PROP_FRAME_WIDTH"), fh = vid.get("CAP_PROP_FRAME_HEIGHT");
+    std::cout << "Frames: " << total_frames << "; Res: " << fw << 'x' << fh; // :212-223
+    if (pack.crop_x || pack.crop_y || pack.crop_width || pack.crop_height) {
+        const Rect r = GetCroppedFrameDims(pack.crop_x, pack.crop_y, pack.crop_width, pack.crop_height, int(fw), int(fh));
+        std::cout << "(" << r.width << 'x' << r.height << " cropped)";
+    }
+    std::cout << "; FPS: " << vid.get("CAP_PROP_FPS") << '\n';
+    std::cout.flush();
+
+    long long frames_to_analyze = pack.frame_limit; // :226-229
+    if (frames_to_analyze <= 0 || frames_to_analyze > total_frames)
+        frames_to_analyze = total_frames;
+
+    if (pack.bg_algo != "hist") { // GetBGAlgo :27-37 + the switch default :255-260
+        std::cerr << "Unknown background algorithm detected: " << pack.bg_algo << '\n';
+        std::cerr << "tried to get vid background with unknown algorithm: " << pack.bg_algo << '\n';
+        return py::none();
+    }
+    if (frames_to_analyze > static_cast<long long>(std::numeric_limits<std::uint32_t>::max())) { // :249-260 falls through
+        std::cerr << "warning, video appears to have over 2^32 frames! (" << total_frames << ") is way too many!\n";
+        std::cerr << "tried to get vid background with unknown algorithm: " << pack.bg_algo << '\n';
+        return py::none();
+    }
+
+    const Rect crop = GetCroppedFrameDims(pack.crop_x, pack.crop_y, pack.crop_width, pack.crop_height, int(fw), int(fh));
+    CVVP_ASSERT(crop.x + crop.width <= int(fw) && crop.y + crop.height <= int(fh)); // generator ctor :90-92
+    vid.set_crop(crop);
+    vid.configure();
+
+    GpuMedianAlgo algo{GpuMedianPack{-1, frames_to_analyze}};
+    long long consumed = 0;
+    int rows = 0, cols = 0, channels = 1;
+    while (consumed < frames_to_analyze) { // generator :128-135
+        py::object f = vid.next();
+        if (f.is_none())
+            break;
+        py::array a = f.cast<py::array>();
+        array_geometry(a, rows, cols, channels);
+        algo.InsertRaw(static_cast<const std::uint8_t *>(a.data()), 1, rows, cols, channels, std::size_t(rows) * cols * channels);
+        ++consumed;
+    }
+    algo.NotifyNoMoreTokens();
+    std::unique_ptr<FrameBatch> res = algo.TryGetResult();
+    if (!res || res->empty())
+        return py::none();
+    // shape (H, W) for one channel, (H, W, C) otherwise (ndarray_converter.cpp:141-142)
+    std::vector<py::ssize_t> shape{res->rows, res->cols};
+    if (res->channels > 1)
+        shape.push_back(res->channels);
+    py::array_t<std::uint8_t> out(shape);
+    std::memcpy(out.mutable_data(), res->data.data(), res->data.size());
+    if (pack.print_timing_report)
+        std::cout << "Background: " << consumed << " frames consumed by the device median\n";
+    return std::move(out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TrackObjects  (cv_vid_objecttrack_helpers.cpp:153-210, :30-150; assign_objects_algo.h:94-161)
+// ---------------------------------------------------------------------------------------------------------------------
+FrameBatch to_u8_image(const py::array &src, const char *what)
+{
+    CVVP_ASSERT_MSG(src.size() > 0, what);
+    CVVP_ASSERT_MSG(src.ndim() == 2, "expected a 2-D array");
+    CVVP_ASSERT_MSG(src.dtype().is(py::dtype::of<std::uint8_t>()), "expected a uint8 array (OpenCV asserts CV_8U here)");
+    u8array a = u8array::ensure(src);
+    FrameBatch b;
+    b.n = 1;
+    b.rows = int(a.shape(0));
+    b.cols = int(a.shape(1));
+    b.channels = 1;
+    b.data.assign(a.data(), a.data() + a.size());
+    return b;
+}
+
+py::dict TrackObjects(const VidObjectTrackPack &pack)
+{
+    FrameSource vid{pack.vid_path, pack.grayscale, pack.vid_is_grayscale};
+    if (!vid.opened()) {
+        std::cerr << "Video file not detected: " << pack.vid_path << '\n';
+        return py::dict{};
+    }
+    const int fw = int(vid.get("CAP_PROP_FRAME_WIDTH")), fh = int(vid.get("CAP_PROP_FRAME_HEIGHT"));
+    // validation :167-175 (raises RuntimeError like EXCEPTION_ASSERT)
+    const py::array &bg = pack.highlight_objects_pack.background;
+    CVVP_ASSERT_MSG(bg.size() > 0, "background must not be empty");
+    const Rect crop = GetCroppedFrameDims(pack.crop_x, pack.crop_y, pack.crop_width, pack.crop_height, fw, fh);
+    CVVP_ASSERT(bg.ndim() >= 2 && crop.width == int(bg.shape(1)));
+    CVVP_ASSERT(bg.ndim() >= 2 && crop.height == int(bg.shape(0)));
+    CVVP_ASSERT_MSG(pack.highlight_objects_pack.struct_element.size() > 0, "struct element must not be empty");
+
+    long long num_frames = static_cast<long long>(vid.get("CAP_PROP_FRAME_COUNT")); // :54-66
+    const long long total = num_frames;
+    if (pack.frame_limit > 0 && num_frames > pack.frame_limit)
+        num_frames = pack.frame_limit;
+    // generator constructor checks (cv_vid_frames_generator_algo.h:94-101)
+    CVVP_ASSERT(pack.start_frame >= 0);
+    CVVP_ASSERT(pack.start_frame < total);
+    CVVP_ASSERT(pack.start_frame + num_frames > 0);
+    CVVP_ASSERT(num_frames > 0);
+    CVVP_ASSERT(crop.x + crop.width <= fw && crop.y + crop.height <= fh);
+    vid.set("CAP_PROP_POS_FRAMES", double(pack.start_frame));
+    vid.set_crop(crop);
+    vid.configure();
+
+    GpuHighlightPack hp;
+    hp.background = to_u8_image(bg, "background must not be empty");
+    hp.struct_element = to_u8_image(pack.highlight_objects_pack.struct_element, "struct element must not be empty");
+    hp.threshold = pack.highlight_objects_pack.threshold;
+    hp.threshold_lo = pack.highlight_objects_pack.threshold_lo;
+    hp.threshold_hi = pack.highlight_objects_pack.threshold_hi;
+    hp.min_size_hyst = pack.highlight_objects_pack.min_size_hyst;
+    hp.min_size_threshold = pack.highlight_objects_pack.min_size_threshold;
+    hp.width_border = pack.highlight_objects_pack.width_border;
+    GpuHighlightAlgo highlighter{std::move(hp)};
+
+    // frames per device batch: the reference's batch_size is a thread count; here it is sized for the GPU and bounded by
+    // token_storage_limit batches of host memory like the reference's queues (token_queue.h:209-214)
+    const long long npix = static_cast<long long>(crop.width) * crop.height;
+    long long batch_frames = (32ll << 20) / npix + 1;
+    if (batch_frames > 256)
+        batch_frames = 256;
+
+    // AssignObjectsAlgo state (assign_objects_algo.h:172-178)
+    py::dict objects_active, objects_archive;
+    long long num_processed = 0;
+    int next_id = 0;
+    bool any = false;
+
+    long long consumed = 0;
+    bool eof = false;
+    while (!eof && consumed < num_frames) {
+        auto batch = std::make_unique<FrameBatch>();
+        batch->rows = crop.height;
+        batch->cols = crop.width;
+        batch->channels = 1;
+        while (batch->n < batch_frames && consumed < num_frames) {
+            py::object f = vid.next();
+            if (f.is_none()) {
+                eof = true;
+                break;
+            }
+            py::array a = f.cast<py::array>();
+            int r, c, ch;
+            array_geometry(a, r, c, ch);
+            CVVP_ASSERT_MSG(ch == 1, "TrackObjects needs single-channel frames: set grayscale or vid_is_grayscale "
+                                     "(cv::findContours requires 8UC1)");
+            CVVP_ASSERT(r == crop.height && c == crop.width);
+            const auto *src = static_cast<const std::uint8_t *>(a.data());
+            batch->data.insert(batch->data.end(), src, src + std::size_t(r) * c);
+            batch->n++;
+            ++consumed;
+        }
+        if (batch->n == 0)
+            break;
+        highlighter.Insert(std::move(batch));
+        std::unique_ptr<FrameBatch> masks = highlighter.TryGetResult();
+        // strictly in frame order, one call per frame (assign_objects_algo.h:111-133)
+        for (int i = 0; i < masks->n; ++i) {
+            py::array_t<std::uint8_t> bw({masks->rows, masks->cols});
+            std::memcpy(bw.mutable_data(), masks->data.data() + std::size_t(i) * masks->frame_bytes(), masks->frame_bytes());
+            using namespace pybind11::literals;
+            next_id = pack.assign_objects_pack.function("bw_frame"_a = bw, "frames_processed"_a = num_processed,
+                                                        "objects_prev"_a = objects_active,
+                                                        "objects_archive"_a = objects_archive, "next_ID"_a = next_id,
+                                                        "kwargs"_a = pack.assign_objects_pack.kwargs)
+                          .cast<int>();
+            ++num_processed;
+            any = true;
+        }
+    }
+    if (pack.print_timing_report)
+        std::cout << "TrackObjects: " << num_processed << " frames highlighted on the device and assigned on the host\n";
+    if (!any)
+        return py::dict{};
+    return objects_archive;
+}
+} // namespace
+
+/// NOTE: cvvidproc_b200/__init__.py re-exports these names exactly like PySources/cvvidproc/__init__.py:3
+PYBIND11_MODULE(_core, mod)
+{
+    mod.doc() = "C++ bindings for processing an opencv video"; // py_bindings.cpp:33
+
+    py::class_<VidBgPack>(mod, "VidBgPack") // py_bindings.cpp:36-60
+        .def(py::init([](const std::string &vid_path, const std::string &bg_algo, int max_threads, long long frame_limit,
+                         bool grayscale, bool vid_is_grayscale, int crop_x, int crop_y, int crop_width, int crop_height,
+                         int token_storage_limit, bool print_timing_report) {
+                 return VidBgPack{vid_path, bg_algo, max_threads, frame_limit, grayscale, vid_is_grayscale, crop_x, crop_y,
+                                  crop_width, crop_height, token_storage_limit, print_timing_report};
+             }),
+             py::arg("vid_path"), py::arg("bg_algo") = "hist", py::arg("max_threads") = -1, py::arg("frame_limit") = -1,
+             py::arg("grayscale") = false, py::arg("vid_is_grayscale") = false, py::arg("crop_x") = 0, py::arg("crop_y") = 0,
+             py::arg("crop_width") = 0, py::arg("crop_height") = 0, py::arg("token_storage_limit") = 10,
+             py::arg("print_timing_report") = false);
+
+    mod.def("GetVideoBackground", &GetVideoBackground, "Get the background of an OpenCV video.", py::arg("pack")); // :63-66
+
+    py::class_<HighlightObjectsPack>(mod, "HighlightObjectsPack") // :69-85
+        .def(py::init([](py::array background, py::array struct_element, int threshold, int threshold_lo, int threshold_hi,
+                         int min_size_hyst, int min_size_threshold, int width_border) {
+                 return HighlightObjectsPack{std::move(background), std::move(struct_element), threshold, threshold_lo,
+                                             threshold_hi, min_size_hyst, min_size_threshold, width_border};
+             }),
+             py::arg("background"), py::arg("struct_element"), py::arg("threshold"), py::arg("threshold_lo"),
+             py::arg("threshold_hi"), py::arg("min_size_hyst"), py::arg("min_size_threshold"), py::arg("width_border"));
+
+    py::class_<AssignObjectsPack>(mod, "AssignObjectsPack") // :88-95
+        .def(py::init([](py::function function, py::dict kwargs) { return AssignObjectsPack{std::move(function), std::move(kwargs)}; }),
+             "Expected signature/behavior of input func: \
+                next_ID = func(bw_frame, frames_processed, objects_prev, objects_archive, next_ID, kwargs) \
+                note: 'kwargs' should be a python dictionary",
+             py::arg("function"), py::arg("kwargs"));
+
+    py::class_<VidObjectTrackPack>(mod, "VidObjectTrackPack") // :98-126
+        .def(py::init([](const std::string &vid_path, HighlightObjectsPack highlight_objects_pack,
+                         AssignObjectsPack assign_objects_pack, int max_threads, long long start_frame, long long frame_limit,
+                         bool grayscale, bool vid_is_grayscale, int crop_x, int crop_y, int crop_width, int crop_height,
+                         int token_storage_limit, bool print_timing_report) {
+                 return VidObjectTrackPack{vid_path, std::move(highlight_objects_pack), std::move(assign_objects_pack),
+                                           max_threads, start_frame, frame_limit, grayscale, vid_is_grayscale, crop_x, crop_y,
+                                           crop_width, crop_height, token_storage_limit, print_timing_report};
+             }),
+             py::arg("vid_path"), py::arg("highlight_objects_pack"), py::arg("assign_objects_pack"),
+             py::arg("max_threads") = -1, py::arg("start_frame") = 0, py::arg("frame_limit") = -1, py::arg("grayscale") = false,
+             py::arg("vid_is_grayscale") = false, py::arg("crop_x") = 0, py::arg("crop_y") = 0, py::arg("crop_width") = 0,
+             py::arg("crop_height") = 0, py::arg("token_storage_limit") = 10, py::arg("print_timing_report") = false);
+
+    mod.def("TrackObjects", &TrackObjects, "Track objects in an OpenCV video.", py::arg("pack")); // :129-130
+}

@@ -1,0 +1,105 @@
+"""GPU end-to-end tests of the drop-in Python surface: GetVideoBackground / TrackObjects on lossless test videos,
+compared with the CPU oracles driven the way the reference drives its algos."""
+import cv2
+import numpy as np
+import pytest
+
+import cvvidproc_b200 as cvp
+import video_util
+from cvvidproc_b200 import synth
+from oracle import highlight_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gray_video(tmp_path_factory):
+    frames = synth.synth_frames(0, 60, 160, 96, 7, 8)
+    return video_util.write_lossless(tmp_path_factory.mktemp("v") / "gray.avi", frames), frames
+
+
+@pytest.fixture(scope="module")
+def color_video(tmp_path_factory):
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (25, 40, 56, 3), dtype=np.uint8)
+    return video_util.write_lossless(tmp_path_factory.mktemp("v") / "color.avi", frames), frames
+
+
+def test_background_of_gray_video(gray_video, oracle_median, capfd):
+    path, frames = gray_video
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+    assert bg.dtype == np.uint8 and bg.shape == (96, 160)
+    assert np.array_equal(bg, oracle_median(frames))
+    assert "Frames: 60; Res: 160x96; FPS: 30" in capfd.readouterr().out
+    # frame_limit (cv_vid_bg_helpers.cpp:226-229) and values beyond the video length
+    bg10 = cvp.GetVideoBackground(cvp.VidBgPack(path, frame_limit=10, vid_is_grayscale=True))
+    assert np.array_equal(bg10, oracle_median(frames[:10]))
+    bg_all = cvp.GetVideoBackground(cvp.VidBgPack(path, frame_limit=10_000, vid_is_grayscale=True))
+    assert np.array_equal(bg_all, bg)
+
+
+def test_background_crop_and_color_modes(color_video, oracle_median, capfd):
+    path, frames = color_video  # BGR as stored
+    # no grayscale flag: element-wise median over all three channels, result (H, W, 3) (ndarray_converter.cpp:141-142)
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path))
+    assert bg.shape == (40, 56, 3)
+    assert np.array_equal(bg, oracle_median(frames))
+    # grayscale=True: COLOR_RGB2GRAY applied to the frames as decoded (cv_vid_frames_generator_algo.h:152-154)
+    gray = np.stack([cv2.cvtColor(f, cv2.COLOR_RGB2GRAY) for f in frames])
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, grayscale=True))
+    assert bg.shape == (40, 56)
+    assert np.array_equal(bg, oracle_median(gray))
+    # vid_is_grayscale=True: channel 0 (:149-151); with a crop window
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True, crop_x=5, crop_y=3, crop_width=30, crop_height=20))
+    assert bg.shape == (20, 30)
+    assert np.array_equal(bg, oracle_median(np.ascontiguousarray(frames[:, 3:23, 5:35, 0])))
+    assert "(30x20 cropped)" in capfd.readouterr().out
+
+
+def _tracker(bw_frame, frames_processed, objects_prev, objects_archive, next_ID, kwargs):
+    """deterministic stand-in for the external bubble tracker: 8-connected components of the mask"""
+    assert bw_frame.dtype == np.uint8 and set(np.unique(bw_frame)) <= {0, 255}
+    n, _, stats, cent = cv2.connectedComponentsWithStats(bw_frame, connectivity=8)
+    objects_prev.clear()
+    for i in range(1, n):
+        if stats[i, cv2.CC_STAT_AREA] < kwargs["min_area"]:
+            continue
+        objects_prev[next_ID] = (frames_processed, int(stats[i, cv2.CC_STAT_AREA]))
+        objects_archive[next_ID] = {"frame": frames_processed, "area": int(stats[i, cv2.CC_STAT_AREA]),
+                                    "cx": round(float(cent[i][0]), 3), "cy": round(float(cent[i][1]), 3)}
+        next_ID += 1
+    return next_ID
+
+
+def _reference_track(frames, p, kwargs):
+    """what the reference computes: HighlightObjects per frame, then the callback strictly in order"""
+    prev, archive, nid = {}, {}, 0
+    for i, f in enumerate(frames):
+        bw = ho.highlight_objects(f.copy(), p)
+        nid = _tracker(bw, i, prev, archive, nid, kwargs)
+    return archive
+
+
+def test_track_objects_end_to_end(gray_video):
+    path, frames = gray_video
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+    p = ho.canonical_params(bg)
+    hp = cvp.HighlightObjectsPack(bg, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                                  p.min_size_threshold, p.width_border)
+    kwargs = {"min_area": 5}
+    ap = cvp.AssignObjectsPack(_tracker, kwargs)
+    archive = cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, ap, vid_is_grayscale=True))
+    want = _reference_track(frames, p, kwargs)
+    assert len(want) > 10
+    assert archive == want
+    # start_frame / frame_limit window (cv_vid_objecttrack_helpers.cpp:54-80): frames_processed restarts at 0
+    archive = cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, ap, start_frame=20, frame_limit=15, vid_is_grayscale=True))
+    assert archive == _reference_track(frames[20:35], p, kwargs)
+
+
+def test_track_objects_needs_single_channel(color_video):
+    path, frames = color_video
+    hp = cvp.HighlightObjectsPack(np.zeros((40, 56), np.uint8), np.ones((2, 2), np.uint8), 1, 1, 1, 1, 1, 1)
+    ap = cvp.AssignObjectsPack(lambda **kw: 0, {})
+    with pytest.raises(RuntimeError, match="single-channel"):
+        cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, ap))
