@@ -232,7 +232,156 @@ def run_reference_arm(args, rank: int, world: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_highlight:
+        try:  # the reference's CPU highlight path on a small host-generated sample of the C3 stream
+            from cvvidproc_b200 import synth
+
+            hw = HL_WORKLOAD
+            st = synth.synth_frames(0, 9, hw["width"], hw["height"], hw["seed"], hw["ndisks"])
+            bg = np.sort(st, axis=0)[4]
+            fr = synth.synth_frames(1000, 8, hw["width"], hw["height"], hw["seed"], hw["ndisks"])
+            rate, done, _ = cpu_highlight_rate(fr, bg, cores, seconds=10.0)
+            line["highlight"] = {"metric": "megapixel-frames/sec (per-frame highlight, 1080p)", "unit": UNIT, "value": rate,
+                                 "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                                  "sample": f"{done} frames, cv2 restatement, background = median of 9 frames"}}
+        except Exception as exc:
+            line["highlight"] = {"value": None, "error": str(exc)}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# highlight stage (second half of the BASELINE metric): reported as an extra object on the same line
+# ------------------------------------------------------------------------------------------------
+HL_WORKLOAD = dict(name="C3: 1920x1080 uint8 frames, per-frame highlight (BASELINE.json configs[2]), background = "
+                        "device median of the stream's first 255 frames, canonical parameters",
+                   width=1920, height=1080, seed=3, ndisks=30, frames_per_step=64)
+
+
+def cpu_highlight_rate(frames: np.ndarray, bg: np.ndarray, threads: int, seconds: float = 12.0):
+    """cv2 restatement of highlight_objects_algo.cpp (oracle/highlight_oracle.py), one frame per task, cv2 internal
+    threading off, `threads` Python threads (cv2 releases the GIL) -- the reference's frame-level data parallelism
+    (cv_vid_objecttrack_helpers.cpp:72-84).  Returns (Mpx-frames/s, frames done, last mask)."""
+    import concurrent.futures as cf
+
+    import cv2
+
+    from oracle import highlight_oracle as ho
+
+    cv2.setNumThreads(1)
+    p = ho.canonical_params(bg)
+    n = frames.shape[0]
+    done = 0
+    last = None
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=threads) as ex:
+        while time.perf_counter() - t0 < seconds:
+            res = list(ex.map(lambda i: ho.highlight_objects(frames[i % n].copy(), p), range(done, done + 2 * threads)))
+            done += len(res)
+            last = res[-1]
+    dt = time.perf_counter() - t0
+    return frames.shape[1] * frames.shape[2] * done / 1e6 / dt, done, last
+
+
+def run_highlight_section(ctx, torch, dist, rank, local_rank, world, args, sampler, stream):
+    """Frames are sharded over ranks by frame (no collective on the data path: frames are independent,
+    highlight_objects_algo.h:82-85); each rank processes frames_per_step frames per step."""
+    from oracle import highlight_oracle as ho
+
+    w = HL_WORKLOAD
+    W, H, nfr = w["width"], w["height"], w["frames_per_step"]
+    npix = W * H
+    dev = f"cuda:{local_rank}"
+    bgstack = torch.empty((255, npix), dtype=torch.uint8, device=dev)
+    bg = torch.empty(npix, dtype=torch.uint8, device=dev)
+    ctx.synth_frames_device(bgstack.data_ptr(), npix, W, H, 0, 255, w["seed"], w["ndisks"])
+    ctx.median_device(bgstack.data_ptr(), 255, npix, npix, bg.data_ptr())
+    ctx.synchronize()
+    del bgstack
+    bg_h = bg.cpu().numpy().reshape(H, W)
+    p = ho.canonical_params(bg_h)
+    frames = torch.empty((nfr, npix), dtype=torch.uint8, device=dev)
+    masks = torch.empty((nfr, npix), dtype=torch.uint8, device=dev)
+    first = 1000 + rank * nfr  # this rank's frames of the stream
+    ctx.synth_frames_device(frames.data_ptr(), npix, W, H, first, nfr, w["seed"], w["ndisks"])
+    ctx.highlight_begin(p.background, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                        p.min_size_threshold, p.width_border)
+    steps = max(3, min(args.steps, 10))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            ctx.highlight_device(frames.data_ptr(), nfr, npix, masks.data_ptr(), npix)
+        barrier()
+        l0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active = True
+        e0.record(stream)
+        for _ in range(steps):
+            ctx.highlight_device(frames.data_ptr(), nfr, npix, masks.data_ptr(), npix)
+        e1.record(stream)
+        barrier()
+        sampler.active = False
+        launches = ctx.launch_count - l0
+    ms = e0.elapsed_time(e1) / steps
+    # end to end from pinned host memory through cvvp_highlight_frames
+    from cvvidproc_b200 import _cabi
+
+    pin_in = _cabi.PinnedBuffer(nfr * npix)
+    pin_out = _cabi.PinnedBuffer(nfr * npix)
+    pin_in.array[:] = frames.cpu().numpy().reshape(-1)
+    lib = _cabi.load()
+
+    def e2e_step():
+        rc = lib.cvvp_highlight_frames(ctx.handle, pin_in.array.ctypes.data, nfr, npix, pin_out.array.ctypes.data, npix)
+        if rc != 0:
+            raise RuntimeError(lib.cvvp_last_error(ctx.handle).decode())
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / steps
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    total_mpx = world * nfr * npix / 1e6
+    same = bool(np.array_equal(pin_out.array.reshape(nfr, npix), masks.cpu().numpy()))
+    out = {
+        "metric": "megapixel-frames/sec (per-frame highlight, 1080p)", "unit": UNIT,
+        "value": total_mpx / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": world * nfr, "steps": steps,
+        "gpu_launches": int(launches), "scaling": "weak", "sharding": "by frame, no collective",
+        "e2e": {"value": total_mpx / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nfr * npix),
+                "d2h_bytes_per_step": int(nfr * npix), "ms_per_step": e2e_s * 1e3},
+        "roofline": {"bound": "hbm", "achieved": 2.0 * nfr * npix / (ms * 1e-3) / 1e9, "peak": load_peaks()[0],
+                     "unit": "GB/s", "frac": 2.0 * nfr * npix / (ms * 1e-3) / 1e9 / load_peaks()[0],
+                     "traffic": None, "note": "algorithmic bytes = frame in + mask out (2 B/px); ~35 kernels per batch"},
+        "config": {"workload": w["name"]},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            host_frames = frames[:16].cpu().numpy().reshape(16, H, W)
+            cores = os.cpu_count() or 1
+            rate, done, last = cpu_highlight_rate(host_frames, bg_h, cores)
+            idx = (done - 1) % 16
+            same = same and bool(np.array_equal(last.reshape(-1), masks[idx].cpu().numpy()))
+            out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{done} frames in ~12 s, cv2 4.x restatement of highlight_objects_algo.cpp, "
+                                             f"{cores} threads x cv2.setNumThreads(1)"}
+        except Exception as exc:
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "unavailable",
+                                   "sample": f"failed: {exc}"}
+    out["parity_spot_check"] = same
+    ctx.highlight_end()
+    pin_in.close()
+    pin_out.close()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -383,6 +532,17 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "unavailable",
                             "sample": f"failed: {exc}"}
     pinned.close()
+    del stack
+
+    highlight = None
+    if not args.no_highlight:
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
+        try:
+            highlight = run_highlight_section(ctx, torch, dist, rank, local_rank, world, args, sampler2, stream)
+            highlight["clocks"] = sampler2.summary()
+        finally:
+            sampler2.stop()
 
     if rank == 0:
         line = {
@@ -399,6 +559,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "parity_spot_check": same,
+            "highlight": highlight,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -413,6 +574,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-highlight", action="store_true", help="skip the highlight-stage section")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
