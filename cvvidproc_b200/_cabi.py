@@ -67,6 +67,8 @@ def load():
         "cvvp_highlight_frames": (i32, [vp, vp, i64, sz, vp, sz]),
         "cvvp_highlight_device": (i32, [vp, vp, i64, sz, vp, sz, vp]),
         "cvvp_highlight_end": (i32, [vp]),
+        "cvvp_highlight_set_path": (i32, [vp, i32]),
+        "cvvp_highlight_frames_in_flight": (i32, [vp, C.POINTER(i32)]),
         "cvvp_synth_frames_device": (i32, [vp, vp, sz, i32, i32, i32, i32, i64, i64, u32, i32, vp]),
     }
     global BOUND_SYMBOLS
@@ -251,6 +253,15 @@ class Context:
 
     def highlight_device(self, d_frames: int, n: int, frame_stride: int, d_out: int, out_stride: int, stream: int = 0):
         self._check(self._lib.cvvp_highlight_device(self._h, d_frames, n, frame_stride, d_out, out_stride, stream or None))
+
+    def highlight_set_path(self, path: int):
+        """0 = fused kernel (default), 1 = per-pixel kernels (on-device cross-check)"""
+        self._check(self._lib.cvvp_highlight_set_path(self._h, path))
+
+    def highlight_frames_in_flight(self) -> int:
+        v = C.c_int()
+        self._check(self._lib.cvvp_highlight_frames_in_flight(self._h, C.byref(v)))
+        return int(v.value)
 
     def highlight_end(self):
         self._check(self._lib.cvvp_highlight_end(self._h))

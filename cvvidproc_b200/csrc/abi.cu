@@ -512,6 +512,21 @@ int cvvp_highlight_end(cvvp_ctx *ctx)
     return CVVP_OK;
 }
 
+int cvvp_highlight_set_path(cvvp_ctx *ctx, int path)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    return highlight_set_path(ctx, path);
+}
+
+int cvvp_highlight_frames_in_flight(cvvp_ctx *ctx, int *out_frames)
+{
+    if (!ctx || !out_frames)
+        return fail(ctx, CVVP_ERR_INVALID, "null argument");
+    DeviceGuard guard(ctx->device);
+    return highlight_frames_in_flight(ctx, out_frames);
+}
+
 int cvvp_synth_frames_device(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width, int height, int row0,
                              int nrows, long long first_frame, long long nframes, uint32_t seed, int ndisks, void *stream)
 {

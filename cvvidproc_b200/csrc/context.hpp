@@ -36,7 +36,7 @@ struct MedianJob {
     size_t d_out_bytes{0};
     size_t d_stack_bytes{0};
 };
-struct HighlightState; // highlight.cu
+struct HighlightState; // highlight_state.hpp
 } // namespace cvvp
 
 struct cvvp_ctx {
@@ -107,6 +107,8 @@ int highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, int hei
                     int threshold, int threshold_lo, int threshold_hi, int min_size_hyst, int min_size_threshold);
 int highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride, uint8_t *d_out,
                      size_t out_stride, cudaStream_t stream);
+int highlight_set_path(cvvp_ctx *ctx, int path);
+int highlight_frames_in_flight(cvvp_ctx *ctx, int *out_frames);
 int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, uint8_t *masks_out,
                           size_t out_stride);
 // synth.cu

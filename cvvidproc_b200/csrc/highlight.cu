@@ -25,8 +25,9 @@
 //
 // Layout: every kernel takes blockIdx.z = frame of the batch.  Masks are u8 0/1 (npix per frame), label / statistic
 // arrays are u32 / i32 with npix + 1 entries per frame (entry npix = the FRAME node).
-#include "context.hpp"
+#include "highlight_state.hpp"
 
+#include <new>
 #include <vector>
 
 namespace cvvp
@@ -34,13 +35,6 @@ namespace cvvp
 namespace
 {
 constexpr uint32_t kNoLabel = 0xFFFFFFFFu;
-
-struct HlGeom {
-    int W, H;
-    uint32_t npix;    // W * H
-    uint32_t lstride; // label-array stride per frame (npix + 1, padded to 4)
-    uint32_t mstride; // mask stride per frame (npix padded to 16)
-};
 
 // ------------------------------------------------------------------------------------------------------------------
 // union-find primitives (labels only ever decrease; stale reads are harmless)
@@ -529,23 +523,6 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-struct HighlightState {
-    HlGeom g{};
-    int th{}, lo{}, hi{}, min_hyst{}, min_th{};
-    int noffs{0};
-    int batch_cap{0};
-    uint8_t *d_bg{nullptr};
-    short2 *d_offs{nullptr};
-    // per-batch work buffers
-    uint8_t *m_a{nullptr}, *m_u{nullptr}, *m_l{nullptr}, *m_t{nullptr}, *m_out{nullptr};
-    uint32_t *lab0{nullptr}, *lab1{nullptr};
-    int *st_s{nullptr}, *st_e{nullptr}, *st_x{nullptr};
-    int *d_th{nullptr};
-    unsigned int *d_hist{nullptr};
-    uint8_t *d_in{nullptr}, *d_res{nullptr}; // staging for the host-buffer entry point
-    size_t in_bytes{0};
-};
-
 namespace
 {
 void free_state(HighlightState *s)
@@ -557,6 +534,7 @@ void free_state(HighlightState *s)
     for (void *p : ptrs)
         if (p)
             cudaFree(p);
+    fused_release(s);
     delete s;
 }
 
@@ -680,8 +658,7 @@ static int ensure_batch(cvvp_ctx *ctx, HighlightState *st, int nb)
     if (nb <= st->batch_cap)
         return CVVP_OK;
     void **bufs[] = {(void **)&st->m_a, (void **)&st->m_u, (void **)&st->m_l, (void **)&st->m_t, (void **)&st->m_out,
-                     (void **)&st->lab0, (void **)&st->lab1, (void **)&st->st_s, (void **)&st->st_e, (void **)&st->st_x,
-                     (void **)&st->d_th, (void **)&st->d_hist};
+                     (void **)&st->lab0, (void **)&st->lab1, (void **)&st->st_s, (void **)&st->st_e, (void **)&st->st_x};
     for (void **b : bufs) {
         if (*b)
             cudaFree(*b);
@@ -693,14 +670,42 @@ static int ensure_batch(cvvp_ctx *ctx, HighlightState *st, int nb)
     if ((rc = dev_alloc(ctx, &st->m_a, m)) || (rc = dev_alloc(ctx, &st->m_u, m)) || (rc = dev_alloc(ctx, &st->m_l, m)) ||
         (rc = dev_alloc(ctx, &st->m_t, m)) || (rc = dev_alloc(ctx, &st->m_out, m)) || (rc = dev_alloc(ctx, &st->lab0, l)) ||
         (rc = dev_alloc(ctx, &st->lab1, l)) || (rc = dev_alloc(ctx, &st->st_s, l)) || (rc = dev_alloc(ctx, &st->st_e, l)) ||
-        (rc = dev_alloc(ctx, &st->st_x, l)) || (rc = dev_alloc(ctx, &st->d_th, size_t(nb))) ||
-        (rc = dev_alloc(ctx, &st->d_hist, size_t(nb) * 256)))
+        (rc = dev_alloc(ctx, &st->st_x, l)))
         return rc;
     st->batch_cap = nb;
     return CVVP_OK;
 }
 
-// frames per launch batch: enough work to fill the GPU, bounded scratch memory (~37 bytes per pixel per frame)
+// per-frame thresholds of branch A for nb frames -> st->d_th: the constant, or Otsu's per frame (threshold == -1, :89-95)
+int highlight_thresholds(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, size_t frame_stride, unsigned nb,
+                         cudaStream_t stream)
+{
+    if (int(nb) > st->th_cap) {
+        // the previous arrays may still be in use by work queued on `stream`
+        cudaStreamSynchronize(stream);
+        if (st->d_th) cudaFree(st->d_th);
+        if (st->d_hist) cudaFree(st->d_hist);
+        st->d_th = nullptr;
+        st->d_hist = nullptr;
+        st->th_cap = 0;
+        int rc;
+        if ((rc = dev_alloc(ctx, &st->d_th, size_t(nb))) || (rc = dev_alloc(ctx, &st->d_hist, size_t(nb) * 256)))
+            return rc;
+        st->th_cap = int(nb);
+    }
+    if (st->th == -1) {
+        cudaMemsetAsync(st->d_hist, 0, size_t(nb) * 256 * sizeof(unsigned int), stream);
+        diff_hist_kernel<<<dim3(64, 1, nb), 256, 0, stream>>>(in, frame_stride, st->d_bg, st->g, st->d_hist);
+        otsu_kernel<<<(nb + 63) / 64, 64, 0, stream>>>(st->d_hist, st->g.npix, st->d_th, int(nb));
+        ctx->launches += 2;
+    } else {
+        fill_int_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(st->d_th, st->th, int(nb));
+        ctx->launches += 1;
+    }
+    return CVVP_OK;
+}
+
+// per-pixel path: frames per launch batch: enough work to fill the GPU, bounded scratch (~37 bytes per pixel per frame)
 static int pick_batch(const HighlightState *st, long long n)
 {
     const long long by_mem = (3ll << 30) / (37ll * st->g.npix + 64);
@@ -712,16 +717,9 @@ static int pick_batch(const HighlightState *st, long long n)
     return int(b);
 }
 
-int highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride, uint8_t *d_out,
-                     size_t out_stride, cudaStream_t stream)
+static int highlight_pixels(cvvp_ctx *ctx, HighlightState *st, const uint8_t *d_frames, long long n, size_t frame_stride,
+                            uint8_t *d_out, size_t out_stride, cudaStream_t stream)
 {
-    HighlightState *st = ctx->hl;
-    if (!st)
-        return fail(ctx, CVVP_ERR_STATE, "highlight: no parameters set (call cvvp_highlight_begin first)");
-    if (!d_frames || !d_out || n < 0 || frame_stride < st->g.npix || out_stride < st->g.npix)
-        return fail(ctx, CVVP_ERR_INVALID, "highlight: bad arguments");
-    if (n == 0)
-        return CVVP_OK;
     const int bcap = pick_batch(st, n);
     int rc = ensure_batch(ctx, st, bcap);
     if (rc != CVVP_OK)
@@ -730,16 +728,8 @@ int highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t
         const unsigned nb = unsigned(n - done < bcap ? n - done : bcap);
         const uint8_t *in = d_frames + size_t(done) * frame_stride;
         Launcher L{ctx, stream, st->g, nb};
-        // thresholds of branch A: constant, or Otsu per frame
-        if (st->th == -1) {
-            cudaMemsetAsync(st->d_hist, 0, size_t(nb) * 256 * sizeof(unsigned int), stream);
-            diff_hist_kernel<<<dim3(64, 1, nb), 256, 0, stream>>>(in, frame_stride, st->d_bg, st->g, st->d_hist);
-            otsu_kernel<<<(nb + 63) / 64, 64, 0, stream>>>(st->d_hist, st->g.npix, st->d_th, int(nb));
-            ctx->launches += 2;
-        } else {
-            fill_int_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(st->d_th, st->th, int(nb));
-            ctx->launches += 1;
-        }
+        if ((rc = highlight_thresholds(ctx, st, in, frame_stride, nb, stream)) != CVVP_OK)
+            return rc;
         diff_thresh_kernel<<<L.per_pixel(), 256, 0, stream>>>(in, frame_stride, st->d_bg, st->g, st->d_th, st->lo, st->hi,
                                                               nullptr, st->m_a, st->m_u, st->m_l);
         ctx->launches += 1;
@@ -766,6 +756,58 @@ int highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t
     return CVVP_OK;
 }
 
+static bool use_fused(const HighlightState *st)
+{
+    return st->path == kPathFused && fused_supports(st);
+}
+
+int highlight_set_path(cvvp_ctx *ctx, int path)
+{
+    HighlightState *st = ctx->hl;
+    if (!st)
+        return fail(ctx, CVVP_ERR_STATE, "highlight: no parameters set (call cvvp_highlight_begin first)");
+    if (path != kPathFused && path != kPathPixel)
+        return fail(ctx, CVVP_ERR_INVALID, "highlight: unknown device path %d", path);
+    st->path = path;
+    return CVVP_OK;
+}
+
+int highlight_frames_in_flight(cvvp_ctx *ctx, int *out_frames)
+{
+    HighlightState *st = ctx->hl;
+    if (!st)
+        return fail(ctx, CVVP_ERR_STATE, "highlight: no parameters set (call cvvp_highlight_begin first)");
+    *out_frames = fused_supports(st) ? fused_frames_in_flight(ctx, st) : 0;
+    return CVVP_OK;
+}
+
+int highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride, uint8_t *d_out,
+                     size_t out_stride, cudaStream_t stream)
+{
+    HighlightState *st = ctx->hl;
+    if (!st)
+        return fail(ctx, CVVP_ERR_STATE, "highlight: no parameters set (call cvvp_highlight_begin first)");
+    if (!d_frames || !d_out || n < 0 || frame_stride < st->g.npix || out_stride < st->g.npix)
+        return fail(ctx, CVVP_ERR_INVALID, "highlight: bad arguments");
+    if (n == 0)
+        return CVVP_OK;
+    if (!use_fused(st))
+        return highlight_pixels(ctx, st, d_frames, n, frame_stride, d_out, out_stride, stream);
+    // fused path: one launch per (up to) 2^20 frames; scratch is per resident CTA, not per frame
+    const long long bmax = 1ll << 20;
+    for (long long done = 0; done < n; done += bmax) {
+        const unsigned nb = unsigned(n - done < bmax ? n - done : bmax);
+        const uint8_t *in = d_frames + size_t(done) * frame_stride;
+        int rc;
+        if (st->th == -1 && (rc = highlight_thresholds(ctx, st, in, frame_stride, nb, stream)) != CVVP_OK)
+            return rc;
+        if ((rc = highlight_fused_batch(ctx, st, in, frame_stride, nb, d_out + size_t(done) * out_stride, out_stride,
+                                        stream)) != CVVP_OK)
+            return rc;
+    }
+    return CVVP_OK;
+}
+
 int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, uint8_t *masks_out,
                           size_t out_stride)
 {
@@ -776,9 +818,19 @@ int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
         return fail(ctx, CVVP_ERR_INVALID, "highlight: bad arguments");
     if (n == 0)
         return CVVP_OK;
-    // chunked: H2D on the copy stream, kernels + D2H on the compute stream
-    const long long chunk = pick_batch(st, n);
-    const size_t need = size_t(chunk) * st->g.npix;
+    // chunked: H2D on the copy stream, kernels + D2H on the compute stream.  The device side is far faster than the
+    // link, so chunks are sized for the copies (~64 MB) rather than for the kernel.
+    long long chunk;
+    if (use_fused(st)) {
+        chunk = (64ll << 20) / st->g.npix;
+        if (chunk < 8) chunk = 8;
+        if (chunk > n) chunk = n;
+    } else {
+        chunk = pick_batch(st, n);
+    }
+    const size_t np = st->g.npix;
+    const size_t pitch = (np + 127) & ~size_t(127); // device frame pitch: keeps every frame 16-byte aligned
+    const size_t need = size_t(chunk) * pitch;
     if (st->in_bytes < need) {
         if (st->d_in) cudaFree(st->d_in);
         if (st->d_res) cudaFree(st->d_res);
@@ -789,7 +841,7 @@ int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
             return rc;
         st->in_bytes = need;
     }
-    const size_t np = st->g.npix;
+    const size_t half = st->in_bytes;
     cudaEvent_t up[2] = {nullptr, nullptr}, down[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming);
@@ -800,11 +852,11 @@ int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
     for (long long done = 0; done < n && rc == CVVP_OK; done += chunk, ++idx) {
         const long long nb = n - done < chunk ? n - done : chunk;
         const int b = int(idx & 1);
-        uint8_t *din = st->d_in + size_t(b) * need;
-        uint8_t *dres = st->d_res + size_t(b) * need;
+        uint8_t *din = st->d_in + size_t(b) * half;
+        uint8_t *dres = st->d_res + size_t(b) * half;
         if (idx >= 2)
             cudaStreamWaitEvent(ctx->copy, down[b], 0); // this half's previous results have left the device
-        cudaError_t e = cudaMemcpy2DAsync(din, np, frames + size_t(done) * frame_stride, frame_stride, np, size_t(nb),
+        cudaError_t e = cudaMemcpy2DAsync(din, pitch, frames + size_t(done) * frame_stride, frame_stride, np, size_t(nb),
                                           cudaMemcpyHostToDevice, ctx->copy);
         if (e != cudaSuccess) {
             rc = fail(ctx, CVVP_ERR_CUDA, "highlight: H2D failed: %s", cudaGetErrorString(e));
@@ -812,10 +864,10 @@ int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
         }
         cudaEventRecord(up[b], ctx->copy);
         cudaStreamWaitEvent(ctx->compute, up[b], 0);
-        rc = highlight_device(ctx, din, nb, np, dres, np, ctx->compute);
+        rc = highlight_device(ctx, din, nb, pitch, dres, pitch, ctx->compute);
         if (rc != CVVP_OK)
             break;
-        e = cudaMemcpy2DAsync(masks_out + size_t(done) * out_stride, out_stride, dres, np, np, size_t(nb),
+        e = cudaMemcpy2DAsync(masks_out + size_t(done) * out_stride, out_stride, dres, pitch, np, size_t(nb),
                               cudaMemcpyDeviceToHost, ctx->compute);
         if (e != cudaSuccess) {
             rc = fail(ctx, CVVP_ERR_CUDA, "highlight: D2H failed: %s", cudaGetErrorString(e));

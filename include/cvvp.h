@@ -131,6 +131,14 @@ CVVP_API int cvvp_highlight_frames(cvvp_ctx *ctx, const uint8_t *frames, long lo
 CVVP_API int cvvp_highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride,
                                    uint8_t *d_out, size_t out_stride, void *stream);
 CVVP_API int cvvp_highlight_end(cvvp_ctx *ctx);
+/* Device implementation used by the calls above (after cvvp_highlight_begin; both give identical masks):
+ *   0 = fused (default): one persistent-CTA kernel launch per batch, run-based labelling (csrc/highlight_fused.cu)
+ *   1 = per-pixel kernels (csrc/highlight.cu), ~35 launches per batch; kept as an on-device cross-check.
+ * Has no counterpart in the reference; it exists so that tests can hold the two device paths to each other at sizes
+ * where the CPU oracle is slow. */
+CVVP_API int cvvp_highlight_set_path(cvvp_ctx *ctx, int path);
+/* Frames the fused kernel keeps in flight on this device (= resident CTAs; one scratch slot each). */
+CVVP_API int cvvp_highlight_frames_in_flight(cvvp_ctx *ctx, int *out_frames);
 
 /* ---------------------------------------------------------------------------------------------
  * synthetic input: deterministic integer-hash frames generated directly in

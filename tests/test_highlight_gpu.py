@@ -13,10 +13,14 @@ from oracle import highlight_oracle as ho
 pytestmark = pytest.mark.gpu
 
 
-def _gpu(ctx, frames, p):
+FUSED, PIXEL = 0, 1  # cvvp_highlight_set_path: the fused persistent-CTA kernel (default) / the per-pixel kernels
+
+
+def _gpu(ctx, frames, p, path=FUSED):
     ctx.highlight_begin(p.background, np.ascontiguousarray(p.struct_element), p.threshold, p.threshold_lo, p.threshold_hi,
                         p.min_size_hyst, p.min_size_threshold, p.width_border)
     try:
+        ctx.highlight_set_path(path)
         return ctx.highlight_frames(frames)
     finally:
         ctx.highlight_end()
@@ -39,6 +43,52 @@ def test_adversarial_frames_match_oracle(gpu_ctx, case):
     got = _gpu(gpu_ctx, frame[None], p)[0]
     want = ho.highlight_objects(frame.copy(), p)
     assert np.array_equal(got, want), f"{(got != want).sum()} pixels differ"
+
+
+@pytest.mark.parametrize("t", range(0, 60, 7))
+def test_pixel_path_random_frames_match_oracle(gpu_ctx, t):
+    """the per-pixel kernels stay held to the oracle: they are the on-device cross-check of the fused kernel"""
+    frame, p = hl_cases.random_case(t)
+    got = _gpu(gpu_ctx, frame[None], p, PIXEL)[0]
+    assert np.array_equal(got, ho.highlight_objects(frame.copy(), p))
+
+
+@pytest.mark.parametrize("case", ADV[::3], ids=[c[0] for c in ADV[::3]])
+def test_pixel_path_adversarial_frames_match_oracle(gpu_ctx, case):
+    _, frame, p = case
+    got = _gpu(gpu_ctx, frame[None], p, PIXEL)[0]
+    assert np.array_equal(got, ho.highlight_objects(frame.copy(), p))
+
+
+@pytest.mark.parametrize("hw", [(40, 32), (33, 64), (50, 96), (21, 128), (30, 160), (24, 288), (17, 640), (9, 1056)])
+def test_word_aligned_widths_match_oracle(gpu_ctx, hw):
+    """W % 32 == 0 takes the 128-bit load/store path of the fused kernel; row pitches that are / are not powers of two"""
+    h, w = hw
+    for seed in range(3):
+        frame, bg = hl_cases.blob_frame(h, w, 300 + seed, sigma=2.0, amp=70)
+        for p in (ho.canonical_params(bg),
+                  ho.HighlightParams(bg, np.ones((1, 1), np.uint8), 12, 6, 20, 0, 3, 5),
+                  ho.HighlightParams(bg, np.ones((3, 2), np.uint8), -1, 9, 14, 10, 30, 5)):
+            got = _gpu(gpu_ctx, frame[None], p)[0]
+            want = ho.highlight_objects(frame.copy(), p)
+            assert np.array_equal(got, want), f"{(got != want).sum()} pixels differ at {h}x{w} seed {seed}"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_noise_frames_match_oracle(gpu_ctx, seed):
+    """salt-and-pepper difference images: the run count approaches the pixel count (worst case of the run-based
+    labelling), nesting is deep and almost every contour is small"""
+    rng = np.random.default_rng(7000 + seed)
+    h, w = int(rng.integers(20, 80)), int(rng.choice([31, 64, 75, 96]))
+    bg = np.full((h, w), 128, np.uint8)
+    frame = (128 - rng.integers(0, 40, (h, w))).astype(np.uint8)
+    one = np.ones((1, 1), np.uint8)
+    for p in (ho.HighlightParams(bg, one, 20, 10, 30, int(rng.choice([0, 2, 6])), int(rng.choice([0, 2, 6])), 5),
+              ho.HighlightParams(bg, one, 5, 30, 8, 4, 0, 5),
+              ho.canonical_params(bg)):
+        got = _gpu(gpu_ctx, frame[None], p)[0]
+        want = ho.highlight_objects(frame.copy(), p)
+        assert np.array_equal(got, want), f"{(got != want).sum()} pixels differ"
 
 
 def test_golden_hashes(gpu_ctx):
@@ -94,6 +144,34 @@ def test_full_hd_synthetic_frames(gpu_ctx):
     for i in range(frames.shape[0]):
         want = ho.highlight_objects(frames[i].copy(), p)
         assert np.array_equal(got[i], want), f"frame {i}: {(got[i] != want).sum()} pixels differ"
+
+
+def test_fused_and_pixel_paths_agree_at_full_hd(gpu_ctx):
+    """device vs device at the BASELINE geometry, more frames than the kernel keeps in flight (the frame queue wraps and
+    every scratch slot is reused), plus two frames of pure noise"""
+    from cvvidproc_b200 import synth
+
+    p_ = synth.CONFIG_PARAMS["C3"]
+    w, h = p_["width"], p_["height"]
+    stack = synth.synth_frames(0, 15, w, h, p_["seed"], p_["ndisks"])
+    bg = np.sort(stack, axis=0)[7]
+    p = ho.canonical_params(bg)
+    gpu_ctx.highlight_begin(p.background, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                            p.min_size_threshold, p.width_border)
+    in_flight = gpu_ctx.highlight_frames_in_flight()
+    gpu_ctx.highlight_end()
+    assert in_flight >= 1
+    n = min(in_flight + 37, 420)
+    frames = np.stack([synth.synth_frame(1000 + 3 * i, w, h, p_["seed"], p_["ndisks"]) for i in range(n)])
+    rng = np.random.default_rng(5)
+    frames[5] = (bg.astype(np.int32) - rng.integers(0, 30, bg.shape)).clip(0, 255).astype(np.uint8)
+    frames[n - 2] = (bg.astype(np.int32) - rng.integers(0, 18, bg.shape)).clip(0, 255).astype(np.uint8)
+    fused = _gpu(gpu_ctx, frames, p, FUSED)
+    pixel = _gpu(gpu_ctx, frames, p, PIXEL)
+    for i in range(n):
+        assert np.array_equal(fused[i], pixel[i]), f"frame {i}: {(fused[i] != pixel[i]).sum()} pixels differ"
+    for i in (0, 5, n - 1):
+        assert np.array_equal(fused[i], ho.highlight_objects(frames[i].copy(), p)), f"frame {i} vs oracle"
 
 
 def test_argument_errors(gpu_ctx):
