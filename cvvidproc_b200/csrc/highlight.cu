@@ -639,6 +639,9 @@ int highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, int hei
     if (offs.empty())
         offs.push_back(make_short2(short(-ax), short(-ay)));
     st->noffs = int(offs.size());
+    st->h_offs = offs;
+    st->dy_min = offs.front().y;
+    st->dy_max = offs.back().y;
     int rc;
     if ((rc = dev_alloc(ctx, &st->d_bg, st->g.npix)) != CVVP_OK || (rc = dev_alloc(ctx, &st->d_offs, offs.size())) != CVVP_OK) {
         highlight_release(ctx);

@@ -27,6 +27,8 @@
 
 #include <climits>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 namespace cvvp
 {
@@ -43,6 +45,25 @@ struct ThreshSpec {
     uint32_t t4;       // threshold replicated into four bytes (clamped to 0..254)
     uint32_t force_or; // all-ones when the threshold is negative (every pixel passes)
     uint32_t force_and; // zero when the threshold is >= 255 (no pixel passes)
+};
+
+// Separable form of the structuring element: its tap rows grouped by their set of column offsets ("patterns").  A
+// pattern's horizontal erosion / dilation of a tile row is computed once and shared by every tap row that uses it, so
+// the vertical step is a plain AND / OR of words.  (The reference's usual ellipse has two patterns: one tap, and a full
+// row.)  Used when there are at most kMaxPat patterns and |dx| <= 31; other elements take the generic tap loop.
+constexpr int kMaxPat = 3;
+constexpr int kMaxPlanRows = 64;
+constexpr int kMaxPlanTaps = 96;
+
+struct MorphPlan {
+    int sep;    // 1 = separable path usable
+    int npat;   // distinct patterns
+    int nrows;  // tap rows
+    signed char row_dy[kMaxPlanRows];
+    signed char row_pat[kMaxPlanRows];
+    signed char pat_ident[kMaxPat];     // pattern == {0}: the tile itself
+    unsigned char pat_start[kMaxPat + 1]; // pattern p's offsets are dx[pat_start[p] .. pat_start[p + 1])
+    signed char dx[kMaxPlanTaps];
 };
 
 struct FusedArgs {
@@ -66,6 +87,11 @@ struct FusedArgs {
     unsigned *queue; // [0] next frame, [1] CTAs finished
     unsigned nframes;
     int fast_io; // W % 32 == 0 and 16-byte aligned pointers / strides
+    uint32_t smem_words; // dynamic shared memory of the CTA, in 32-bit words
+    // opening in shared-memory row bands (0 rows = structuring element too large: global-memory taps instead)
+    int band_rows, dy_min, dy_max, pad_words;
+    MorphPlan plan;
+    unsigned long long *prof; // per-phase nanoseconds summed over frames (CVVP_HL_PROF=1), or nullptr
     int debug_stage; // 0 = off; k > 0: write the bit image of intermediate stage k instead of the result (tools/)
 };
 
@@ -75,7 +101,13 @@ struct RunSet {
     uint32_t *rowoff; // [H + 1]; rowoff[H] = T
 };
 
+enum ProfPhase {
+    kPBits, kPErodeA, kPDilateA, kPExtract, kPMerge, kPFlatten, kPRso, kPFill, kPHyst, kPErodeB, kPDilateB, kPExpand,
+    kPRuns, kPFrames, kPCount
+};
+
 struct Shared {
+    unsigned long long prof_last;
     unsigned frame;
     uint32_t wsum[NW];
     uint32_t T[2];
@@ -85,6 +117,24 @@ struct Shared {
 // ------------------------------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// developer aid: thread 0 charges the time since the previous tick to `phase`
+__device__ __forceinline__ void prof_tick(const unsigned long long *enabled, unsigned long long *acc, Shared &sh, int phase)
+{
+    if (enabled && threadIdx.x == 0) {
+        const unsigned long long t = global_ns();
+        if (phase >= 0)
+            atomicAdd(acc + phase, t - sh.prof_last);
+        sh.prof_last = t;
+    }
+}
+
 __device__ __forceinline__ uint32_t ld(const uint32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ int ld(const int *p) { return __ldcg(p); }
 __device__ __forceinline__ void st(uint32_t *p, uint32_t v) { __stcg(p, v); }
@@ -116,28 +166,50 @@ __device__ __forceinline__ uint32_t range_mask(int lo, int hi) // bits lo..hi (0
     return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
 }
 
-__device__ __forceinline__ uint32_t uf_find(const uint32_t *lab, uint32_t x)
+// The parent array of the union-find lives in shared memory while a frame's run count fits (the usual case: a few
+// thousand runs), else in the slot's global scratch.  Labels only ever decrease, so a stale read is harmless: every
+// link is re-validated by the atomicMin that makes it.
+template <bool SM>
+struct Par {
+    uint32_t *p;
+    __device__ __forceinline__ uint32_t get(uint32_t i) const
+    {
+        return SM ? *reinterpret_cast<volatile uint32_t *>(p + i) : __ldcg(p + i);
+    }
+    __device__ __forceinline__ void set(uint32_t i, uint32_t v) const
+    {
+        if (SM)
+            *reinterpret_cast<volatile uint32_t *>(p + i) = v;
+        else
+            __stcg(p + i, v);
+    }
+    __device__ __forceinline__ uint32_t amin(uint32_t i, uint32_t v) const { return atomicMin(p + i, v); }
+};
+
+template <bool SM>
+__device__ __forceinline__ uint32_t uf_find(const Par<SM> &lab, uint32_t x)
 {
-    uint32_t p = ld(lab + x);
+    uint32_t p = lab.get(x);
     while (p != x) {
         x = p;
-        p = ld(lab + x);
+        p = lab.get(x);
     }
     return x;
 }
 
-__device__ __forceinline__ void uf_union(uint32_t *lab, uint32_t a, uint32_t b)
+template <bool SM>
+__device__ __forceinline__ void uf_union(const Par<SM> &lab, uint32_t a, uint32_t b)
 {
     bool done;
     do {
         a = uf_find(lab, a);
         b = uf_find(lab, b);
         if (a < b) {
-            const uint32_t old = atomicMin(&lab[b], a);
+            const uint32_t old = lab.amin(b, a);
             done = (old == b);
             b = old;
         } else if (b < a) {
-            const uint32_t old = atomicMin(&lab[a], b);
+            const uint32_t old = lab.amin(a, b);
             done = (old == a);
             a = old;
         } else {
@@ -368,6 +440,297 @@ __device__ void morph_phase(const FusedArgs &P, const uint32_t *src, uint32_t *d
     }
 }
 
+// Opening through shared-memory row bands: a band of source rows (plus the halo both steps need) is staged once with
+// 128-bit loads, eroded into a second tile and dilated from there straight into `dst` (a different image), so the
+// image makes one trip through L2 instead of four and every tap is a shared-memory access.  Tile rows carry
+// kPadWords words on both sides so that no tap needs a horizontal bounds test; out-of-image samples are the neutral
+// element of each step (all-ones for the erosion's AND, zeros for the dilation's OR).
+constexpr int kPadWords = 4; // covers |dx| <= 127 (structuring elements up to 255 wide)
+
+template <bool ERODE>
+__device__ __forceinline__ uint32_t morph_word(const short2 *offs, int noffs, const uint32_t *tile, int pitch, int trow_base,
+                                               int wx)
+{
+    uint32_t acc = ERODE ? 0xFFFFFFFFu : 0u;
+    int cur_dy = INT_MIN, cur_q = INT_MIN;
+    const uint32_t *rowp = tile;
+    uint32_t w0 = 0, w1 = 0;
+    for (int k = 0; k < noffs; ++k) {
+        const short2 o = offs[k];
+        if (o.y != cur_dy) {
+            cur_dy = o.y;
+            cur_q = INT_MIN;
+            rowp = tile + (trow_base + o.y) * pitch + kPadWords + wx;
+        }
+        const int q = int(o.x) >> 5, r = int(o.x) & 31; // floor division: columns 32*wx + dx .. + 31
+        if (q != cur_q) {
+            cur_q = q;
+            w0 = rowp[q];
+            w1 = rowp[q + 1];
+        }
+        const uint32_t v = r ? __funnelshift_r(w0, w1, r) : w0;
+        acc = ERODE ? (acc & v) : (acc | v);
+        if (ERODE && acc == 0)
+            break;
+    }
+    return acc;
+}
+
+__device__ void open_bands(const FusedArgs &P, const short2 *offs, const uint32_t *src, uint32_t *dst, uint32_t *smem)
+{
+    const int tid = threadIdx.x;
+    const int pitch = P.WWp + 2 * kPadWords;
+    const int span = P.dy_max - P.dy_min;
+    const int BH = P.band_rows;
+    const int s_rows_max = BH + 2 * span, e_rows_max = BH + span;
+    uint32_t *S = smem;
+    uint32_t *E = smem + size_t(s_rows_max) * pitch;
+    const int qpr = P.WWp >> 2; // quads per row
+    // side pads: written once per call (the tiles alias the union-find's parent array between calls)
+    for (int i = tid; i < (s_rows_max + e_rows_max) * 2 * kPadWords; i += NT) {
+        const int row = i / (2 * kPadWords), c = i - row * (2 * kPadWords);
+        const int col = c < kPadWords ? c : P.WWp + c;
+        if (row < s_rows_max)
+            S[row * pitch + col] = 0xFFFFFFFFu;
+        else
+            E[(row - s_rows_max) * pitch + col] = 0u;
+    }
+    for (int y0 = 0; y0 < P.H; y0 += BH) {
+        const int y1 = min(y0 + BH, P.H);
+        const int e0 = y0 + P.dy_min, e1 = y1 + P.dy_max; // eroded rows the band's dilation reads
+        const int s0 = e0 + P.dy_min, s1 = e1 + P.dy_max; // source rows their erosion reads
+        const int srows = s1 - s0, erows = e1 - e0;
+        // stage the source rows; invalid columns and out-of-image rows read as set
+        for (int i = tid; i < srows * qpr; i += NT) {
+            int tr, qc;
+            if (P.wwp_shift >= 0) {
+                tr = i >> (P.wwp_shift - 2);
+                qc = i & (qpr - 1);
+            } else {
+                tr = i / qpr;
+                qc = i - tr * qpr;
+            }
+            const int r = s0 + tr;
+            uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (r >= 0 && r < P.H) {
+                v = __ldcg(reinterpret_cast<const uint4 *>(src + size_t(r) * P.WWp) + qc);
+                v.x |= ~valid_mask(P, 4 * qc);
+                v.y |= ~valid_mask(P, 4 * qc + 1);
+                v.z |= ~valid_mask(P, 4 * qc + 2);
+                v.w |= ~valid_mask(P, 4 * qc + 3);
+            }
+            *reinterpret_cast<uint4 *>(S + tr * pitch + kPadWords + 4 * qc) = v;
+        }
+        __syncthreads();
+        // erode: tile row te <-> image row e0 + te; its taps read S rows te + dy - dy_min
+        for (int i = tid; i < erows * P.WWp; i += NT) {
+            int te, wx;
+            split(P, uint32_t(i), te, wx);
+            const int e = e0 + te;
+            uint32_t v = 0;
+            if (e >= 0 && e < P.H && wx < P.WW)
+                v = morph_word<true>(offs, P.noffs, S, pitch, te - P.dy_min, wx) & valid_mask(P, wx);
+            E[te * pitch + kPadWords + wx] = v;
+        }
+        __syncthreads();
+        // dilate: output row y0 + ty reads E rows ty + dy - dy_min
+        for (int i = tid; i < (y1 - y0) * P.WWp; i += NT) {
+            int ty, wx;
+            split(P, uint32_t(i), ty, wx);
+            uint32_t v = 0;
+            if (wx < P.WW)
+                v = morph_word<false>(offs, P.noffs, E, pitch, ty - P.dy_min, wx) & valid_mask(P, wx);
+            dst[size_t(y0 + ty) * P.WWp + wx] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- separable opening (MorphPlan) -----------------------------------------------------------------------------------
+// horizontal step of one pattern over `rows` tile rows: dst row = AND / OR over the pattern's dx of (src row shifted)
+template <bool ERODE>
+__device__ void morph_rows_h(const FusedArgs &P, int pat, const uint32_t *src, uint32_t *dst, int rows, int pitch)
+{
+    const int qpr = P.WWp >> 2;
+    const int k0 = P.plan.pat_start[pat], k1 = P.plan.pat_start[pat + 1];
+    for (int i = threadIdx.x; i < rows * qpr; i += NT) {
+        int tr, qc;
+        if (P.wwp_shift >= 0) {
+            tr = i >> (P.wwp_shift - 2);
+            qc = i & (qpr - 1);
+        } else {
+            tr = i / qpr;
+            qc = i - tr * qpr;
+        }
+        const uint32_t *row = src + tr * pitch + kPadWords + 4 * qc;
+        const uint4 c = *reinterpret_cast<const uint4 *>(row);
+        const uint32_t w[6] = {row[-1], c.x, c.y, c.z, c.w, row[4]};
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5]) != 0) { // an all-clear neighbourhood stays clear in both steps
+            uint32_t acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                acc[j] = ERODE ? 0xFFFFFFFFu : 0u;
+            for (int k = k0; k < k1; ++k) {
+                const int dx = P.plan.dx[k];
+                const int sh = dx & 31;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t v = dx < 0 ? __funnelshift_r(w[j], w[j + 1], sh) : __funnelshift_r(w[j + 1], w[j + 2], sh);
+                    acc[j] = ERODE ? (acc[j] & v) : (acc[j] | v);
+                }
+            }
+            o = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        }
+        *reinterpret_cast<uint4 *>(dst + tr * pitch + kPadWords + 4 * qc) = o;
+    }
+}
+
+// vertical step for tile row `trow` (taps read rows trow + dy - dy_min of the pattern tiles)
+template <bool ERODE>
+__device__ __forceinline__ uint4 morph_quad_v(const FusedArgs &P, const uint32_t *tiles, size_t tile_words, int pitch, int trow,
+                                              int qc)
+{
+    uint4 acc = ERODE ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint4(0, 0, 0, 0);
+    for (int k = 0; k < P.plan.nrows; ++k) {
+        const int pat = P.plan.row_pat[k];
+        const uint32_t *t = tiles + (P.plan.pat_ident[pat] ? 0 : size_t(pat + 1) * tile_words);
+        const uint4 v = *reinterpret_cast<const uint4 *>(t + (trow + P.plan.row_dy[k] - P.dy_min) * pitch + kPadWords + 4 * qc);
+        if (ERODE) {
+            acc.x &= v.x;
+            acc.y &= v.y;
+            acc.z &= v.z;
+            acc.w &= v.w;
+            if ((acc.x | acc.y | acc.z | acc.w) == 0)
+                break;
+        } else {
+            acc.x |= v.x;
+            acc.y |= v.y;
+            acc.z |= v.z;
+            acc.w |= v.w;
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ uint4 valid_quad(const FusedArgs &P, int qc)
+{
+    return make_uint4(valid_mask(P, 4 * qc), valid_mask(P, 4 * qc + 1), valid_mask(P, 4 * qc + 2), valid_mask(P, 4 * qc + 3));
+}
+
+// tiles: [0] staged rows (source, later the eroded rows' own tile is separate), [1 + p] pattern p's horizontal result,
+// [1 + npat] the eroded rows.  All tiles share one geometry (BH + 2 * span rows of `pitch` words).
+__device__ void open_bands_sep(const FusedArgs &P, const uint32_t *src, uint32_t *dst, uint32_t *smem)
+{
+    const int tid = threadIdx.x;
+    const int pitch = P.WWp + 2 * kPadWords;
+    const int span = P.dy_max - P.dy_min;
+    const int BH = P.band_rows;
+    const int rows_max = BH + 2 * span;
+    const size_t tile_words = size_t(rows_max) * pitch;
+    const int npat = P.plan.npat;
+    uint32_t *S = smem;
+    uint32_t *E = smem + size_t(npat + 1) * tile_words;
+    const int qpr = P.WWp >> 2;
+    // side pads of the staged rows (set) and of the eroded rows (clear); the pattern tiles' pads are never read
+    for (int i = tid; i < rows_max * 2 * kPadWords; i += NT) {
+        const int row = i / (2 * kPadWords), c = i - row * (2 * kPadWords);
+        const int col = c < kPadWords ? c : P.WWp + c;
+        S[row * pitch + col] = 0xFFFFFFFFu;
+        E[row * pitch + col] = 0u;
+    }
+    for (int y0 = 0; y0 < P.H; y0 += BH) {
+        const int y1 = min(y0 + BH, P.H);
+        const int e0 = y0 + P.dy_min, e1 = y1 + P.dy_max; // eroded rows the band's dilation reads
+        const int s0 = e0 + P.dy_min, s1 = e1 + P.dy_max; // source rows their erosion reads
+        const int srows = s1 - s0, erows = e1 - e0;
+        for (int i = tid; i < srows * qpr; i += NT) {
+            int tr, qc;
+            if (P.wwp_shift >= 0) {
+                tr = i >> (P.wwp_shift - 2);
+                qc = i & (qpr - 1);
+            } else {
+                tr = i / qpr;
+                qc = i - tr * qpr;
+            }
+            const int r = s0 + tr;
+            uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (r >= 0 && r < P.H) {
+                v = __ldcg(reinterpret_cast<const uint4 *>(src + size_t(r) * P.WWp) + qc);
+                const uint4 m = valid_quad(P, qc);
+                v.x |= ~m.x;
+                v.y |= ~m.y;
+                v.z |= ~m.z;
+                v.w |= ~m.w;
+            }
+            *reinterpret_cast<uint4 *>(S + tr * pitch + kPadWords + 4 * qc) = v;
+        }
+        __syncthreads();
+        for (int p = 0; p < npat; ++p)
+            if (!P.plan.pat_ident[p])
+                morph_rows_h<true>(P, p, S, smem + size_t(p + 1) * tile_words, srows, pitch);
+        __syncthreads();
+        for (int i = tid; i < erows * qpr; i += NT) {
+            int te, qc;
+            if (P.wwp_shift >= 0) {
+                te = i >> (P.wwp_shift - 2);
+                qc = i & (qpr - 1);
+            } else {
+                te = i / qpr;
+                qc = i - te * qpr;
+            }
+            const int e = e0 + te;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (e >= 0 && e < P.H) {
+                v = morph_quad_v<true>(P, smem, tile_words, pitch, te, qc);
+                const uint4 m = valid_quad(P, qc);
+                v.x &= m.x;
+                v.y &= m.y;
+                v.z &= m.z;
+                v.w &= m.w;
+            }
+            *reinterpret_cast<uint4 *>(E + te * pitch + kPadWords + 4 * qc) = v;
+        }
+        __syncthreads();
+        // dilation: the pattern tiles are reused for the horizontal results of the eroded rows; an identity pattern
+        // reads the eroded rows themselves, which must then sit where tile 0 is expected: pass E as the tile base
+        for (int p = 0; p < npat; ++p)
+            if (!P.plan.pat_ident[p])
+                morph_rows_h<false>(P, p, E, smem + size_t(p + 1) * tile_words, erows, pitch);
+        __syncthreads();
+        for (int i = tid; i < (y1 - y0) * qpr; i += NT) {
+            int ty, qc;
+            if (P.wwp_shift >= 0) {
+                ty = i >> (P.wwp_shift - 2);
+                qc = i & (qpr - 1);
+            } else {
+                ty = i / qpr;
+                qc = i - ty * qpr;
+            }
+            // tile base E for identity patterns, smem + (p + 1) * tile_words for the others: expressed through one base
+            // pointer by giving morph_quad_v E as "tile 0" and the offset of the pattern tiles relative to it
+            uint4 acc = make_uint4(0, 0, 0, 0);
+            for (int k = 0; k < P.plan.nrows; ++k) {
+                const int pat = P.plan.row_pat[k];
+                const uint32_t *t = P.plan.pat_ident[pat] ? E : smem + size_t(pat + 1) * tile_words;
+                const uint4 v =
+                    *reinterpret_cast<const uint4 *>(t + (ty + P.plan.row_dy[k] - P.dy_min) * pitch + kPadWords + 4 * qc);
+                acc.x |= v.x;
+                acc.y |= v.y;
+                acc.z |= v.z;
+                acc.w |= v.w;
+            }
+            const uint4 m = valid_quad(P, qc);
+            acc.x &= m.x;
+            acc.y &= m.y;
+            acc.z &= m.z;
+            acc.w &= m.w;
+            *reinterpret_cast<uint4 *>(dst + size_t(y0 + ty) * P.WWp + 4 * qc) = acc;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // run extraction.  Warp w owns a contiguous range of 128-bit quads of the bit image; pass 1 counts run starts, a scan
 // over the warp totals gives each warp its first id, pass 2 writes the run records.  Returns T (the run count);
@@ -393,30 +756,55 @@ __device__ __forceinline__ uint32_t quad_transitions(const FusedArgs &P, const u
     return c;
 }
 
+constexpr int kQU = 4; // quads (128-bit loads) in flight per lane in the run extraction
+
+// one warp-iteration of the extraction: kQU quads per lane, all loads issued before the first use; bit u of `prevs` is the
+// bit that precedes quad u (the MSB of the previous word in raster order)
+__device__ __forceinline__ void load_quad_batch(const uint32_t *img, uint32_t qb, uint32_t q1, int lane, uint32_t &carry,
+                                                uint4 w[kQU], uint32_t &prevs)
+{
+#pragma unroll
+    for (int u = 0; u < kQU; ++u) {
+        const uint32_t q = qb + 32u * u + lane;
+        w[u] = make_uint4(0, 0, 0, 0);
+        if (q < q1)
+            w[u] = __ldcg(reinterpret_cast<const uint4 *>(img) + q);
+    }
+    prevs = 0;
+#pragma unroll
+    for (int u = 0; u < kQU; ++u) {
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, w[u].w, 1) >> 31;
+        if (lane == 0)
+            prev = carry;
+        carry = __shfl_sync(0xFFFFFFFFu, w[u].w, 31) >> 31;
+        prevs |= prev << u;
+    }
+}
+
 __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nq = P.nwords >> 2;
-    const uint32_t per_warp = ((nq + NW * 32 - 1) / (NW * 32)) * 32;
+    constexpr uint32_t step = 32u * kQU;
+    const uint32_t per_warp = ((nq + NW * step - 1) / (NW * step)) * step;
     const uint32_t q0 = min(uint32_t(warp) * per_warp, nq), q1 = min(q0 + per_warp, nq);
     const uint32_t first_carry = (q0 < q1 && q0 > 0) ? (ld(img + 4 * size_t(q0) - 1) >> 31) : 0u;
     // pass 1: count
     {
         uint32_t cnt = 0, carry = first_carry;
-        for (uint32_t qb = q0; qb < q1; qb += 32) {
-            const uint32_t q = qb + lane;
-            uint4 w = make_uint4(0, 0, 0, 0);
-            if (q < q1)
-                w = __ldcg(reinterpret_cast<const uint4 *>(img) + q);
-            uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, w.w, 1) >> 31;
-            if (lane == 0)
-                prev = carry;
-            carry = __shfl_sync(0xFFFFFFFFu, w.w, 31) >> 31;
-            if (q < q1) {
-                int y, wx0;
-                split(P, 4 * q, y, wx0);
-                uint32_t t[4];
-                cnt += quad_transitions(P, w, prev, wx0, t);
+        for (uint32_t qb = q0; qb < q1; qb += step) {
+            uint4 w[kQU];
+            uint32_t prevs;
+            load_quad_batch(img, qb, q1, lane, carry, w, prevs);
+#pragma unroll
+            for (int u = 0; u < kQU; ++u) {
+                const uint32_t q = qb + 32u * u + lane;
+                if (q < q1) {
+                    int y, wx0;
+                    split(P, 4 * q, y, wx0);
+                    uint32_t t[4];
+                    cnt += quad_transitions(P, w[u], (prevs >> u) & 1u, wx0, t);
+                }
             }
         }
 #pragma unroll
@@ -437,55 +825,51 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
     // pass 2: fill
     {
         uint32_t carry = first_carry;
-        for (uint32_t qb = q0; qb < q1; qb += 32) {
-            const uint32_t q = qb + lane;
-            uint4 w = make_uint4(0, 0, 0, 0);
-            if (q < q1)
-                w = __ldcg(reinterpret_cast<const uint4 *>(img) + q);
-            uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, w.w, 1) >> 31;
-            if (lane == 0)
-                prev = carry;
-            carry = __shfl_sync(0xFFFFFFFFu, w.w, 31) >> 31;
-            uint32_t t[4] = {0, 0, 0, 0};
-            uint32_t c = 0;
-            int y = 0, wx0 = 0;
-            if (q < q1) {
-                split(P, 4 * q, y, wx0);
-                c = quad_transitions(P, w, prev, wx0, t);
-            }
-            if (__ballot_sync(0xFFFFFFFFu, c != 0) == 0)
-                continue;
-            uint32_t inc = c;
+        for (uint32_t qb = q0; qb < q1; qb += step) {
+            uint4 w[kQU];
+            uint32_t prevs;
+            load_quad_batch(img, qb, q1, lane, carry, w, prevs);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d)
-                    inc += n;
-            }
-            uint32_t id = base + inc - c;
-            base += __shfl_sync(0xFFFFFFFFu, inc, 31);
-            if (c) {
-                if (wx0 == 0)
-                    rs.rowoff[y] = id;
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            for (int u = 0; u < kQU; ++u) {
+                const uint32_t q = qb + 32u * u + lane;
+                uint32_t t[4] = {0, 0, 0, 0};
+                uint32_t c = 0;
+                int y = 0, wx0 = 0;
+                if (q < q1) {
+                    split(P, 4 * q, y, wx0);
+                    c = quad_transitions(P, w[u], (prevs >> u) & 1u, wx0, t);
+                }
+                if (__ballot_sync(0xFFFFFFFFu, c != 0) == 0)
+                    continue;
+                uint32_t inc = c;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t tt = t[k];
-                    while (tt) {
-                        const int b = __ffs(tt) - 1;
-                        tt &= tt - 1;
-                        rs.xinfo[id] = uint32_t(32 * (wx0 + k) + b) | (uint32_t(y) << 16) | (((ww[k] >> b) & 1u) << 31);
-                        st(rs.parent + id, id);
-                        ++id;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= d)
+                        inc += n;
+                }
+                uint32_t id = base + inc - c;
+                base += __shfl_sync(0xFFFFFFFFu, inc, 31);
+                if (c) {
+                    if (wx0 == 0)
+                        rs.rowoff[y] = id;
+                    const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t tt = t[k];
+                        while (tt) {
+                            const int b = __ffs(tt) - 1;
+                            tt &= tt - 1;
+                            rs.xinfo[id] = uint32_t(32 * (wx0 + k) + b) | (uint32_t(y) << 16) | (((ww[k] >> b) & 1u) << 31);
+                            ++id;
+                        }
                     }
                 }
             }
         }
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0)
         rs.rowoff[P.H] = T;
-        st(rs.parent + T, T);
-    }
     __syncthreads();
     return T;
 }
@@ -493,8 +877,8 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
 // ------------------------------------------------------------------------------------------------------------------
 // labelling of runs
 // ------------------------------------------------------------------------------------------------------------------
-template <bool FG8, bool FRAME, bool MERGE_FG>
-__device__ void merge_phase(const FusedArgs &P, const RunSet &rs, uint32_t T)
+template <bool FG8, bool FRAME, bool MERGE_FG, bool SM>
+__device__ void merge_phase(const FusedArgs &P, const RunSet &rs, const Par<SM> &par, uint32_t T)
 {
     for (uint32_t r = threadIdx.x; r < T; r += NT) {
         const uint32_t xi = rs.xinfo[r];
@@ -512,28 +896,47 @@ __device__ void merge_phase(const FusedArgs &P, const RunSet &rs, uint32_t T)
                 if (run_x(xj) > c1)
                     break;
                 if (run_v(xj) == v)
-                    uf_union(rs.parent, r, j);
+                    uf_union(par, r, j);
             }
         }
         if (FRAME && !v && (y == 0 || y == uint32_t(P.H - 1) || s == 0 || e == uint32_t(P.W - 1)))
-            uf_union(rs.parent, r, T);
+            uf_union(par, r, T);
     }
 }
 
-__device__ void flatten_phase(const RunSet &rs, uint32_t T)
+template <bool FG8, bool FRAME, bool MERGE_FG, bool SM>
+__device__ void label_with(const FusedArgs &P, Shared &sh, const RunSet &rs, uint32_t *par_mem, uint32_t T)
 {
+    const Par<SM> par{par_mem};
     for (uint32_t r = threadIdx.x; r <= T; r += NT)
-        st(rs.parent + r, uf_find(rs.parent, r));
+        par.set(r, r); // entry T is the FRAME node
+    __syncthreads();
+    merge_phase<FG8, FRAME, MERGE_FG, SM>(P, rs, par, T);
+    __syncthreads();
+    prof_tick(P.prof, P.prof, sh, kPMerge);
+    // flatten; later phases read the roots from the slot's global array
+    for (uint32_t r = threadIdx.x; r <= T; r += NT) {
+        const uint32_t root = uf_find(par, r);
+        if (SM)
+            st(rs.parent + r, root);
+        else
+            par.set(r, root);
+    }
+    __syncthreads();
+    prof_tick(P.prof, P.prof, sh, kPFlatten);
 }
 
 template <bool FG8, bool FRAME, bool MERGE_FG>
-__device__ uint32_t label_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs)
+__device__ uint32_t label_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs, uint32_t *smem_words)
 {
     const uint32_t T = extract_runs(P, sh, img, rs);
-    merge_phase<FG8, FRAME, MERGE_FG>(P, rs, T);
-    __syncthreads();
-    flatten_phase(rs, T);
-    __syncthreads();
+    prof_tick(P.prof, P.prof, sh, kPExtract);
+    if (T + 1 <= P.smem_words)
+        label_with<FG8, FRAME, MERGE_FG, true>(P, sh, rs, smem_words, T);
+    else
+        label_with<FG8, FRAME, MERGE_FG, false>(P, sh, rs, rs.parent, T);
+    if (P.prof && threadIdx.x == 0)
+        atomicAdd(P.prof + kPRuns, (unsigned long long)T);
     return T;
 }
 
@@ -796,9 +1199,20 @@ __device__ void expand_phase(const FusedArgs &P, unsigned f, const uint32_t *A, 
 // ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kSmemOffs = 256; // structuring-element taps cached in shared memory
+
 __global__ void __launch_bounds__(NT, 2) highlight_fused_kernel(const FusedArgs P)
 {
+    extern __shared__ uint4 dyn_smem4[];
+    uint32_t *dyn = reinterpret_cast<uint32_t *>(dyn_smem4);
     __shared__ Shared sh;
+    __shared__ short2 sh_offs[kSmemOffs];
+    const short2 *offs = P.offs;
+    if (P.noffs <= kSmemOffs) {
+        for (int k = threadIdx.x; k < P.noffs; k += NT)
+            sh_offs[k] = P.offs[k];
+        offs = sh_offs;
+    }
     const size_t slot = blockIdx.x;
     uint32_t *A = P.bits + slot * kImages * size_t(P.nwords);
     uint32_t *U = A + P.nwords, *L = U + P.nwords, *Tm = L + P.nwords;
@@ -820,8 +1234,10 @@ __global__ void __launch_bounds__(NT, 2) highlight_fused_kernel(const FusedArgs 
         const unsigned f = sh.frame;
         if (f >= P.nframes)
             break;
+        prof_tick(P.prof, P.prof, sh, -1);
         bits_phase(P, f, A, U, L);
         __syncthreads();
+        prof_tick(P.prof, P.prof, sh, kPBits);
         // debug_stage (CVVP_HL_DEBUG_STAGE): 1 A=d>th, 2 U=d>hi, 3 L=d>lo, 4 A opened, 5 A small removed, 6 A filled,
         // 7 B=hysteresis, 8 B opened, 9 B small removed, 10 B filled
 #define CVVP_DEBUG_STAGE(k, img, w)                                                                                    \
@@ -834,37 +1250,69 @@ __global__ void __launch_bounds__(NT, 2) highlight_fused_kernel(const FusedArgs 
         CVVP_DEBUG_STAGE(2, U, false)
         CVVP_DEBUG_STAGE(3, L, false)
         // ---- branch A: threshold -> open -> remove small -> fill holes                                  (:35-47)
-        morph_phase<true, false>(P, A, Tm);
-        __syncthreads();
-        morph_phase<false, false>(P, Tm, A);
-        __syncthreads();
+        if (P.band_rows > 0) {
+            if (P.plan.sep)
+                open_bands_sep(P, A, Tm, dyn);
+            else
+                open_bands(P, offs, A, Tm, dyn);
+            uint32_t *t = A;
+            A = Tm;
+            Tm = t;
+        } else {
+            morph_phase<true, false>(P, A, Tm);
+            __syncthreads();
+            prof_tick(P.prof, P.prof, sh, kPErodeA);
+            morph_phase<false, false>(P, Tm, A);
+            __syncthreads();
+        }
+        prof_tick(P.prof, P.prof, sh, kPDilateA);
         CVVP_DEBUG_STAGE(4, A, false)
-        uint32_t T = label_runs<true, true, true>(P, sh, A, ra);
+        uint32_t T = label_runs<true, true, true>(P, sh, A, ra, dyn);
         rso_phase(P, A, ra, T, link, st_s, st_e, st_x, P.min_th);
+        prof_tick(P.prof, P.prof, sh, kPRso);
         CVVP_DEBUG_STAGE(5, A, false)
-        T = label_runs<false, false, false>(P, sh, A, ra);
+        T = label_runs<false, false, false>(P, sh, A, ra, dyn);
         fill_phase(P, A, ra, T, &sh.white[0]);
+        prof_tick(P.prof, P.prof, sh, kPFill);
         CVVP_DEBUG_STAGE(6, A, sh.white[0] != 0)
         // ---- branch B: hysteresis -> open -> remove small -> fill holes                                 (:54-73)
-        const uint32_t Tu = label_runs<true, true, true>(P, sh, U, ra);
-        const uint32_t Tl = label_runs<false, false, true>(P, sh, L, rb);
+        const uint32_t Tu = label_runs<true, true, true>(P, sh, U, ra, dyn);
+        const uint32_t Tl = label_runs<false, false, true>(P, sh, L, rb, dyn);
         hysteresis_phase(P, ra, Tu, rb, Tl, st_x, U); // U's bits are no longer needed: it now holds the result
+        prof_tick(P.prof, P.prof, sh, kPHyst);
         CVVP_DEBUG_STAGE(7, U, false)
-        morph_phase<true, true>(P, U, Tm);
-        __syncthreads();
-        morph_phase<false, false>(P, Tm, U);
-        __syncthreads();
+        if (P.band_rows > 0) {
+            if (P.plan.sep)
+                open_bands_sep(P, U, Tm, dyn);
+            else
+                open_bands(P, offs, U, Tm, dyn);
+            uint32_t *t = U;
+            U = Tm;
+            Tm = t;
+        } else {
+            morph_phase<true, true>(P, U, Tm);
+            __syncthreads();
+            prof_tick(P.prof, P.prof, sh, kPErodeB);
+            morph_phase<false, false>(P, Tm, U);
+            __syncthreads();
+        }
+        prof_tick(P.prof, P.prof, sh, kPDilateB);
         CVVP_DEBUG_STAGE(8, U, false)
-        T = label_runs<true, true, true>(P, sh, U, ra);
+        T = label_runs<true, true, true>(P, sh, U, ra, dyn);
         rso_phase(P, U, ra, T, link, st_s, st_e, st_x, P.min_hyst);
+        prof_tick(P.prof, P.prof, sh, kPRso);
         CVVP_DEBUG_STAGE(9, U, false)
-        T = label_runs<false, false, false>(P, sh, U, ra);
+        T = label_runs<false, false, false>(P, sh, U, ra, dyn);
         fill_phase(P, U, ra, T, &sh.white[1]);
+        prof_tick(P.prof, P.prof, sh, kPFill);
         CVVP_DEBUG_STAGE(10, U, sh.white[1] != 0)
 #undef CVVP_DEBUG_STAGE
         // ---- out = 255 * (A | B)                                                                         (:77)
         expand_phase(P, f, A, U, sh.white[0] || sh.white[1]);
         __syncthreads();
+        prof_tick(P.prof, P.prof, sh, kPExpand);
+        if (P.prof && threadIdx.x == 0)
+            atomicAdd(P.prof + kPFrames, 1ull);
     }
     // the last CTA to leave re-arms the queue for the next launch
     if (threadIdx.x == 0) {
@@ -887,6 +1335,64 @@ struct FusedGeom {
     int WW, WWp, wwp_shift;
     uint32_t nwords, cap, rstride;
 };
+
+constexpr size_t kDynSmemBytes = 96 * 1024; // per CTA; two CTAs per SM
+
+// rows per band of the shared-memory opening (0: the tiles do not fit, use the global-memory taps)
+int pick_band_rows(const FusedGeom &fg, int dy_min, int dy_max, const MorphPlan &plan)
+{
+    const int span = dy_max - dy_min;
+    const size_t pitch = size_t(fg.WWp) + 2 * kPadWords;
+    for (int bh = 128; bh >= 8; bh -= 8) {
+        const size_t words = plan.sep ? size_t(plan.npat + 2) * (size_t(bh) + 2 * span) * pitch
+                                      : (size_t(bh) * 2 + 3 * size_t(span)) * pitch;
+        if (words * sizeof(uint32_t) <= kDynSmemBytes)
+            return bh;
+    }
+    return 0;
+}
+
+// taps (sorted by row, then column) -> MorphPlan
+MorphPlan make_plan(const std::vector<short2> &offs)
+{
+    MorphPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    std::vector<std::vector<int>> pats;
+    size_t i = 0;
+    int ntaps = 0;
+    while (i < offs.size()) {
+        const int dy = offs[i].y;
+        std::vector<int> dxs;
+        for (; i < offs.size() && offs[i].y == dy; ++i) {
+            if (offs[i].x < -31 || offs[i].x > 31)
+                return pl;
+            dxs.push_back(offs[i].x);
+        }
+        if (dy < -127 || dy > 127 || pl.nrows >= kMaxPlanRows)
+            return pl;
+        int id = -1;
+        for (size_t p = 0; p < pats.size(); ++p)
+            if (pats[p] == dxs)
+                id = int(p);
+        if (id < 0) {
+            if (int(pats.size()) >= kMaxPat || ntaps + int(dxs.size()) > kMaxPlanTaps)
+                return pl;
+            id = int(pats.size());
+            pats.push_back(dxs);
+            pl.pat_start[id] = (unsigned char)ntaps;
+            for (int dx : dxs)
+                pl.dx[ntaps++] = (signed char)dx;
+            pl.pat_start[id + 1] = (unsigned char)ntaps;
+            pl.pat_ident[id] = (dxs.size() == 1 && dxs[0] == 0) ? 1 : 0;
+        }
+        pl.row_dy[pl.nrows] = (signed char)dy;
+        pl.row_pat[pl.nrows] = (signed char)id;
+        ++pl.nrows;
+    }
+    pl.npat = int(pats.size());
+    pl.sep = 1;
+    return pl;
+}
 
 FusedGeom fused_geom(const HlGeom &g)
 {
@@ -937,7 +1443,9 @@ int fused_frames_in_flight(cvvp_ctx *ctx, HighlightState *st)
     if (st->fs.slots > 0)
         return st->fs.slots;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, highlight_fused_kernel, NT, 0) != cudaSuccess || per_sm < 1) {
+    cudaFuncSetAttribute(highlight_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kDynSmemBytes));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, highlight_fused_kernel, NT, kDynSmemBytes) != cudaSuccess ||
+        per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
     }
@@ -954,6 +1462,11 @@ int fused_frames_in_flight(cvvp_ctx *ctx, HighlightState *st)
     const long long by_mem = (long long)(budget / slot_bytes(fg));
     if (slots > by_mem)
         slots = by_mem;
+    if (const char *ov = getenv("CVVP_HL_SLOTS")) { // developer aid: frames in flight
+        const long long v = atoll(ov);
+        if (v >= 1 && v <= by_mem)
+            slots = v;
+    }
     if (slots < 1)
         slots = 1;
     return int(slots);
@@ -1021,17 +1534,46 @@ int highlight_fused_batch(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, 
     P.rowoff = st->fs.rowoff;
     P.queue = st->fs.queue;
     P.nframes = nb;
+    P.smem_words = uint32_t(kDynSmemBytes / sizeof(uint32_t));
+    P.dy_min = st->dy_min;
+    P.dy_max = st->dy_max;
+    P.pad_words = kPadWords;
+    P.plan = make_plan(st->h_offs);
+    if (getenv("CVVP_HL_NO_SEP"))
+        P.plan.sep = 0; // developer aid: force the generic tap loop
+    P.band_rows = pick_band_rows(fg, st->dy_min, st->dy_max, P.plan);
     auto aligned16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     P.fast_io = (P.W % 32 == 0) && aligned16(in) && aligned16(d_out) && aligned16(st->d_bg) && frame_stride % 16 == 0 &&
                 out_stride % 16 == 0;
     const char *dbg = getenv("CVVP_HL_DEBUG_STAGE");
     P.debug_stage = dbg ? atoi(dbg) : 0;
+    P.prof = nullptr;
+    const bool want_prof = getenv("CVVP_HL_PROF") != nullptr;
+    if (want_prof && cudaMalloc(reinterpret_cast<void **>(&P.prof), kPCount * sizeof(unsigned long long)) == cudaSuccess)
+        cudaMemsetAsync(P.prof, 0, kPCount * sizeof(unsigned long long), stream);
     const unsigned grid = nb < unsigned(st->fs.slots) ? nb : unsigned(st->fs.slots);
-    highlight_fused_kernel<<<grid, NT, 0, stream>>>(P);
+    highlight_fused_kernel<<<grid, NT, kDynSmemBytes, stream>>>(P);
     ctx->launches += 1;
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         return fail(ctx, CVVP_ERR_CUDA, "highlight: kernel launch failed: %s", cudaGetErrorString(e));
+    if (P.prof) { // developer aid (CVVP_HL_PROF=1): per-phase time of an average frame, measured by thread 0 of each CTA
+        unsigned long long h[kPCount];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, P.prof, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(P.prof);
+        static const char *names[] = {"bits", "erodeA", "dilateA", "extract(x6)", "merge(x6)", "flatten(x6)", "rso(x2)",
+                                      "fill(x2)", "hyst", "erodeB", "dilateB", "expand"};
+        const double nf = h[kPFrames] ? double(h[kPFrames]) : 1.0;
+        double total = 0;
+        for (int k = 0; k < kPRuns; ++k)
+            total += double(h[k]);
+        fprintf(stderr, "[cvvp prof] %llu frames, grid %u, %.1f runs per labelling, %.1f us per frame per CTA\n", h[kPFrames],
+                grid, double(h[kPRuns]) / nf / 6.0, total / nf / 1e3);
+        for (int k = 0; k < kPRuns; ++k)
+            fprintf(stderr, "[cvvp prof]   %-12s %9.1f us  %5.1f %%\n", names[k], double(h[k]) / nf / 1e3,
+                    100.0 * double(h[k]) / total);
+    }
     return CVVP_OK;
 }
 } // namespace cvvp

@@ -6,6 +6,8 @@
 #pragma once
 #include "context.hpp"
 
+#include <vector>
+
 namespace cvvp
 {
 struct HlGeom {
@@ -30,9 +32,11 @@ struct HighlightState {
     HlGeom g{};
     int th{}, lo{}, hi{}, min_hyst{}, min_th{};
     int noffs{0};
+    int dy_min{0}, dy_max{0}; // row range of the structuring element's taps (offsets are sorted by row, then column)
     int path{kPathFused};
     uint8_t *d_bg{nullptr};
     short2 *d_offs{nullptr};
+    std::vector<short2> h_offs; // host copy of the taps
     // per-pixel path: per-batch work buffers
     int batch_cap{0};
     uint8_t *m_a{nullptr}, *m_u{nullptr}, *m_l{nullptr}, *m_t{nullptr}, *m_out{nullptr};
