@@ -80,6 +80,7 @@ struct FusedArgs {
     int wwp_shift;    // log2(WWp) when WWp is a power of two, else -1
     uint32_t nwords;  // H * WWp
     uint32_t cap;     // run-array capacity per slot
+    size_t run_words; // run scratch per slot: kRunArrays arrays of cap words + cap / 32 flag words
     uint32_t rstride; // rowoff stride
     uint32_t *bits;
     uint32_t *runs;
@@ -99,6 +100,7 @@ struct RunSet {
     uint32_t *xinfo;
     uint32_t *parent;
     uint32_t *rowoff; // [H + 1]; rowoff[H] = T
+    uint32_t *fbits;  // FRAME flags of the set's roots (one bit per run id)
 };
 
 enum ProfPhase {
@@ -186,15 +188,22 @@ struct Par {
     __device__ __forceinline__ uint32_t amin(uint32_t i, uint32_t v) const { return atomicMin(p + i, v); }
 };
 
+// find with path halving: every second node of the walked chain is re-linked to its grandparent (atomicMin keeps the
+// "labels only decrease" invariant under concurrent unions), so repeated walks of the long vertical chains a frame's
+// background produces stay short
 template <bool SM>
 __device__ __forceinline__ uint32_t uf_find(const Par<SM> &lab, uint32_t x)
 {
-    uint32_t p = lab.get(x);
-    while (p != x) {
-        x = p;
-        p = lab.get(x);
+    for (;;) {
+        const uint32_t p = lab.get(x);
+        if (p == x)
+            return x;
+        const uint32_t gp = lab.get(p);
+        if (gp == p)
+            return p;
+        lab.amin(x, gp);
+        x = gp;
     }
-    return x;
 }
 
 template <bool SM>
@@ -218,37 +227,11 @@ __device__ __forceinline__ void uf_union(const Par<SM> &lab, uint32_t a, uint32_
     } while (!done);
 }
 
-// largest j in [a, b) with x_start(j) <= x   (a row's first run starts at 0, so it always exists)
-__device__ __forceinline__ uint32_t run_at(const uint32_t *xinfo, uint32_t a, uint32_t b, uint32_t x)
-{
-    uint32_t lo = a, hi = b - 1;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (run_x(xinfo[mid]) <= x)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
-    return lo;
-}
-
-__device__ __forceinline__ uint32_t run_end(const uint32_t *xinfo, uint32_t r, uint32_t row_end, int W)
-{
-    return (r + 1 < row_end) ? run_x(xinfo[r + 1]) - 1u : uint32_t(W - 1);
-}
-
 __device__ __forceinline__ bool bit_at(const uint32_t *img, const FusedArgs &P, int x, int y)
 {
     if (x < 0 || y < 0 || x >= P.W || y >= P.H)
         return false;
     return (ld(img + size_t(y) * P.WWp + (x >> 5)) >> (x & 31)) & 1u;
-}
-
-// canonical id of the background region of run j: the FRAME region -> T
-__device__ __forceinline__ uint32_t bg_region(const uint32_t *parent, uint32_t j, uint32_t T, uint32_t frame_root)
-{
-    const uint32_t r = ld(parent + j);
-    return r == frame_root ? T : r;
 }
 
 __device__ __forceinline__ void clear_range(uint32_t *row, int x0, int x1)
@@ -781,7 +764,71 @@ __device__ __forceinline__ void load_quad_batch(const uint32_t *img, uint32_t qb
     }
 }
 
-__device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs)
+// Where the run-level phases read a labelled run set from.  The slot's global arrays always hold the complete set (run
+// records, row offsets and, after the flatten, the roots); while a frame's run count fits, the same three arrays also
+// sit in shared memory and every dependent access of the merge / statistics phases stays on the SM.
+template <bool SM>
+struct View {
+    const uint32_t *xinfo;
+    const uint32_t *rowoff;
+    uint32_t *parent;
+    uint32_t *fbits; // one bit per run id: the root of a background region that touches the image border (FRAME)
+    __device__ __forceinline__ uint32_t xi(uint32_t i) const { return xinfo[i]; }
+    __device__ __forceinline__ uint32_t ro(uint32_t y) const { return rowoff[y]; }
+    __device__ __forceinline__ uint32_t par(uint32_t i) const { return Par<SM>{parent}.get(i); }
+    // largest j in [a, b) with x_start(j) <= x   (a row's first run starts at 0, so it always exists)
+    __device__ __forceinline__ uint32_t at(uint32_t a, uint32_t b, uint32_t x) const
+    {
+        uint32_t lo = a, hi = b - 1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (run_x(xinfo[mid]) <= x)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        return lo;
+    }
+    __device__ __forceinline__ uint32_t end(uint32_t r, uint32_t row_end, int W) const
+    {
+        return (r + 1 < row_end) ? run_x(xinfo[r + 1]) - 1u : uint32_t(W - 1);
+    }
+    // root -> does its background region touch the image border (i.e. belong to the FRAME region)?
+    __device__ __forceinline__ bool is_frame(uint32_t root) const
+    {
+        const uint32_t w = SM ? *reinterpret_cast<volatile uint32_t *>(fbits + (root >> 5)) : __ldcg(fbits + (root >> 5));
+        return (w >> (root & 31)) & 1u;
+    }
+    // canonical id of the background region of run j: any region of the FRAME -> T
+    __device__ __forceinline__ uint32_t region(uint32_t j, uint32_t T) const
+    {
+        const uint32_t r = par(j);
+        return is_frame(r) ? T : r;
+    }
+};
+
+// shared-memory copy of a run set: [rowoff: H + 2, padded][xinfo: cap][parent: cap]
+struct SmemRuns {
+    uint32_t *rowoff, *xinfo, *parent, *fbits;
+    uint32_t cap; // runs (incl. the FRAME node) the copy can hold; 0 = the row offsets alone do not fit
+};
+
+__device__ __forceinline__ SmemRuns smem_runs(const FusedArgs &P, uint32_t *smem)
+{
+    SmemRuns m;
+    const uint32_t ro_words = (uint32_t(P.H) + 2 + 3) & ~3u;
+    m.rowoff = smem;
+    // cap records + cap parents + cap / 32 + 1 flag words
+    m.cap = ro_words + 256 < P.smem_words ? (((P.smem_words - ro_words - 4) * 32u) / 65u) & ~31u : 0;
+    m.xinfo = smem + ro_words;
+    m.parent = m.xinfo + m.cap;
+    m.fbits = m.parent + m.cap;
+    return m;
+}
+
+// Returns T (the run count).  rowoff[H] = T.  sm_ok <- the set also sits in shared memory.
+__device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs, const SmemRuns &sm,
+                                 bool &sm_ok)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nq = P.nwords >> 2;
@@ -822,6 +869,7 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
             base += c;
         T += c;
     }
+    sm_ok = T + 1 <= sm.cap;
     // pass 2: fill
     {
         uint32_t carry = first_carry;
@@ -851,8 +899,11 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
                 uint32_t id = base + inc - c;
                 base += __shfl_sync(0xFFFFFFFFu, inc, 31);
                 if (c) {
-                    if (wx0 == 0)
+                    if (wx0 == 0) {
                         rs.rowoff[y] = id;
+                        if (sm_ok)
+                            sm.rowoff[y] = id;
+                    }
                     const uint32_t ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -860,7 +911,10 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
                         while (tt) {
                             const int b = __ffs(tt) - 1;
                             tt &= tt - 1;
-                            rs.xinfo[id] = uint32_t(32 * (wx0 + k) + b) | (uint32_t(y) << 16) | (((ww[k] >> b) & 1u) << 31);
+                            const uint32_t rec = uint32_t(32 * (wx0 + k) + b) | (uint32_t(y) << 16) | (((ww[k] >> b) & 1u) << 31);
+                            rs.xinfo[id] = rec;
+                            if (sm_ok)
+                                sm.xinfo[id] = rec;
                             ++id;
                         }
                     }
@@ -868,8 +922,11 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
             }
         }
     }
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         rs.rowoff[P.H] = T;
+        if (sm_ok)
+            sm.rowoff[P.H] = T;
+    }
     __syncthreads();
     return T;
 }
@@ -878,100 +935,120 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
 // labelling of runs
 // ------------------------------------------------------------------------------------------------------------------
 template <bool FG8, bool FRAME, bool MERGE_FG, bool SM>
-__device__ void merge_phase(const FusedArgs &P, const RunSet &rs, const Par<SM> &par, uint32_t T)
+__device__ void merge_phase(const FusedArgs &P, const View<SM> &V, uint32_t T)
 {
+    const Par<SM> par{V.parent};
     for (uint32_t r = threadIdx.x; r < T; r += NT) {
-        const uint32_t xi = rs.xinfo[r];
+        const uint32_t xi = V.xi(r);
         const uint32_t s = run_x(xi), y = run_y(xi), v = run_v(xi);
         if (!MERGE_FG && v)
             continue;
-        const uint32_t e = run_end(rs.xinfo, r, rs.rowoff[y + 1], P.W);
+        const uint32_t e = V.end(r, V.ro(y + 1), P.W);
         if (y > 0) {
             const uint32_t d = (FG8 && v) ? 1u : 0u; // 8-connected runs may touch diagonally
-            const uint32_t a = rs.rowoff[y - 1], b = rs.rowoff[y];
+            const uint32_t a = V.ro(y - 1), b = V.ro(y);
             const uint32_t c0 = s >= d ? s - d : 0u;
             const uint32_t c1 = min(e + d, uint32_t(P.W - 1));
-            for (uint32_t j = run_at(rs.xinfo, a, b, c0); j < b; ++j) {
-                const uint32_t xj = rs.xinfo[j];
+            for (uint32_t j = V.at(a, b, c0); j < b; ++j) {
+                const uint32_t xj = V.xi(j);
                 if (run_x(xj) > c1)
                     break;
                 if (run_v(xj) == v)
                     uf_union(par, r, j);
             }
         }
-        if (FRAME && !v && (y == 0 || y == uint32_t(P.H - 1) || s == 0 || e == uint32_t(P.W - 1)))
-            uf_union(par, r, T);
     }
 }
 
 template <bool FG8, bool FRAME, bool MERGE_FG, bool SM>
-__device__ void label_with(const FusedArgs &P, Shared &sh, const RunSet &rs, uint32_t *par_mem, uint32_t T)
+__device__ void label_with(const FusedArgs &P, Shared &sh, const RunSet &rs, const View<SM> &V, uint32_t T)
 {
-    const Par<SM> par{par_mem};
+    const Par<SM> par{V.parent};
     for (uint32_t r = threadIdx.x; r <= T; r += NT)
-        par.set(r, r); // entry T is the FRAME node
+        par.set(r, r);
+    if (FRAME)
+        for (uint32_t i = threadIdx.x; i <= (T >> 5); i += NT) {
+            if (SM)
+                V.fbits[i] = 0;
+            st(rs.fbits + i, 0u);
+        }
     __syncthreads();
-    merge_phase<FG8, FRAME, MERGE_FG, SM>(P, rs, par, T);
+    merge_phase<FG8, FRAME, MERGE_FG, SM>(P, V, T);
     __syncthreads();
     prof_tick(P.prof, P.prof, sh, kPMerge);
-    // flatten; later phases read the roots from the slot's global array
-    for (uint32_t r = threadIdx.x; r <= T; r += NT) {
+    // flatten (roots are final: shortening a chain under a concurrent walk is harmless); the slot's global array always
+    // receives the roots.  FRAME: instead of a node that every border run is united with (thousands of atomics on
+    // one root), the roots of the background regions that touch the image border are flagged.
+    for (uint32_t r = threadIdx.x; r < T; r += NT) {
         const uint32_t root = uf_find(par, r);
+        par.set(r, root);
         if (SM)
             st(rs.parent + r, root);
-        else
-            par.set(r, root);
+        if (FRAME) {
+            const uint32_t xi = V.xi(r);
+            if (!run_v(xi)) {
+                const uint32_t y = run_y(xi);
+                if (y == 0 || y == uint32_t(P.H - 1) || run_x(xi) == 0 || V.end(r, V.ro(y + 1), P.W) == uint32_t(P.W - 1)) {
+                    if (SM)
+                        atomicOr(V.fbits + (root >> 5), 1u << (root & 31));
+                    atomicOr(rs.fbits + (root >> 5), 1u << (root & 31));
+                }
+            }
+        }
     }
     __syncthreads();
     prof_tick(P.prof, P.prof, sh, kPFlatten);
 }
 
+// labels the runs of `img` into run set rs; returns T; sm_ok <- the set is also resident in shared memory
 template <bool FG8, bool FRAME, bool MERGE_FG>
-__device__ uint32_t label_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs, uint32_t *smem_words)
+__device__ uint32_t label_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs, const SmemRuns &sm,
+                               bool &sm_ok)
 {
-    const uint32_t T = extract_runs(P, sh, img, rs);
+    const uint32_t T = extract_runs(P, sh, img, rs, sm, sm_ok);
     prof_tick(P.prof, P.prof, sh, kPExtract);
-    if (T + 1 <= P.smem_words)
-        label_with<FG8, FRAME, MERGE_FG, true>(P, sh, rs, smem_words, T);
+    if (sm_ok)
+        label_with<FG8, FRAME, MERGE_FG, true>(P, sh, rs, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T);
     else
-        label_with<FG8, FRAME, MERGE_FG, false>(P, sh, rs, rs.parent, T);
+        label_with<FG8, FRAME, MERGE_FG, false>(P, sh, rs, View<false>{rs.xinfo, rs.rowoff, rs.parent, rs.fbits}, T);
     if (P.prof && threadIdx.x == 0)
         atomicAdd(P.prof + kPRuns, (unsigned long long)T);
     return T;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// hysteresis (ThresholdImageWithHysteresis :107-144)
+// hysteresis (ThresholdImageWithHysteresis :107-144).  U's set is read from the slot's global arrays (the shared-memory
+// copy, if any, holds L's set, labelled last).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ void hysteresis_phase(const FusedArgs &P, const RunSet &ru, uint32_t Tu, const RunSet &rl, uint32_t Tl, int *marks,
-                                 uint32_t *out)
+template <bool SM>
+__device__ void hysteresis_phase(const FusedArgs &P, const View<false> &VU, uint32_t Tu, const View<SM> &VL, uint32_t Tl,
+                                 int *marks, uint32_t *out)
 {
     for (uint32_t r = threadIdx.x; r <= Tl; r += NT)
         st(marks + r, 0);
     for (uint32_t i = threadIdx.x; i < (P.nwords >> 2); i += NT)
         reinterpret_cast<uint4 *>(out)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    const uint32_t frame_root = ld(ru.parent + Tu);
     for (uint32_t r = threadIdx.x; r < Tu; r += NT) {
-        const uint32_t xi = ru.xinfo[r];
-        if (!run_v(xi) || ld(ru.parent + r) != r)
+        const uint32_t xi = VU.xi(r);
+        if (!run_v(xi) || VU.par(r) != r)
             continue; // seeds are the raster-first pixels of the hi components (contour[0])
         const uint32_t s = run_x(xi), y = run_y(xi);
         // RETR_EXTERNAL: the region left of the first pixel (the component's outer background) must be FRAME
-        const bool external = (s == 0) || (ld(ru.parent + r - 1) == frame_root);
+        const bool external = (s == 0) || VU.is_frame(VU.par(r - 1));
         if (external) {
-            const uint32_t j = run_at(rl.xinfo, rl.rowoff[y], rl.rowoff[y + 1], s);
-            st(marks + ld(rl.parent + j), 1);
+            const uint32_t j = VL.at(VL.ro(y), VL.ro(y + 1), s);
+            st(marks + VL.par(j), 1);
         }
     }
     __syncthreads();
     // runs of the lower mask whose region holds a seed (both values: the lo > hi quirk)
     for (uint32_t r = threadIdx.x; r < Tl; r += NT) {
-        if (!ld(marks + ld(rl.parent + r)))
+        if (!ld(marks + VL.par(r)))
             continue;
-        const uint32_t xi = rl.xinfo[r];
+        const uint32_t xi = VL.xi(r);
         const uint32_t y = run_y(xi);
-        set_range(out + size_t(y) * P.WWp, int(run_x(xi)), int(run_end(rl.xinfo, r, rl.rowoff[y + 1], P.W)));
+        set_range(out + size_t(y) * P.WWp, int(run_x(xi)), int(VL.end(r, VL.ro(y + 1), P.W)));
     }
     __syncthreads();
 }
@@ -979,40 +1056,40 @@ __device__ void hysteresis_phase(const FusedArgs &P, const RunSet &ru, uint32_t 
 // ------------------------------------------------------------------------------------------------------------------
 // remove small objects (RemoveSmallObjects :146-181), in place on img
 // ------------------------------------------------------------------------------------------------------------------
-__device__ void rso_phase(const FusedArgs &P, uint32_t *img, const RunSet &rs, uint32_t T, uint32_t *link, int *st_s, int *st_e,
+template <bool SM>
+__device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, uint32_t T, uint32_t *link, int *st_s, int *st_e,
                           int *st_x, int min_size)
 {
-    const uint32_t frame_root = ld(rs.parent + T);
     // roots: zero the statistics; link = outer background region (components) / parent component (holes)
     for (uint32_t r = threadIdx.x; r <= T; r += NT) {
-        if (r < T && ld(rs.parent + r) != r)
+        if (r < T && V.par(r) != r)
             continue;
         st(st_s + r, 0);
         st(st_e + r, 0);
         st(st_x + r, 0);
         if (r == T)
             continue;
-        const uint32_t xi = rs.xinfo[r];
+        const uint32_t xi = V.xi(r);
         const uint32_t s = run_x(xi);
         if (run_v(xi))
-            st(link + r, s == 0 ? T : bg_region(rs.parent, r - 1, T, frame_root)); // region left of the first pixel
+            st(link + r, s == 0 ? T : V.region(r - 1, T)); // region left of the first pixel
         else
-            st(link + r, (r == frame_root || s == 0) ? kNoLabel : ld(rs.parent + r - 1)); // component left of the hole
+            st(link + r, (s == 0 || V.is_frame(r)) ? kNoLabel : V.par(r - 1)); // component left of the hole
     }
     __syncthreads();
     // contour statistics, accumulated on the contour's owner: the component for its outer contour, the hole's
     // background region for a hole contour
     for (uint32_t r = threadIdx.x; r < T; r += NT) {
-        const uint32_t xi = rs.xinfo[r];
+        const uint32_t xi = V.xi(r);
         if (!run_v(xi))
             continue;
         const int s = int(run_x(xi)), y = int(run_y(xi));
-        const int e = int(run_end(rs.xinfo, r, rs.rowoff[y + 1], P.W));
-        const uint32_t C = ld(rs.parent + r);
+        const int e = int(V.end(r, V.ro(y + 1), P.W));
+        const uint32_t C = V.par(r);
         const uint32_t bout = ld(link + C);
         auto owner = [&](uint32_t b) { return b == bout ? C : b; };
-        const uint32_t own_l = owner(s == 0 ? T : bg_region(rs.parent, r - 1, T, frame_root));
-        const uint32_t own_r = owner(e == P.W - 1 ? T : bg_region(rs.parent, r + 1, T, frame_root));
+        const uint32_t own_l = owner(s == 0 ? T : V.region(r - 1, T));
+        const uint32_t own_r = owner(e == P.W - 1 ? T : V.region(r + 1, T));
         // horizontal cracks at the two run ends, and the convex corners there: 2x2 blocks in which a run end is the
         // only foreground pixel
         int xl = 0, xr = 0;
@@ -1046,33 +1123,33 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const RunSet &rs, u
                 atomicAdd(&st_e[owner(T)], e - s + 1);
                 continue;
             }
-            const uint32_t a = rs.rowoff[yy], b = rs.rowoff[yy + 1];
-            for (uint32_t j = run_at(rs.xinfo, a, b, uint32_t(s)); j < b; ++j) {
-                const uint32_t xj = rs.xinfo[j];
+            const uint32_t a = V.ro(yy), b = V.ro(yy + 1);
+            for (uint32_t j = V.at(a, b, uint32_t(s)); j < b; ++j) {
+                const uint32_t xj = V.xi(j);
                 if (int(run_x(xj)) > e)
                     break;
                 if (run_v(xj))
                     continue;
-                const int js = max(int(run_x(xj)), s), je = min(int(run_end(rs.xinfo, j, b, P.W)), e);
-                atomicAdd(&st_e[owner(bg_region(rs.parent, j, T, frame_root))], je - js + 1);
+                const int js = max(int(run_x(xj)), s), je = min(int(V.end(j, b, P.W)), e);
+                atomicAdd(&st_e[owner(V.region(j, T))], je - js + 1);
             }
         }
     }
     __syncthreads();
     // per root: st_e <- small flag (2*area < 2*min_size; contourArea(c) < min_size, :171)
     for (uint32_t r = threadIdx.x; r < T; r += NT) {
-        if (ld(rs.parent + r) != r)
+        if (V.par(r) != r)
             continue;
         const long long s = ld(st_s + r);
         const int cracks = ld(st_e + r);
         const long long len = (long long)cracks - ld(st_x + r);
-        const long long two_a = run_v(rs.xinfo[r]) ? 2 * s - len - 2 : 2 * (s < 0 ? -s : s) + len - 2;
+        const long long two_a = run_v(V.xi(r)) ? 2 * s - len - 2 : 2 * (s < 0 ? -s : s) + len - 2;
         st(st_e + r, (cracks > 0 && two_a < 2ll * min_size) ? 1 : 0);
     }
     __syncthreads();
     // per component: st_x <- parity of the number of consecutive small contours up the nesting chain
     for (uint32_t r = threadIdx.x; r < T; r += NT) {
-        if (ld(rs.parent + r) != r || !run_v(rs.xinfo[r]))
+        if (V.par(r) != r || !run_v(V.xi(r)))
             continue;
         int count = 0;
         uint32_t cur = r;
@@ -1096,12 +1173,12 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const RunSet &rs, u
     __syncthreads();
     // clear the pixels the single filled drawContours call erases (:178)
     for (uint32_t r = threadIdx.x; r < T; r += NT) {
-        const uint32_t xi = rs.xinfo[r];
+        const uint32_t xi = V.xi(r);
         if (!run_v(xi))
             continue;
         const int s = int(run_x(xi)), y = int(run_y(xi));
-        const int e = int(run_end(rs.xinfo, r, rs.rowoff[y + 1], P.W));
-        const uint32_t C = ld(rs.parent + r);
+        const int e = int(V.end(r, V.ro(y + 1), P.W));
+        const uint32_t C = V.par(r);
         uint32_t *row = img + size_t(y) * P.WWp;
         if (ld(st_x + C)) {
             clear_range(row, s, e);
@@ -1109,9 +1186,9 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const RunSet &rs, u
         }
         const uint32_t bout = ld(link + C);
         auto is_small = [&](uint32_t b) { return ld(st_e + (b == bout ? C : b)) != 0; };
-        if (is_small(s == 0 ? T : bg_region(rs.parent, r - 1, T, frame_root)))
+        if (is_small(s == 0 ? T : V.region(r - 1, T)))
             clear_range(row, s, s);
-        if (is_small(e == P.W - 1 ? T : bg_region(rs.parent, r + 1, T, frame_root)))
+        if (is_small(e == P.W - 1 ? T : V.region(r + 1, T)))
             clear_range(row, e, e);
         for (int dy = -1; dy <= 1; dy += 2) {
             const int yy = y + dy;
@@ -1120,14 +1197,14 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const RunSet &rs, u
                     clear_range(row, s, e);
                 continue;
             }
-            const uint32_t a = rs.rowoff[yy], b = rs.rowoff[yy + 1];
-            for (uint32_t j = run_at(rs.xinfo, a, b, uint32_t(s)); j < b; ++j) {
-                const uint32_t xj = rs.xinfo[j];
+            const uint32_t a = V.ro(yy), b = V.ro(yy + 1);
+            for (uint32_t j = V.at(a, b, uint32_t(s)); j < b; ++j) {
+                const uint32_t xj = V.xi(j);
                 if (int(run_x(xj)) > e)
                     break;
-                if (run_v(xj) || !is_small(bg_region(rs.parent, j, T, frame_root)))
+                if (run_v(xj) || !is_small(V.region(j, T)))
                     continue;
-                clear_range(row, max(int(run_x(xj)), s), min(int(run_end(rs.xinfo, j, b, P.W)), e));
+                clear_range(row, max(int(run_x(xj)), s), min(int(V.end(j, b, P.W)), e));
             }
         }
     }
@@ -1138,21 +1215,22 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const RunSet &rs, u
 // hole fill (FillHoles :183-221), in place: set every background run that is not connected to the seed corner.
 // white <- 1 when the seed pixel itself is set (the flood fill is then a no-op and the result is all 255).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ void fill_phase(const FusedArgs &P, uint32_t *img, const RunSet &rs, uint32_t T, int *white)
+template <bool SM>
+__device__ void fill_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, uint32_t T, int *white)
 {
     // seed = (0,0) if that pixel is set, else the bottom-right corner (follow the code :201-209, not its comment)
-    const uint32_t seed = run_v(rs.xinfo[0]) ? 0u : T - 1u;
-    if (run_v(rs.xinfo[seed])) {
+    const uint32_t seed = run_v(V.xi(0)) ? 0u : T - 1u;
+    if (run_v(V.xi(seed))) {
         if (threadIdx.x == 0)
             *white = 1;
     } else {
-        const uint32_t seed_root = ld(rs.parent + seed);
+        const uint32_t seed_root = V.par(seed);
         for (uint32_t r = threadIdx.x; r < T; r += NT) {
-            const uint32_t xi = rs.xinfo[r];
-            if (run_v(xi) || ld(rs.parent + r) == seed_root)
+            const uint32_t xi = V.xi(r);
+            if (run_v(xi) || V.par(r) == seed_root)
                 continue;
             const uint32_t y = run_y(xi);
-            set_range(img + size_t(y) * P.WWp, int(run_x(xi)), int(run_end(rs.xinfo, r, rs.rowoff[y + 1], P.W)));
+            set_range(img + size_t(y) * P.WWp, int(run_x(xi)), int(V.end(r, V.ro(y + 1), P.W)));
         }
     }
     __syncthreads();
@@ -1216,14 +1294,16 @@ __global__ void __launch_bounds__(NT, 2) highlight_fused_kernel(const FusedArgs 
     const size_t slot = blockIdx.x;
     uint32_t *A = P.bits + slot * kImages * size_t(P.nwords);
     uint32_t *U = A + P.nwords, *L = U + P.nwords, *Tm = L + P.nwords;
-    uint32_t *rbase = P.runs + slot * kRunArrays * size_t(P.cap);
+    uint32_t *rbase = P.runs + slot * P.run_words;
     uint32_t *ro = P.rowoff + slot * 2 * size_t(P.rstride);
-    const RunSet ra{rbase, rbase + P.cap, ro};
-    const RunSet rb{rbase + 2 * size_t(P.cap), rbase + 3 * size_t(P.cap), ro + P.rstride};
+    uint32_t *fb = rbase + kRunArrays * size_t(P.cap); // FRAME flag bits of set a (set b is never labelled with FRAME)
+    const RunSet ra{rbase, rbase + P.cap, ro, fb};
+    const RunSet rb{rbase + 2 * size_t(P.cap), rbase + 3 * size_t(P.cap), ro + P.rstride, fb};
     uint32_t *link = rbase + 4 * size_t(P.cap);
     int *st_s = reinterpret_cast<int *>(rbase + 5 * size_t(P.cap));
     int *st_e = reinterpret_cast<int *>(rbase + 6 * size_t(P.cap));
     int *st_x = reinterpret_cast<int *>(rbase + 7 * size_t(P.cap));
+    const SmemRuns sm = smem_runs(P, dyn);
 
     for (;;) {
         if (threadIdx.x == 0) {
@@ -1267,18 +1347,31 @@ __global__ void __launch_bounds__(NT, 2) highlight_fused_kernel(const FusedArgs 
         }
         prof_tick(P.prof, P.prof, sh, kPDilateA);
         CVVP_DEBUG_STAGE(4, A, false)
-        uint32_t T = label_runs<true, true, true>(P, sh, A, ra, dyn);
-        rso_phase(P, A, ra, T, link, st_s, st_e, st_x, P.min_th);
+        bool sm_ok;
+        uint32_t T = label_runs<true, true, true>(P, sh, A, ra, sm, sm_ok);
+        if (sm_ok)
+            rso_phase(P, A, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link, st_s, st_e, st_x, P.min_th);
+        else
+            rso_phase(P, A, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link, st_s, st_e, st_x, P.min_th);
         prof_tick(P.prof, P.prof, sh, kPRso);
         CVVP_DEBUG_STAGE(5, A, false)
-        T = label_runs<false, false, false>(P, sh, A, ra, dyn);
-        fill_phase(P, A, ra, T, &sh.white[0]);
+        T = label_runs<false, false, false>(P, sh, A, ra, sm, sm_ok);
+        if (sm_ok)
+            fill_phase(P, A, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, &sh.white[0]);
+        else
+            fill_phase(P, A, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, &sh.white[0]);
         prof_tick(P.prof, P.prof, sh, kPFill);
         CVVP_DEBUG_STAGE(6, A, sh.white[0] != 0)
         // ---- branch B: hysteresis -> open -> remove small -> fill holes                                 (:54-73)
-        const uint32_t Tu = label_runs<true, true, true>(P, sh, U, ra, dyn);
-        const uint32_t Tl = label_runs<false, false, true>(P, sh, L, rb, dyn);
-        hysteresis_phase(P, ra, Tu, rb, Tl, st_x, U); // U's bits are no longer needed: it now holds the result
+        const uint32_t Tu = label_runs<true, true, true>(P, sh, U, ra, sm, sm_ok);
+        const uint32_t Tl = label_runs<false, false, true>(P, sh, L, rb, sm, sm_ok);
+        // U's bits are no longer needed: its image now receives the result
+        if (sm_ok)
+            hysteresis_phase(P, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, Tu, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits},
+                             Tl, st_x, U);
+        else
+            hysteresis_phase(P, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, Tu, View<false>{rb.xinfo, rb.rowoff, rb.parent, rb.fbits},
+                             Tl, st_x, U);
         prof_tick(P.prof, P.prof, sh, kPHyst);
         CVVP_DEBUG_STAGE(7, U, false)
         if (P.band_rows > 0) {
@@ -1298,12 +1391,18 @@ __global__ void __launch_bounds__(NT, 2) highlight_fused_kernel(const FusedArgs 
         }
         prof_tick(P.prof, P.prof, sh, kPDilateB);
         CVVP_DEBUG_STAGE(8, U, false)
-        T = label_runs<true, true, true>(P, sh, U, ra, dyn);
-        rso_phase(P, U, ra, T, link, st_s, st_e, st_x, P.min_hyst);
+        T = label_runs<true, true, true>(P, sh, U, ra, sm, sm_ok);
+        if (sm_ok)
+            rso_phase(P, U, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link, st_s, st_e, st_x, P.min_hyst);
+        else
+            rso_phase(P, U, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link, st_s, st_e, st_x, P.min_hyst);
         prof_tick(P.prof, P.prof, sh, kPRso);
         CVVP_DEBUG_STAGE(9, U, false)
-        T = label_runs<false, false, false>(P, sh, U, ra, dyn);
-        fill_phase(P, U, ra, T, &sh.white[1]);
+        T = label_runs<false, false, false>(P, sh, U, ra, sm, sm_ok);
+        if (sm_ok)
+            fill_phase(P, U, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, &sh.white[1]);
+        else
+            fill_phase(P, U, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, &sh.white[1]);
         prof_tick(P.prof, P.prof, sh, kPFill);
         CVVP_DEBUG_STAGE(10, U, sh.white[1] != 0)
 #undef CVVP_DEBUG_STAGE
@@ -1416,9 +1515,14 @@ FusedGeom fused_geom(const HlGeom &g)
     return fg;
 }
 
+size_t run_words(const FusedGeom &fg)
+{
+    return size_t(kRunArrays) * fg.cap + round_up_sz(fg.cap / 32 + 4, 4);
+}
+
 size_t slot_bytes(const FusedGeom &fg)
 {
-    return sizeof(uint32_t) * (size_t(kImages) * fg.nwords + size_t(kRunArrays) * fg.cap + 2 * size_t(fg.rstride));
+    return sizeof(uint32_t) * (size_t(kImages) * fg.nwords + run_words(fg) + 2 * size_t(fg.rstride));
 }
 } // namespace
 
@@ -1480,7 +1584,7 @@ static int ensure_fused(cvvp_ctx *ctx, HighlightState *st)
     const int slots = fused_frames_in_flight(ctx, st);
     const FusedGeom fg = fused_geom(st->g);
     const size_t nb = sizeof(uint32_t) * size_t(slots) * kImages * fg.nwords;
-    const size_t nr = sizeof(uint32_t) * size_t(slots) * kRunArrays * fg.cap;
+    const size_t nr = sizeof(uint32_t) * size_t(slots) * run_words(fg);
     const size_t no = sizeof(uint32_t) * size_t(slots) * 2 * fg.rstride;
     if (cudaMalloc(reinterpret_cast<void **>(&fs.bits), nb) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void **>(&fs.runs), nr) != cudaSuccess ||
@@ -1528,6 +1632,7 @@ int highlight_fused_batch(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, 
     P.wwp_shift = fg.wwp_shift;
     P.nwords = fg.nwords;
     P.cap = fg.cap;
+    P.run_words = run_words(fg);
     P.rstride = fg.rstride;
     P.bits = st->fs.bits;
     P.runs = st->fs.runs;
