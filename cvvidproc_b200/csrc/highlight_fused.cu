@@ -114,6 +114,7 @@ struct Shared {
     uint32_t wsum[NW];
     uint32_t T[2];
     int white[2];
+    int changed; // remove-small-objects cleared at least one pixel of the current image
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -598,6 +599,8 @@ __device__ __forceinline__ uint4 morph_quad_v(const FusedArgs &P, const uint32_t
 
 __device__ __forceinline__ uint4 valid_quad(const FusedArgs &P, int qc)
 {
+    if (32 * (4 * qc + 4) <= P.W)
+        return make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     return make_uint4(valid_mask(P, 4 * qc), valid_mask(P, 4 * qc + 1), valid_mask(P, 4 * qc + 2), valid_mask(P, 4 * qc + 3));
 }
 
@@ -723,20 +726,24 @@ __device__ __forceinline__ uint32_t quad_transitions(const FusedArgs &P, const u
 {
     const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
     const bool row_start = wx0 == 0;
+    const bool full = 32 * (wx0 + 4) <= P.W; // all four words lie inside the image: no column masks needed
     const uint32_t any = w.x | w.y | w.z | w.w, all = w.x & w.y & w.z & w.w;
-    if (!row_start && ((any == 0 && prev_msb == 0) || (all == 0xFFFFFFFFu && prev_msb == 1 && 32 * (wx0 + 4) <= P.W))) {
+    if (!row_start && ((any == 0 && prev_msb == 0) || (all == 0xFFFFFFFFu && prev_msb == 1 && full))) {
         t[0] = t[1] = t[2] = t[3] = 0;
         return 0;
     }
     uint32_t p = row_start ? (~w.x & 1u) : prev_msb; // x = 0 always starts a run
-    uint32_t c = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        t[k] = (ww[k] ^ ((ww[k] << 1) | p)) & valid_mask(P, wx0 + k);
+        t[k] = ww[k] ^ ((ww[k] << 1) | p);
         p = ww[k] >> 31;
-        c += __popc(t[k]);
     }
-    return c;
+    if (!full) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            t[k] &= valid_mask(P, wx0 + k);
+    }
+    return __popc(t[0]) + __popc(t[1]) + __popc(t[2]) + __popc(t[3]);
 }
 
 constexpr int kQU = 4; // quads (128-bit loads) in flight per lane in the run extraction
@@ -1058,8 +1065,10 @@ __device__ void hysteresis_phase(const FusedArgs &P, const View<false> &VU, uint
 // ------------------------------------------------------------------------------------------------------------------
 template <bool SM>
 __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, uint32_t T, uint32_t *link, int *st_s, int *st_e,
-                          int *st_x, int min_size)
+                          int *st_x, int min_size, int *changed)
 {
+    if (threadIdx.x == 0)
+        *changed = 0;
     // roots: zero the statistics; link = outer background region (components) / parent component (holes)
     for (uint32_t r = threadIdx.x; r <= T; r += NT) {
         if (r < T && V.par(r) != r)
@@ -1180,21 +1189,29 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, 
         const int e = int(V.end(r, V.ro(y + 1), P.W));
         const uint32_t C = V.par(r);
         uint32_t *row = img + size_t(y) * P.WWp;
+        bool cleared = false;
         if (ld(st_x + C)) {
             clear_range(row, s, e);
+            *changed = 1;
             continue;
         }
         const uint32_t bout = ld(link + C);
         auto is_small = [&](uint32_t b) { return ld(st_e + (b == bout ? C : b)) != 0; };
-        if (is_small(s == 0 ? T : V.region(r - 1, T)))
+        if (is_small(s == 0 ? T : V.region(r - 1, T))) {
             clear_range(row, s, s);
-        if (is_small(e == P.W - 1 ? T : V.region(r + 1, T)))
+            cleared = true;
+        }
+        if (is_small(e == P.W - 1 ? T : V.region(r + 1, T))) {
             clear_range(row, e, e);
+            cleared = true;
+        }
         for (int dy = -1; dy <= 1; dy += 2) {
             const int yy = y + dy;
             if (yy < 0 || yy >= P.H) {
-                if (is_small(T))
+                if (is_small(T)) {
                     clear_range(row, s, e);
+                    cleared = true;
+                }
                 continue;
             }
             const uint32_t a = V.ro(yy), b = V.ro(yy + 1);
@@ -1205,8 +1222,11 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, 
                 if (run_v(xj) || !is_small(V.region(j, T)))
                     continue;
                 clear_range(row, max(int(run_x(xj)), s), min(int(V.end(j, b, P.W)), e));
+                cleared = true;
             }
         }
+        if (cleared)
+            *changed = 1;
     }
     __syncthreads();
 }
@@ -1350,12 +1370,17 @@ __global__ void __launch_bounds__(NT, 2) highlight_fused_kernel(const FusedArgs 
         bool sm_ok;
         uint32_t T = label_runs<true, true, true>(P, sh, A, ra, sm, sm_ok);
         if (sm_ok)
-            rso_phase(P, A, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link, st_s, st_e, st_x, P.min_th);
+            rso_phase(P, A, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link, st_s, st_e, st_x, P.min_th,
+                      &sh.changed);
         else
-            rso_phase(P, A, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link, st_s, st_e, st_x, P.min_th);
+            rso_phase(P, A, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link, st_s, st_e, st_x, P.min_th,
+                      &sh.changed);
         prof_tick(P.prof, P.prof, sh, kPRso);
         CVVP_DEBUG_STAGE(5, A, false)
-        T = label_runs<false, false, false>(P, sh, A, ra, sm, sm_ok);
+        // the hole fill needs the 4-connected background regions of the image: when nothing was cleared they are the
+        // ones just labelled, else the image is labelled again
+        if (sh.changed)
+            T = label_runs<false, false, false>(P, sh, A, ra, sm, sm_ok);
         if (sm_ok)
             fill_phase(P, A, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, &sh.white[0]);
         else
@@ -1393,12 +1418,15 @@ __global__ void __launch_bounds__(NT, 2) highlight_fused_kernel(const FusedArgs 
         CVVP_DEBUG_STAGE(8, U, false)
         T = label_runs<true, true, true>(P, sh, U, ra, sm, sm_ok);
         if (sm_ok)
-            rso_phase(P, U, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link, st_s, st_e, st_x, P.min_hyst);
+            rso_phase(P, U, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link, st_s, st_e, st_x, P.min_hyst,
+                      &sh.changed);
         else
-            rso_phase(P, U, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link, st_s, st_e, st_x, P.min_hyst);
+            rso_phase(P, U, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link, st_s, st_e, st_x, P.min_hyst,
+                      &sh.changed);
         prof_tick(P.prof, P.prof, sh, kPRso);
         CVVP_DEBUG_STAGE(9, U, false)
-        T = label_runs<false, false, false>(P, sh, U, ra, sm, sm_ok);
+        if (sh.changed)
+            T = label_runs<false, false, false>(P, sh, U, ra, sm, sm_ok);
         if (sm_ok)
             fill_phase(P, U, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, &sh.white[1]);
         else
