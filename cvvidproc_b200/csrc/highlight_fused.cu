@@ -34,7 +34,7 @@ namespace cvvp
 {
 namespace
 {
-constexpr int NT = 512; // threads per CTA
+constexpr int NT = 1024; // threads per CTA (one CTA per SM)
 constexpr int NW = NT / 32;
 constexpr int kImages = 4;    // A, U (later B), L, Tm
 constexpr int kRunArrays = 8; // xinfo0, parent0, xinfo1, parent1, link, st_s, st_e, st_x
@@ -1299,7 +1299,7 @@ __device__ void expand_phase(const FusedArgs &P, unsigned f, const uint32_t *A, 
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kSmemOffs = 256; // structuring-element taps cached in shared memory
 
-__global__ void __launch_bounds__(NT, 2) highlight_fused_kernel(const FusedArgs P)
+__global__ void __launch_bounds__(NT, 1) highlight_fused_kernel(const FusedArgs P)
 {
     extern __shared__ uint4 dyn_smem4[];
     uint32_t *dyn = reinterpret_cast<uint32_t *>(dyn_smem4);
@@ -1463,7 +1463,7 @@ struct FusedGeom {
     uint32_t nwords, cap, rstride;
 };
 
-constexpr size_t kDynSmemBytes = 96 * 1024; // per CTA; two CTAs per SM
+constexpr size_t kDynSmemBytes = 192 * 1024; // per CTA; one CTA per SM
 
 // rows per band of the shared-memory opening (0: the tiles do not fit, use the global-memory taps)
 int pick_band_rows(const FusedGeom &fg, int dy_min, int dy_max, const MorphPlan &plan)
