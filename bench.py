@@ -52,9 +52,9 @@ def load_peaks():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic():
-    """dram bytes per launch of the median kernel from the committed ncu --set full capture."""
-    p = REPO / "profiles" / "median_ncu_summary.json"
+def load_traffic(name: str = "median_ncu_summary.json"):
+    """dram bytes per launch of a kernel from its committed ncu --set full capture (profiles/)."""
+    p = REPO / "profiles" / name
     if p.exists():
         try:
             d = json.loads(p.read_text())
@@ -361,7 +361,8 @@ def run_highlight_section(ctx, torch, dist, rank, local_rank, world, args, sampl
                 "d2h_bytes_per_step": int(nfr * npix), "ms_per_step": e2e_s * 1e3},
         "roofline": {"bound": "hbm", "achieved": 2.0 * nfr * npix / (ms * 1e-3) / 1e9, "peak": load_peaks()[0],
                      "unit": "GB/s", "frac": 2.0 * nfr * npix / (ms * 1e-3) / 1e9 / load_peaks()[0],
-                     "traffic": None, "kernel": "highlight_fused_kernel",
+                     "traffic": load_traffic("highlight_ncu_summary.json") if (world == 1 and nfr == 1024) else None,
+                     "kernel": "highlight_fused_kernel",
                      "note": "algorithmic bytes = frame in + mask out (2 B/px); one fused kernel launch per step"},
         "config": {"workload": w["name"]},
     }
