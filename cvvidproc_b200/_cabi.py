@@ -56,6 +56,7 @@ def load():
         "cvvp_ctx_launch_count": (i64, [vp]),
         "cvvp_host_alloc": (i32, [sz, C.POINTER(vp)]),
         "cvvp_host_free": (i32, [vp]),
+        "cvvp_ctx_copy_to_host": (i32, [vp, vp, vp, sz]),
         "cvvp_median_begin": (i32, [vp, sz, i64]),
         "cvvp_median_push": (i32, [vp, vp, i64, sz]),
         "cvvp_median_count": (i64, [vp]),
@@ -70,6 +71,13 @@ def load():
         "cvvp_highlight_set_path": (i32, [vp, i32]),
         "cvvp_highlight_frames_in_flight": (i32, [vp, C.POINTER(i32)]),
         "cvvp_synth_frames_device": (i32, [vp, vp, sz, i32, i32, i32, i32, i64, i64, u32, i32, vp]),
+        "cvvp_median_shard_begin": (i32, [vp, sz, i32, i32]),
+        "cvvp_median_shard_export": (i32, [vp, vp]),
+        "cvvp_median_shard_import": (i32, [vp, i32, vp]),
+        "cvvp_median_shard_attach": (i32, [vp, i32, vp]),
+        "cvvp_median_shard_phase": (i32, [vp, i32, vp, i64, sz, vp]),
+        "cvvp_median_shard_result": (i32, [vp, C.POINTER(vp)]),
+        "cvvp_median_shard_end": (i32, [vp]),
     }
     global BOUND_SYMBOLS
     BOUND_SYMBOLS = sorted(sigs)
@@ -163,6 +171,11 @@ class Context:
     def synchronize(self):
         self._check(self._lib.cvvp_ctx_synchronize(self._h))
 
+    def copy_to_host(self, device_ptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, np.uint8)
+        self._check(self._lib.cvvp_ctx_copy_to_host(self._h, out.ctypes.data, device_ptr, nbytes))
+        return out
+
     # -- median ---------------------------------------------------------------------------
     def median_begin(self, nelem: int, nframes_hint: int = -1):
         self._check(self._lib.cvvp_median_begin(self._h, nelem, nframes_hint))
@@ -223,6 +236,36 @@ class Context:
         v = C.c_float()
         self._check(self._lib.cvvp_median_last_kernel_ms(self._h, C.byref(v)))
         return float(v.value)
+
+    # -- frame-sharded median (one context per rank) ----------------------------------------
+    IPC_HANDLE_BYTES = 64
+
+    def median_shard_begin(self, nelem: int, rank: int, world: int):
+        self._check(self._lib.cvvp_median_shard_begin(self._h, nelem, rank, world))
+
+    def median_shard_export(self) -> bytes:
+        buf = C.create_string_buffer(self.IPC_HANDLE_BYTES)
+        self._check(self._lib.cvvp_median_shard_export(self._h, buf))
+        return bytes(buf.raw)
+
+    def median_shard_import(self, peer: int, handle: bytes):
+        if len(handle) != self.IPC_HANDLE_BYTES:
+            raise ValueError("an exported handle is 64 bytes")
+        self._check(self._lib.cvvp_median_shard_import(self._h, peer, C.create_string_buffer(handle, len(handle))))
+
+    def median_shard_attach(self, peer: int, peer_ctx: "Context"):
+        self._check(self._lib.cvvp_median_shard_attach(self._h, peer, peer_ctx.handle))
+
+    def median_shard_phase(self, phase: int, d_frames: int = 0, nframes: int = 0, frame_stride: int = 0, stream: int = 0):
+        self._check(self._lib.cvvp_median_shard_phase(self._h, phase, d_frames or None, nframes, frame_stride, stream or None))
+
+    def median_shard_result(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.cvvp_median_shard_result(self._h, C.byref(p)))
+        return int(p.value or 0)
+
+    def median_shard_end(self):
+        self._check(self._lib.cvvp_median_shard_end(self._h))
 
     # -- highlight ------------------------------------------------------------------------
     def highlight_begin(self, background: np.ndarray, struct_element: np.ndarray, threshold: int, threshold_lo: int,

@@ -53,12 +53,31 @@ def _run(cmd, log_name: str, verbose: bool) -> None:
 
 
 def build_cuda_lib(force: bool = False, verbose: bool = False) -> Path:
+    """Each .cu is compiled to its own object (in parallel, only when it or a header changed), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+
     sources = sorted(CSRC.glob("*.cu"))
-    deps = sources + sorted(CSRC.glob("*.hpp")) + sorted(CSRC.glob("*.cuh")) + [REPO / "include" / "cvvp.h"]
-    if not force and _newer_than(LIB_PATH, deps):
+    headers = sorted(CSRC.glob("*.hpp")) + sorted(CSRC.glob("*.cuh")) + [REPO / "include" / "cvvp.h"]
+    objdir = PKG_DIR / "_buildlogs" / "obj"
+    objdir.mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+    todo = []
+    for src in sources:
+        obj = objdir / (src.stem + ".o")
+        if force or not _newer_than(obj, [src] + headers):
+            todo.append((src, obj))
+    if not todo and _newer_than(LIB_PATH, sources + headers):
         return LIB_PATH
-    cmd = [_nvcc(), "-shared", *NVCC_FLAGS, "-I", str(REPO / "include"), "-o", str(LIB_PATH), *map(str, sources)]
-    _run(cmd, "libcvvp_cuda.log", verbose)
+
+    def compile_one(job):
+        src, obj = job
+        _run([nvcc, "-c", *NVCC_FLAGS, "-I", str(REPO / "include"), "-o", str(obj), str(src)], f"{src.stem}.log", verbose)
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(todo)))) as ex:
+        list(ex.map(compile_one, todo))
+    objs = [str(objdir / (src.stem + ".o")) for src in sources]
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", str(LIB_PATH), *objs],
+         "libcvvp_cuda.log", verbose)
     return LIB_PATH
 
 

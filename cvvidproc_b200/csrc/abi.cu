@@ -170,6 +170,8 @@ int cvvp_ctx_create(int device, cvvp_ctx **out_ctx)
         return bail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess)
         return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreate(&ctx->ev_start)) != cudaSuccess)
         return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev_stop)) != cudaSuccess)
@@ -199,6 +201,8 @@ void cvvp_ctx_destroy(cvvp_ctx *ctx)
         cudaStreamSynchronize(ctx->compute);
     if (ctx->copy)
         cudaStreamSynchronize(ctx->copy);
+    if (ctx->copy_out)
+        cudaStreamSynchronize(ctx->copy_out);
     for (auto &b : ctx->staging) {
         if (b.done)
             cudaEventDestroy(b.done);
@@ -206,6 +210,7 @@ void cvvp_ctx_destroy(cvvp_ctx *ctx)
             cudaFreeHost(b.host);
     }
     highlight_release(ctx);
+    median_shard_release(ctx);
     if (ctx->med.d_stack)
         cudaFree(ctx->med.d_stack);
     if (ctx->med.d_out)
@@ -220,6 +225,8 @@ void cvvp_ctx_destroy(cvvp_ctx *ctx)
         cudaStreamDestroy(ctx->compute);
     if (ctx->copy)
         cudaStreamDestroy(ctx->copy);
+    if (ctx->copy_out)
+        cudaStreamDestroy(ctx->copy_out);
     cudaGetLastError();
     delete ctx;
 }
@@ -236,6 +243,7 @@ int cvvp_ctx_synchronize(cvvp_ctx *ctx)
     DeviceGuard guard(ctx->device);
     CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy));
     CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->compute));
+    CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_out));
     for (auto &b : ctx->staging)
         b.in_flight = false;
     return CVVP_OK;
@@ -283,6 +291,16 @@ int cvvp_host_free(void *ptr)
         cudaGetLastError();
         return fail(nullptr, CVVP_ERR_CUDA, "cudaFreeHost failed: %s", cudaGetErrorString(e));
     }
+    return CVVP_OK;
+}
+
+int cvvp_ctx_copy_to_host(cvvp_ctx *ctx, void *host_dst, const void *device_src, size_t bytes)
+{
+    if (!ctx || !host_dst || !device_src)
+        return fail(ctx, CVVP_ERR_INVALID, "cvvp_ctx_copy_to_host: null argument");
+    DeviceGuard guard(ctx->device);
+    CVVP_CUDA_OK(ctx, cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, ctx->compute));
+    CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->compute));
     return CVVP_OK;
 }
 
@@ -508,6 +526,7 @@ int cvvp_highlight_end(cvvp_ctx *ctx)
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->compute);
+    cudaStreamSynchronize(ctx->copy_out);
     highlight_release(ctx);
     return CVVP_OK;
 }

@@ -37,6 +37,17 @@ struct MedianJob {
     size_t d_stack_bytes{0};
 };
 struct HighlightState; // highlight_state.hpp
+
+// Where the counting rounds of a frame-sharded median push their per-element nibble counts (median_shard.cu):
+// element e belongs to rank e / slice, whose receive area for THIS rank's counts starts at dst[e / slice]
+// (8 words = 16 u16 counts per element, peer memory over NVLink or local).
+constexpr int kMaxShardRanks = 16;
+struct ShardPush {
+    uint32_t *dst[kMaxShardRanks];
+    const uint32_t *sel; // round 2: per element, the globally selected high nibble in bits 0..3
+    uint32_t slice;
+};
+struct MedianShard; // median_shard.cu
 } // namespace cvvp
 
 struct cvvp_ctx {
@@ -46,7 +57,8 @@ struct cvvp_ctx {
     int cc_minor{0};
     size_t smem_optin{0};
     cudaStream_t compute{nullptr};
-    cudaStream_t copy{nullptr};
+    cudaStream_t copy{nullptr};     // host -> device
+    cudaStream_t copy_out{nullptr}; // device -> host (so both directions of the link overlap)
     cudaEvent_t ev_start{nullptr};
     cudaEvent_t ev_stop{nullptr};
     cudaEvent_t ev_copy{nullptr};
@@ -56,6 +68,7 @@ struct cvvp_ctx {
     cvvp::EncodeTiledFn encode_tiled{nullptr};
     cvvp::MedianJob med;
     cvvp::HighlightState *hl{nullptr};
+    cvvp::MedianShard *shard{nullptr};
     std::vector<cvvp::StagingBuf> staging;
     size_t staging_next{0};
 };
@@ -97,10 +110,14 @@ struct DeviceGuard {
 // median.cu
 int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
                   uint8_t *d_out, cudaStream_t stream);
+int median_launch_mode(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
+                       uint8_t *d_out, int mode, const ShardPush &push, cudaStream_t stream);
 // median_pipe.cu
 long long median_max_frames();
 int median_pipe_launch(cvvp_ctx *ctx, const CUtensorMap &tmap, int log2s, uint8_t *d_out, uint32_t nelem, uint32_t nframes,
-                       uint32_t nst, cudaStream_t stream);
+                       uint32_t nst, int mode, const ShardPush &push, cudaStream_t stream);
+// median_shard.cu
+void median_shard_release(cvvp_ctx *ctx);
 // highlight.cu
 void highlight_release(cvvp_ctx *ctx);
 int highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, int height, const uint8_t *selem, int kw, int kh,

@@ -821,12 +821,15 @@ int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
         return fail(ctx, CVVP_ERR_INVALID, "highlight: bad arguments");
     if (n == 0)
         return CVVP_OK;
-    // chunked: H2D on the copy stream, kernels + D2H on the compute stream.  The device side is far faster than the
-    // link, so chunks are sized for the copies (~64 MB) rather than for the kernel.
+    // chunked, three streams: H2D on `copy`, kernels on `compute`, D2H on `copy_out`, so that both directions of
+    // the link stay busy while a chunk is computed.  The device side is far faster than the link, so chunks are
+    // sized for the copies (about n/16 frames, at most one frame per resident CTA) rather than for the kernel.
     long long chunk;
     if (use_fused(st)) {
-        chunk = (64ll << 20) / st->g.npix;
-        if (chunk < 8) chunk = 8;
+        const long long slots = fused_frames_in_flight(ctx, st);
+        chunk = (n + 15) / 16;
+        if (chunk < 16) chunk = 16;
+        if (chunk > slots) chunk = slots;
         if (chunk > n) chunk = n;
     } else {
         chunk = pick_batch(st, n);
@@ -845,9 +848,10 @@ int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
         st->in_bytes = need;
     }
     const size_t half = st->in_bytes;
-    cudaEvent_t up[2] = {nullptr, nullptr}, down[2] = {nullptr, nullptr};
+    cudaEvent_t up[2] = {nullptr, nullptr}, kdone[2] = {nullptr, nullptr}, down[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&kdone[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&down[i], cudaEventDisableTiming);
     }
     int rc = CVVP_OK;
@@ -858,7 +862,7 @@ int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
         uint8_t *din = st->d_in + size_t(b) * half;
         uint8_t *dres = st->d_res + size_t(b) * half;
         if (idx >= 2)
-            cudaStreamWaitEvent(ctx->copy, down[b], 0); // this half's previous results have left the device
+            cudaStreamWaitEvent(ctx->copy, kdone[b], 0); // the kernel that read this input half has finished
         cudaError_t e = cudaMemcpy2DAsync(din, pitch, frames + size_t(done) * frame_stride, frame_stride, np, size_t(nb),
                                           cudaMemcpyHostToDevice, ctx->copy);
         if (e != cudaSuccess) {
@@ -867,25 +871,33 @@ int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
         }
         cudaEventRecord(up[b], ctx->copy);
         cudaStreamWaitEvent(ctx->compute, up[b], 0);
+        if (idx >= 2)
+            cudaStreamWaitEvent(ctx->compute, down[b], 0); // this result half's previous masks have left the device
         rc = highlight_device(ctx, din, nb, pitch, dres, pitch, ctx->compute);
         if (rc != CVVP_OK)
             break;
+        cudaEventRecord(kdone[b], ctx->compute);
+        cudaStreamWaitEvent(ctx->copy_out, kdone[b], 0);
         e = cudaMemcpy2DAsync(masks_out + size_t(done) * out_stride, out_stride, dres, pitch, np, size_t(nb),
-                              cudaMemcpyDeviceToHost, ctx->compute);
+                              cudaMemcpyDeviceToHost, ctx->copy_out);
         if (e != cudaSuccess) {
             rc = fail(ctx, CVVP_ERR_CUDA, "highlight: D2H failed: %s", cudaGetErrorString(e));
             break;
         }
-        cudaEventRecord(down[b], ctx->compute);
+        cudaEventRecord(down[b], ctx->copy_out);
     }
     cudaError_t e1 = cudaStreamSynchronize(ctx->copy);
     cudaError_t e2 = cudaStreamSynchronize(ctx->compute);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->copy_out);
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(up[i]);
+        cudaEventDestroy(kdone[i]);
         cudaEventDestroy(down[i]);
     }
-    if (rc == CVVP_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
-        rc = fail(ctx, CVVP_ERR_CUDA, "highlight: execution failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    if (e1 == cudaSuccess)
+        e1 = e2 != cudaSuccess ? e2 : e3;
+    if (rc == CVVP_OK && e1 != cudaSuccess)
+        rc = fail(ctx, CVVP_ERR_CUDA, "highlight: execution failed: %s", cudaGetErrorString(e1));
     return rc;
 }
 } // namespace cvvp

@@ -28,7 +28,16 @@ namespace cvvp
 int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
                   uint8_t *d_out, cudaStream_t stream)
 {
-    if (!d_frames || !d_out || nframes <= 0 || nelem == 0)
+    if (!d_out)
+        return fail(ctx, CVVP_ERR_INVALID, "median: null output pointer");
+    return median_launch_mode(ctx, d_frames, nframes, nelem, frame_stride, d_out, 0, ShardPush{}, stream);
+}
+
+// mode 0: on-chip select into d_out; modes 1 / 2: the two counting rounds of a frame-sharded job (median_shard.cu)
+int median_launch_mode(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
+                       uint8_t *d_out, int mode, const ShardPush &push, cudaStream_t stream)
+{
+    if (!d_frames || nframes <= 0 || nelem == 0)
         return fail(ctx, CVVP_ERR_INVALID, "median: null pointer or empty stack");
     if ((reinterpret_cast<uintptr_t>(d_frames) & 15u) || (frame_stride & 15u) || frame_stride < nelem)
         return fail(ctx, CVVP_ERR_INVALID,
@@ -62,6 +71,6 @@ int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, siz
                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS)
         return fail(ctx, CVVP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(cr));
-    return median_pipe_launch(ctx, tmap, log2s, d_out, uint32_t(nelem), uint32_t(nframes), nst, stream);
+    return median_pipe_launch(ctx, tmap, log2s, d_out, uint32_t(nelem), uint32_t(nframes), nst, mode, push, stream);
 }
 } // namespace cvvp

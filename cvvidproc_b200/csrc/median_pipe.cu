@@ -44,13 +44,43 @@ constexpr int kStageBytes = 4096;
 constexpr int kStageWords = kStageBytes / 4;
 constexpr int kRing = 2 * kTrWarps; // two private slots per transposer warp
 
+// minterm c of three plane words (a = bit 2 of c, b = bit 1, d = bit 0): one LOP3 with the immediate 1 << c
+template <int C>
+__device__ __forceinline__ uint32_t minterm3(uint32_t a, uint32_t b, uint32_t d)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(d), "n"(1 << C));
+    return r;
+}
+
+// Counts of the 16 values of one nibble over the 32 frame slots of a plane word, restricted to `mask`:
+// acc[c] += count(nibble == 2c) | count(nibble == 2c + 1) << 16.   p3..p0 = the nibble's bit planes, MSB first.
+__device__ __forceinline__ void nibble_counts(uint32_t (&acc)[8], uint32_t p3, uint32_t p2, uint32_t p1, uint32_t p0,
+                                              uint32_t mask)
+{
+    const uint32_t m0 = mask & ~p0, m1 = mask & p0;
+#define CVVP_MT(C)                                                                                                     \
+    {                                                                                                                  \
+        const uint32_t t = minterm3<C>(p3, p2, p1);                                                                    \
+        acc[C] += __popc(t & m0) + (__popc(t & m1) << 16);                                                             \
+    }
+    CVVP_MT(0) CVVP_MT(1) CVVP_MT(2) CVVP_MT(3) CVVP_MT(4) CVVP_MT(5) CVVP_MT(6) CVVP_MT(7)
+#undef CVVP_MT
+}
+
 // LOG2S : log2(32-frame sub-blocks per stage per element); P = 128 >> LOG2S elements per tile
 // JT    : stages per select thread (compile time)
 // NSELW : select warps, 8 (two stage classes, two plane buffers) or 16 (four stage classes, one plane buffer)
-template <int LOG2S, int JT, int NSELW>
+// MODE  : 0 = select the median on chip (single-GPU job)
+//         1 = frame-sharded job, round 1: 16-bin counts of the HIGH nibble of this rank's frames, pushed to the
+//             element's owner rank through peer memory
+//         2 = round 2: 16-bin counts of the LOW nibble among the frames whose high nibble equals the globally selected
+//             one (push.sel[e] & 15), pushed the same way
+template <int LOG2S, int JT, int NSELW, int MODE>
 __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     median_pipe_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ out, const uint32_t nelem,
-                       const uint32_t nframes, const uint32_t nst, const uint32_t ntiles, const uint64_t l2_policy)
+                       const uint32_t nframes, const uint32_t nst, const uint32_t ntiles, const uint64_t l2_policy,
+                       const __grid_constant__ ShardPush push)
 {
     constexpr int S = 1 << LOG2S;
     constexpr int P = 128 >> LOG2S;
@@ -182,6 +212,80 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
         const uint32_t q = (NBUF == 2) ? (it >> 1) : it;
         mbar_wait(&planes_full[buf], q & 1u);
         const uint4 *base = reinterpret_cast<const uint4 *>(planes + buf * kBufWords + s_g * 1024u) + s_p * 64u + s_col;
+        if constexpr (MODE != 0) {
+            // ---- frame-sharded job: nibble counts of this rank's frames, pushed to the owner of the element ----
+            const size_t e = size_t(tile) * P + s_elem;
+            uint32_t acc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                acc[c] = 0;
+            uint32_t h = 0;
+            if (MODE == 1) {
+                uint4 w4[JT];
+#pragma unroll
+                for (int j = 0; j < JT; ++j)
+                    w4[j] = base[j * (G * 256) + 32]; // high-nibble planes
+                __syncwarp();
+                if (lane == 0) {
+                    atomicAdd(const_cast<uint32_t *>(sel_done) + buf, 1u);
+                    mbar_arrive(&planes_empty[buf]);
+                }
+#pragma unroll
+                for (int j = 0; j < JT; ++j)
+                    if ((G * j + s_g) < nst) // rows >= nst hold garbage
+                        nibble_counts(acc, w4[j].w, w4[j].z, w4[j].y, w4[j].x, 0xFFFFFFFFu);
+            } else {
+                h = e < nelem ? (__ldcg(push.sel + e) & 15u) : 0u;
+                const uint32_t f4 = (h & 1u) ? 0u : 0xFFFFFFFFu, f5 = (h & 2u) ? 0u : 0xFFFFFFFFu;
+                const uint32_t f6 = (h & 4u) ? 0u : 0xFFFFFFFFu, f7 = (h & 8u) ? 0u : 0xFFFFFFFFu;
+                uint32_t eq[JT];
+#pragma unroll
+                for (int j = 0; j < JT; ++j) {
+                    const uint4 w = base[j * (G * 256) + 32];
+                    const uint32_t m = (w.x ^ f4) & (w.y ^ f5) & (w.z ^ f6) & (w.w ^ f7); // high nibble == h
+                    eq[j] = (G * j + s_g) < nst ? m : 0u;
+                }
+                uint4 w4[JT];
+#pragma unroll
+                for (int j = 0; j < JT; ++j)
+                    w4[j] = base[j * (G * 256)]; // low-nibble planes
+                __syncwarp();
+                if (lane == 0) {
+                    atomicAdd(const_cast<uint32_t *>(sel_done) + buf, 1u);
+                    mbar_arrive(&planes_empty[buf]);
+                }
+#pragma unroll
+                for (int j = 0; j < JT; ++j)
+                    nibble_counts(acc, w4[j].w, w4[j].z, w4[j].y, w4[j].x, eq[j]);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t v = acc[c];
+                v += __shfl_xor_sync(0xFFFFFFFFu, v, 1); // stage classes
+                if (G == 4) v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+                if (LOG2S >= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, 16); // sub-blocks
+                if (LOG2S >= 2) v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+                if (LOG2S >= 3) v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+                acc[c] = v;
+            }
+            // the zero-filled pad slots were counted as value 0
+            if (MODE == 1 || h == 0u)
+                acc[0] -= nst * kSlotsPerStage - nframes;
+            if ((lane >> kColBits) == 0u && e < nelem) {
+                const uint32_t owner = uint32_t(e) / push.slice;
+                uint32_t *dst = push.dst[owner] + (size_t(e) - size_t(owner) * push.slice) * 8u;
+                if (G == 4) {
+                    const uint2 v = s_g == 0 ? make_uint2(acc[0], acc[1])
+                                  : s_g == 1 ? make_uint2(acc[2], acc[3])
+                                  : s_g == 2 ? make_uint2(acc[4], acc[5])
+                                             : make_uint2(acc[6], acc[7]);
+                    *reinterpret_cast<uint2 *>(dst + 2u * s_g) = v;
+                } else {
+                    const uint4 v = s_g == 0 ? make_uint4(acc[0], acc[1], acc[2], acc[3]) : make_uint4(acc[4], acc[5], acc[6], acc[7]);
+                    *reinterpret_cast<uint4 *>(dst + 4u * s_g) = v;
+                }
+            }
+        } else {
         uint32_t alive[JT];
 #pragma unroll
         for (int j = 0; j < JT; ++j)
@@ -231,12 +335,15 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
         const size_t e = size_t(tile) * P + s_elem;
         if (s_writer && e < nelem)
             out[e] = uint8_t(med);
+        } // MODE == 0
     }
+    if (MODE != 0)
+        __threadfence_system(); // pushed counts are visible to the peers once this kernel has completed
 }
 
-template <int LOG2S, int JT, int NSELW>
+template <int LOG2S, int JT, int NSELW, int MODE>
 int launch_pipe_variant(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes,
-                        uint32_t nst, cudaStream_t stream)
+                        uint32_t nst, const ShardPush &push, cudaStream_t stream)
 {
     constexpr int P = 128 >> LOG2S;
     constexpr uint32_t G = NSELW / 4;
@@ -245,26 +352,26 @@ int launch_pipe_variant(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, 
     const size_t smem_bytes = size_t(kRing) * kStageBytes + size_t(NBUF) * (G * JT * 4096u) + size_t(kRing + 4) * 8 + 16;
     if (smem_bytes > ctx->smem_optin)
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: tile does not fit shared memory");
-    auto kern = median_pipe_kernel<LOG2S, JT, NSELW>;
+    auto kern = median_pipe_kernel<LOG2S, JT, NSELW, MODE>;
     CVVP_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
     const uint32_t grid = ntiles < uint32_t(ctx->sm_count) ? ntiles : uint32_t(ctx->sm_count);
     // P == 128: every line is read exactly once -> evict-first.  P < 128: the neighbouring CTA reads the other part
     // of the line at about the same time and should hit L2.
     const uint64_t policy = (LOG2S == 0) ? kL2EvictFirst : kL2EvictNormal;
-    kern<<<grid, (NSELW + kTrWarps) * 32, smem_bytes, stream>>>(tmap, d_out, nelem, nframes, nst, ntiles, policy);
+    kern<<<grid, (NSELW + kTrWarps) * 32, smem_bytes, stream>>>(tmap, d_out, nelem, nframes, nst, ntiles, policy, push);
     CVVP_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches++;
     return CVVP_OK;
 }
 
-template <int LOG2S, int NSELW>
+template <int LOG2S, int NSELW, int MODE>
 int dispatch_jt(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes, uint32_t nst,
-                cudaStream_t stream)
+                const ShardPush &push, cudaStream_t stream)
 {
     constexpr uint32_t G = NSELW / 4;
     switch ((nst + G - 1u) / G) {
 #define CVVP_JT_CASE(J) \
-    case J: return launch_pipe_variant<LOG2S, J, NSELW>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+    case J: return launch_pipe_variant<LOG2S, J, NSELW, MODE>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
         CVVP_JT_CASE(1)
         CVVP_JT_CASE(2)
         CVVP_JT_CASE(3)
@@ -278,15 +385,27 @@ int dispatch_jt(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t
     }
 }
 
-template <int LOG2S>
-int dispatch_mode(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes, uint32_t nst,
-                  cudaStream_t stream)
+template <int LOG2S, int MODE>
+int dispatch_bufs(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes, uint32_t nst,
+                  const ShardPush &push, cudaStream_t stream)
 {
     const char *e = getenv("CVVP_MEDIAN_BUFFERS"); // development switch: "1" forces the single-buffer mode
     const bool force_single = e && e[0] == '1';
     if (nst <= 16 && !force_single)
-        return dispatch_jt<LOG2S, 8>(ctx, tmap, d_out, nelem, nframes, nst, stream);
-    return dispatch_jt<LOG2S, 16>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+        return dispatch_jt<LOG2S, 8, MODE>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
+    return dispatch_jt<LOG2S, 16, MODE>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
+}
+
+template <int LOG2S>
+int dispatch_mode(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32_t nelem, uint32_t nframes, uint32_t nst,
+                  int mode, const ShardPush &push, cudaStream_t stream)
+{
+    switch (mode) {
+    case 0: return dispatch_bufs<LOG2S, 0>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
+    case 1: return dispatch_bufs<LOG2S, 1>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
+    case 2: return dispatch_bufs<LOG2S, 2>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
+    default: return fail(ctx, CVVP_ERR_INVALID, "median: bad kernel mode %d", mode);
+    }
 }
 } // namespace
 
@@ -297,15 +416,15 @@ long long median_max_frames()
 }
 
 int median_pipe_launch(cvvp_ctx *ctx, const CUtensorMap &tmap, int log2s, uint8_t *d_out, uint32_t nelem,
-                       uint32_t nframes, uint32_t nst, cudaStream_t stream)
+                       uint32_t nframes, uint32_t nst, int mode, const ShardPush &push, cudaStream_t stream)
 {
     if (nst == 0 || nst > 32)
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: %u stages exceed the plane buffer", nst);
     switch (log2s) {
-    case 0: return dispatch_mode<0>(ctx, tmap, d_out, nelem, nframes, nst, stream);
-    case 1: return dispatch_mode<1>(ctx, tmap, d_out, nelem, nframes, nst, stream);
-    case 2: return dispatch_mode<2>(ctx, tmap, d_out, nelem, nframes, nst, stream);
-    case 3: return dispatch_mode<3>(ctx, tmap, d_out, nelem, nframes, nst, stream);
+    case 0: return dispatch_mode<0>(ctx, tmap, d_out, nelem, nframes, nst, mode, push, stream);
+    case 1: return dispatch_mode<1>(ctx, tmap, d_out, nelem, nframes, nst, mode, push, stream);
+    case 2: return dispatch_mode<2>(ctx, tmap, d_out, nelem, nframes, nst, mode, push, stream);
+    case 3: return dispatch_mode<3>(ctx, tmap, d_out, nelem, nframes, nst, mode, push, stream);
     default: return fail(ctx, CVVP_ERR_INVALID, "median: bad tile variant");
     }
 }

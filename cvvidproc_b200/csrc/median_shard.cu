@@ -1,0 +1,376 @@
+// Frame-sharded temporal median across GPUs: the exchange step of BASELINE.json:north_star ("the median shards over
+// frame chunks ... before the median select"), fused with the counting kernels over NVLink peer memory.
+//
+// The reference's analogue is its temporal sharding of the frame range over generator threads
+// (/root/reference/Sources/cv_vid_bg_helpers.cpp:84-120) feeding one order-independent histogram
+// (histogram_median_algo.h:116-141); the result is the same sorted[N/2] of ALL frames (:160-166).
+//
+// Every rank holds a chunk of the frames (all elements).  Element e is OWNED by rank e / slice.  Instead of
+// all-reducing 256-bin histograms (512 B per element), the select is a two-round radix select on nibbles, and
+// the counts travel straight from the counting kernel into the owner's memory (reduce-scatter by peer stores):
+//
+//   phase 0  every rank : 16-bin counts of the HIGH nibble of its frames (median_pipe_kernel MODE 1, the same
+//                         TMA -> bit-transpose pipeline as the single-GPU kernel), 32 B per element stored into
+//                         owner's  counts1[src rank][e - owner * slice]
+//   phase 1  owner      : sums the `world` count vectors, N = their total, k = N / 2, picks the high nibble h with
+//                         cum(h) > k and the residual rank k' = k - cum(< h); stores  sel[e] = h | k' << 8  into
+//                         EVERY rank's sel array (4 B per element)
+//   phase 2  every rank : 16-bin counts of the LOW nibble among its frames with high nibble == h (MODE 2), pushed
+//                         into owner's counts2 the same way
+//   phase 3  owner      : sums, picks the low nibble l with cum(l) > k'; stores the result byte h << 4 | l into
+//                         EVERY rank's result image (all-gather by peer stores)
+//
+// Between phases the caller places a cross-rank barrier on the stream (a kernel's peer stores are complete when the
+// kernel is; the barrier orders them before the peer's next kernel).  No kernel ever waits for another rank, so ranks
+// can also be emulated one after another on a single device (tests).  Traffic per element per rank: 2 x 32 B out,
+// 2 x 32 B x (world-1)/world in, + 5 B broadcast -- 8x less than all-reducing 256 x u16 histograms, and the two
+// passes over the frames stay at HBM speed.
+#include "context.hpp"
+
+#include <cstring>
+#include <new>
+
+namespace cvvp
+{
+struct MedianShard {
+    int rank{0}, world{1};
+    size_t nelem{0};
+    uint32_t slice{0};      // elements owned per rank (multiple of 128)
+    uint8_t *buf{nullptr};  // one allocation: counts1 | counts2 | sel | result
+    size_t bytes{0};
+    size_t off_c1{0}, off_c2{0}, off_sel{0}, off_res{0};
+    uint8_t *peer[kMaxShardRanks]{}; // base of every rank's buffer as mapped into this process (peer[rank] == buf)
+    bool ipc_opened[kMaxShardRanks]{};
+    bool attached[kMaxShardRanks]{};
+};
+
+namespace
+{
+struct OwnerArgs {
+    const uint32_t *counts; // this rank's receive area of the round: [world][slice][8 words]
+    uint32_t slice, world, rank;
+    uint32_t owned;         // elements this rank owns
+    uint32_t *sel[kMaxShardRanks];    // every rank's sel array
+    uint8_t *result[kMaxShardRanks];  // every rank's result image
+};
+
+__device__ __forceinline__ void add_counts(uint32_t (&cnt)[16], const uint32_t *p)
+{
+    const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(p));
+    const uint4 b = __ldcg(reinterpret_cast<const uint4 *>(p) + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        cnt[2 * c] += w[c] & 0xFFFFu;
+        cnt[2 * c + 1] += w[c] >> 16;
+    }
+}
+
+// phase 1: one thread per owned element
+__global__ void __launch_bounds__(256) shard_pick_kernel(const __grid_constant__ OwnerArgs A)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < A.owned) {
+        uint32_t cnt[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+            cnt[b] = 0;
+        for (uint32_t src = 0; src < A.world; ++src)
+            add_counts(cnt, A.counts + (size_t(src) * A.slice + i) * 8u);
+        uint32_t total = 0;
+#pragma unroll
+        for (int b = 0; b < 16; ++b)
+            total += cnt[b];
+        const uint32_t k = total / 2u; // halfway rank: first bin with cumulative count > N / 2  (:160-166)
+        uint32_t h = 15u, below = 0u, cum = 0u;
+        bool found = false;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            if (!found && cum + cnt[b] > k) {
+                h = uint32_t(b);
+                below = cum;
+                found = true;
+            }
+            cum += cnt[b];
+        }
+        if (!found)
+            below = total - cnt[15]; // unreachable with exact counts; mirrors the reference's default bin
+        const uint32_t v = h | ((k - below) << 8);
+        const size_t e = size_t(A.rank) * A.slice + i;
+        for (uint32_t r = 0; r < A.world; ++r)
+            A.sel[r][e] = v;
+    }
+    __threadfence_system();
+}
+
+// phase 3: one thread per 4 owned elements (one 32-bit store of result bytes per rank)
+__global__ void __launch_bounds__(256) shard_final_kernel(const __grid_constant__ OwnerArgs A)
+{
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i4 < A.owned) {
+        const size_t e0 = size_t(A.rank) * A.slice + i4;
+        uint32_t packed = 0;
+        const uint32_t n = min(4u, A.owned - i4);
+        for (uint32_t q = 0; q < n; ++q) {
+            uint32_t cnt[16];
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                cnt[b] = 0;
+            for (uint32_t src = 0; src < A.world; ++src)
+                add_counts(cnt, A.counts + (size_t(src) * A.slice + i4 + q) * 8u);
+            const uint32_t s = __ldcg(A.sel[A.rank] + e0 + q);
+            const uint32_t h = s & 15u, k = s >> 8;
+            uint32_t l = 15u, cum = 0u;
+            bool found = false;
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                if (!found && cum + cnt[b] > k) {
+                    l = uint32_t(b);
+                    found = true;
+                }
+                cum += cnt[b];
+            }
+            packed |= ((h << 4) | l) << (8u * q);
+        }
+        for (uint32_t r = 0; r < A.world; ++r) {
+            uint8_t *dst = A.result[r] + e0;
+            if (n == 4u) {
+                *reinterpret_cast<uint32_t *>(dst) = packed; // e0 is a multiple of 4 (slice % 128 == 0)
+            } else {
+                for (uint32_t q = 0; q < n; ++q)
+                    dst[q] = uint8_t(packed >> (8u * q));
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+// a rank without frames still owes every owner a (zero) count vector
+__global__ void __launch_bounds__(256) shard_zero_push_kernel(const __grid_constant__ ShardPush push, uint32_t nelem)
+{
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; // one 16-byte half of an element's counts
+    if (i < size_t(nelem) * 2u) {
+        const uint32_t e = uint32_t(i >> 1);
+        const uint32_t owner = e / push.slice;
+        uint32_t *dst = push.dst[owner] + (size_t(e) - size_t(owner) * push.slice) * 8u + 4u * (i & 1u);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    __threadfence_system();
+}
+
+size_t round_up(size_t v, size_t a)
+{
+    return (v + a - 1) / a * a;
+}
+
+bool all_peers_known(const MedianShard *sh)
+{
+    for (int r = 0; r < sh->world; ++r)
+        if (!sh->peer[r])
+            return false;
+    return true;
+}
+} // namespace
+
+void median_shard_release(cvvp_ctx *ctx)
+{
+    MedianShard *sh = ctx->shard;
+    if (!sh)
+        return;
+    cudaStreamSynchronize(ctx->compute);
+    for (int r = 0; r < sh->world; ++r)
+        if (sh->ipc_opened[r] && sh->peer[r])
+            cudaIpcCloseMemHandle(sh->peer[r]);
+    if (sh->buf)
+        cudaFree(sh->buf);
+    cudaGetLastError();
+    delete sh;
+    ctx->shard = nullptr;
+}
+} // namespace cvvp
+
+using namespace cvvp;
+
+extern "C" {
+
+int cvvp_median_shard_begin(cvvp_ctx *ctx, size_t nelem, int rank, int world)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    if (ctx->shard)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: a sharded job is already open on this context");
+    if (nelem == 0 || nelem >= (1ull << 31))
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: nelem must be in [1, 2^31)");
+    if (world < 1 || world > kMaxShardRanks || rank < 0 || rank >= world)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: rank %d / world %d out of range (world <= %d)", rank, world,
+                    kMaxShardRanks);
+    DeviceGuard guard(ctx->device);
+    MedianShard *sh = new (std::nothrow) MedianShard();
+    if (!sh)
+        return fail(ctx, CVVP_ERR_NOMEM, "out of host memory");
+    sh->rank = rank;
+    sh->world = world;
+    sh->nelem = nelem;
+    sh->slice = uint32_t(round_up((nelem + size_t(world) - 1) / size_t(world), 128));
+    const size_t counts_bytes = size_t(world) * sh->slice * 32u;
+    sh->off_c1 = 0;
+    sh->off_c2 = counts_bytes;
+    sh->off_sel = 2 * counts_bytes;
+    sh->off_res = sh->off_sel + round_up(nelem * 4u, 256);
+    sh->bytes = sh->off_res + round_up(nelem, 256);
+    if (cudaMalloc(reinterpret_cast<void **>(&sh->buf), sh->bytes) != cudaSuccess) {
+        cudaGetLastError();
+        const size_t wanted = sh->bytes;
+        delete sh;
+        return fail(ctx, CVVP_ERR_NOMEM, "median shard: cudaMalloc of %zu bytes of exchange buffers failed", wanted);
+    }
+    if (cudaMemsetAsync(sh->buf, 0, sh->bytes, ctx->compute) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
+        cudaFree(sh->buf);
+        delete sh;
+        return fail(ctx, CVVP_ERR_CUDA, "median shard: clearing the exchange buffers failed");
+    }
+    sh->peer[rank] = sh->buf;
+    ctx->shard = sh;
+    return CVVP_OK;
+}
+
+int cvvp_median_shard_export(cvvp_ctx *ctx, void *handle_out)
+{
+    if (!ctx || !handle_out)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: null argument");
+    if (!ctx->shard)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: no sharded job is open");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CVVP_IPC_HANDLE_BYTES, "handle size is part of the ABI");
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    CVVP_CUDA_OK(ctx, cudaIpcGetMemHandle(&h, ctx->shard->buf));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return CVVP_OK;
+}
+
+int cvvp_median_shard_import(cvvp_ctx *ctx, int peer, const void *handle)
+{
+    if (!ctx || !handle)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: null argument");
+    MedianShard *sh = ctx->shard;
+    if (!sh)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: no sharded job is open");
+    if (peer < 0 || peer >= sh->world || peer == sh->rank)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: bad peer rank %d", peer);
+    if (sh->peer[peer])
+        return fail(ctx, CVVP_ERR_STATE, "median shard: peer %d is already mapped", peer);
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    CVVP_CUDA_OK(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    sh->peer[peer] = static_cast<uint8_t *>(p);
+    sh->ipc_opened[peer] = true;
+    return CVVP_OK;
+}
+
+int cvvp_median_shard_attach(cvvp_ctx *ctx, int peer, cvvp_ctx *peer_ctx)
+{
+    if (!ctx || !peer_ctx)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: null argument");
+    MedianShard *sh = ctx->shard, *ps = peer_ctx->shard;
+    if (!sh || !ps)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: both contexts need an open sharded job");
+    if (peer < 0 || peer >= sh->world || peer == sh->rank || ps->rank != peer || ps->world != sh->world ||
+        ps->nelem != sh->nelem)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: peer context does not describe rank %d of the same job", peer);
+    if (sh->peer[peer])
+        return fail(ctx, CVVP_ERR_STATE, "median shard: peer %d is already mapped", peer);
+    if (peer_ctx->device != ctx->device) {
+        DeviceGuard guard(ctx->device);
+        int can = 0;
+        CVVP_CUDA_OK(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer_ctx->device));
+        if (!can)
+            return fail(ctx, CVVP_ERR_UNSUPPORTED, "median shard: device %d cannot access device %d", ctx->device,
+                        peer_ctx->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(peer_ctx->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(ctx, CVVP_ERR_CUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    sh->peer[peer] = ps->buf;
+    sh->attached[peer] = true;
+    return CVVP_OK;
+}
+
+int cvvp_median_shard_phase(cvvp_ctx *ctx, int phase, const uint8_t *d_frames, long long nframes, size_t frame_stride,
+                            void *stream)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    MedianShard *sh = ctx->shard;
+    if (!sh)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: no sharded job is open");
+    if (!all_peers_known(sh))
+        return fail(ctx, CVVP_ERR_STATE, "median shard: not every peer buffer is mapped (import / attach all ranks first)");
+    if (nframes < 0)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: negative frame count");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->compute;
+    if (phase == 0 || phase == 2) {
+        ShardPush push{};
+        const size_t off = (phase == 0 ? sh->off_c1 : sh->off_c2) + size_t(sh->rank) * sh->slice * 32u;
+        for (int r = 0; r < sh->world; ++r)
+            push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
+        push.sel = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_sel);
+        push.slice = sh->slice;
+        if (nframes == 0) {
+            const size_t n = sh->nelem * 2;
+            shard_zero_push_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(push, uint32_t(sh->nelem));
+            CVVP_CUDA_OK(ctx, cudaGetLastError());
+            ctx->launches++;
+            return CVVP_OK;
+        }
+        return median_launch_mode(ctx, d_frames, nframes, sh->nelem, frame_stride, nullptr, phase == 0 ? 1 : 2, push, s);
+    }
+    if (phase == 1 || phase == 3) {
+        OwnerArgs A{};
+        A.counts = reinterpret_cast<const uint32_t *>(sh->buf + (phase == 1 ? sh->off_c1 : sh->off_c2));
+        A.slice = sh->slice;
+        A.world = uint32_t(sh->world);
+        A.rank = uint32_t(sh->rank);
+        const size_t first = size_t(sh->rank) * sh->slice;
+        A.owned = first >= sh->nelem ? 0u : uint32_t(sh->nelem - first < sh->slice ? sh->nelem - first : sh->slice);
+        for (int r = 0; r < sh->world; ++r) {
+            A.sel[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_sel);
+            A.result[r] = sh->peer[r] + sh->off_res;
+        }
+        if (A.owned == 0)
+            return CVVP_OK;
+        if (phase == 1)
+            shard_pick_kernel<<<(A.owned + 255) / 256, 256, 0, s>>>(A);
+        else
+            shard_final_kernel<<<((A.owned + 3) / 4 + 255) / 256, 256, 0, s>>>(A);
+        CVVP_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches++;
+        return CVVP_OK;
+    }
+    return fail(ctx, CVVP_ERR_INVALID, "median shard: phase must be 0..3");
+}
+
+int cvvp_median_shard_result(cvvp_ctx *ctx, const uint8_t **d_result)
+{
+    if (!ctx || !d_result)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: null argument");
+    if (!ctx->shard)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: no sharded job is open");
+    *d_result = ctx->shard->buf + ctx->shard->off_res;
+    return CVVP_OK;
+}
+
+int cvvp_median_shard_end(cvvp_ctx *ctx)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    median_shard_release(ctx);
+    return CVVP_OK;
+}
+
+} // extern "C"

@@ -65,6 +65,9 @@ CVVP_API int cvvp_ctx_sm_count(const cvvp_ctx *ctx);
  * batched into pinned buffers" part of BASELINE.json:north_star. */
 CVVP_API int cvvp_host_alloc(size_t bytes, void **out_ptr);
 CVVP_API int cvvp_host_free(void *ptr);
+/* synchronous device -> host copy on the context's compute stream (after everything queued there): lets callers
+ * of the device-resident entry points fetch a result without a CUDA binding of their own */
+CVVP_API int cvvp_ctx_copy_to_host(cvvp_ctx *ctx, void *host_dst, const void *device_src, size_t bytes);
 
 /* ---------------------------------------------------------------------------------------------
  * temporal median -- replaces HistogramMedianAlgo<T>
@@ -104,6 +107,44 @@ CVVP_API int cvvp_median_abort(cvvp_ctx *ctx);
  * (a cudaStream_t, NULL = the context's compute stream) and does not synchronize. */
 CVVP_API int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem,
                        size_t frame_stride, uint8_t *d_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * frame-sharded temporal median across GPUs (one process -- or at least one context -- per GPU).
+ *   The reference splits the frame range of a video over its generator threads
+ *   (Sources/cv_vid_bg_helpers.cpp:84-120) and merges them in ONE order-independent histogram
+ *   (histogram_median_algo.h:116-141); here every rank keeps a chunk of the frames in its own HBM
+ *   and the merge is a two-round exchange of 16-bin nibble counts written directly into the
+ *   owner rank's memory over NVLink (csrc/median_shard.cu).  The result is the same upper median
+ *   sorted[N/2] of ALL ranks' frames (:160-166), delivered to every rank.
+ *
+ *   call order on every rank:
+ *     cvvp_median_shard_begin
+ *     cvvp_median_shard_export -> (the host exchanges the 64-byte handles, e.g. torch.distributed
+ *                                  all_gather) -> cvvp_median_shard_import for every other rank
+ *                                  (or cvvp_median_shard_attach for a context of the same process)
+ *     per job: phase 0, BARRIER, phase 1, BARRIER, phase 2, BARRIER, phase 3, BARRIER
+ *     cvvp_median_shard_result ; cvvp_median_shard_end
+ *   BARRIER = a cross-rank barrier ordered on the stream (e.g. a one-element NCCL all-reduce):
+ *   phase p+1 of any rank must not start before phase p of every rank has completed.  No kernel
+ *   of this library waits for another rank.
+ * ------------------------------------------------------------------------------------------- */
+#define CVVP_IPC_HANDLE_BYTES 64
+/* rank in [0, world), world <= 16; allocates this rank's exchange buffers (64 B per element and
+ * rank for the counts + 5 B per element) */
+CVVP_API int cvvp_median_shard_begin(cvvp_ctx *ctx, size_t nelem, int rank, int world);
+/* CVVP_IPC_HANDLE_BYTES bytes that let another PROCESS on the same box map this rank's buffers */
+CVVP_API int cvvp_median_shard_export(cvvp_ctx *ctx, void *handle_out);
+CVVP_API int cvvp_median_shard_import(cvvp_ctx *ctx, int peer_rank, const void *handle);
+/* same-process peer (several contexts in one process, on one or several devices) */
+CVVP_API int cvvp_median_shard_attach(cvvp_ctx *ctx, int peer_rank, cvvp_ctx *peer_ctx);
+/* phases 0 and 2 read this rank's frames (device pointer, same layout rules as cvvp_median_device;
+ * nframes may be 0, and may differ between ranks); phases 1 and 3 ignore the frame arguments.
+ * Runs on `stream` (NULL = the context's compute stream) and does not synchronize. */
+CVVP_API int cvvp_median_shard_phase(cvvp_ctx *ctx, int phase, const uint8_t *d_frames, long long nframes,
+                                     size_t frame_stride, void *stream);
+/* device pointer to the nelem result bytes (complete on every rank after the barrier that follows phase 3) */
+CVVP_API int cvvp_median_shard_result(cvvp_ctx *ctx, const uint8_t **d_result);
+CVVP_API int cvvp_median_shard_end(cvvp_ctx *ctx);
 
 /* ---------------------------------------------------------------------------------------------
  * per-frame highlight -- replaces HighlightObjectsAlgo

@@ -1,0 +1,150 @@
+"""GPU parity of the frame-sharded median (csrc/median_shard.cu) against the CPU oracle, through the C ABI.
+
+`world` ranks are emulated as `world` contexts of ONE process on ONE device (cvvp_median_shard_attach): every kernel is
+the one a real multi-GPU job runs, peer stores simply land in local memory, and the barrier between phases is a
+synchronize of every context.  (Real peer memory over NVLink is exercised by `bench.py --gpus N`.)  Bit-exact is the
+bar: the result must be sorted[N/2] over ALL ranks' frames (histogram_median_algo.h:160-166).
+"""
+import numpy as np
+import pytest
+import torch
+
+from cvvidproc_b200 import _cabi, sharded
+
+pytestmark = pytest.mark.gpu
+
+
+def _sharded_median(frames_per_rank, nelem):
+    """frames_per_rank: list of uint8 arrays (n_r, nelem); returns every rank's result image."""
+    world = len(frames_per_rank)
+    ctxs = [_cabi.Context(0) for _ in range(world)]
+    jobs, stacks = [], []
+    try:
+        stride = (nelem + 127) // 128 * 128
+        for r, fr in enumerate(frames_per_rank):
+            jobs.append(sharded.ShardedMedian(ctxs[r], nelem, r, world))
+            t = torch.zeros((max(fr.shape[0], 1), stride), dtype=torch.uint8, device="cuda:0")
+            if fr.shape[0]:
+                t[: fr.shape[0], :nelem] = torch.from_numpy(np.ascontiguousarray(fr)).to("cuda:0")
+            stacks.append(t)
+        torch.cuda.synchronize()
+        sharded.ShardedMedian.connect_local(jobs)
+        for p in range(4):
+            for r, job in enumerate(jobs):
+                job.phase(p, stacks[r].data_ptr(), frames_per_rank[r].shape[0], stride)
+            for c in ctxs:
+                c.synchronize()
+        return [job.ctx.copy_to_host(job.result_ptr(), nelem) for job in jobs]
+    finally:
+        for job in jobs:
+            job.close()
+        for c in ctxs:
+            c.close()
+
+
+def _split(frames, world, ragged=None):
+    n = frames.shape[0]
+    parts = []
+    for r in range(world):
+        first, cnt = sharded.frame_chunk(n, r, world) if ragged is None else ragged[r]
+        parts.append(frames[first : first + cnt])
+    return parts
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("n", [1, 2, 7, 100, 101, 1000])
+def test_random_stack_matches_oracle(oracle_median, world, n):
+    rng = np.random.default_rng(1000 * world + n)
+    h, w = 9, 150
+    frames = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    want = oracle_median(frames).reshape(-1)
+    outs = _sharded_median(_split(frames.reshape(n, -1), world), h * w)
+    for r, got in enumerate(outs):
+        assert np.array_equal(got, want), f"rank {r} of {world}"
+    assert np.array_equal(want, np.sort(frames.reshape(n, -1), axis=0)[n // 2])
+
+
+@pytest.mark.parametrize("nelem", [1, 5, 127, 128, 129, 1000, 4099])
+def test_ragged_element_counts(oracle_median, nelem):
+    rng = np.random.default_rng(nelem)
+    frames = rng.integers(90, 140, (77, nelem), dtype=np.uint8)
+    want = oracle_median(frames.reshape(77, 1, nelem)).reshape(-1)
+    for world in (2, 3):
+        for got in _sharded_median(_split(frames, world), nelem):
+            assert np.array_equal(got, want)
+
+
+def test_uneven_and_empty_chunks(oracle_median):
+    """ranks may hold different numbers of frames, including none"""
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (50, 700), dtype=np.uint8)
+    want = oracle_median(frames.reshape(50, 1, 700)).reshape(-1)
+    for ragged in ([(0, 50), (50, 0)], [(0, 1), (1, 49)], [(0, 0), (0, 20), (20, 30)], [(0, 33), (33, 0), (33, 17), (50, 0)]):
+        for got in _sharded_median(_split(frames, len(ragged), ragged), 700):
+            assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n_local", [513, 1024, 1025, 2049, 4097])
+def test_every_tile_variant(oracle_median, n_local):
+    """local frame counts that select each tile width / buffering mode of the counting kernel"""
+    rng = np.random.default_rng(n_local)
+    world = 2
+    n = world * n_local - 1
+    frames = rng.integers(100, 132, (n, 300), dtype=np.uint8)
+    want = oracle_median(frames.reshape(n, 1, 300)).reshape(-1)
+    for got in _sharded_median(_split(frames, world), 300):
+        assert np.array_equal(got, want)
+
+
+def test_two_valued_split_pins_upper_median():
+    """exact 50/50 split across ranks: rank 0 holds only the low value, rank 1 only the high one"""
+    n = 200
+    lo = np.full((n // 2, 256), 16, np.uint8)   # differ in the high nibble
+    hi = np.full((n // 2, 256), 32, np.uint8)
+    for got in _sharded_median([lo, hi], 256):
+        assert (got == 32).all()
+    for got in _sharded_median([lo, hi[:-1]], 256):  # one fewer high value tips it
+        assert (got == 16).all()
+    lo2 = np.full((n // 2, 256), 0x51, np.uint8)  # same high nibble, differ in the low one
+    hi2 = np.full((n // 2, 256), 0x5E, np.uint8)
+    for got in _sharded_median([lo2, hi2], 256):
+        assert (got == 0x5E).all()
+    zeros = np.zeros((33, 256), np.uint8)  # value 0 coincides with the zero-filled pad slots
+    for got in _sharded_median([zeros, zeros[:5]], 256):
+        assert (got == 0).all()
+    ff = np.full((33, 256), 255, np.uint8)
+    for got in _sharded_median([ff, zeros[:30]], 256):
+        assert (got == 255).all()
+
+
+def test_matches_single_gpu_kernel_at_c1_size(gpu_ctx):
+    """C1-sized synthetic stack (640x480x100) split over 4 ranks == the single-GPU on-chip select"""
+    from cvvidproc_b200 import synth
+
+    p = synth.CONFIG_PARAMS["C1"]
+    frames = synth.synth_frames(0, 100, p["width"], 120, p["seed"], p["ndisks"])
+    want = gpu_ctx.median(frames).reshape(-1)
+    flat = frames.reshape(100, -1)
+    for got in _sharded_median(_split(flat, 4), flat.shape[1]):
+        assert np.array_equal(got, want)
+
+
+def test_call_order_errors():
+    ctx = _cabi.Context(0)
+    try:
+        with pytest.raises(_cabi.CvvpError):
+            ctx.median_shard_phase(0)  # no job
+        ctx.median_shard_begin(1000, 0, 2)
+        with pytest.raises(_cabi.CvvpError):
+            ctx.median_shard_begin(1000, 0, 2)  # already open
+        with pytest.raises(_cabi.CvvpError):
+            ctx.median_shard_phase(1)  # peer 1 not mapped
+        with pytest.raises(_cabi.CvvpError):
+            ctx.median_shard_import(0, b"\0" * 64)  # own rank
+        ctx.median_shard_end()
+        with pytest.raises(_cabi.CvvpError):
+            ctx.median_shard_begin(1000, 3, 2)  # rank out of range
+        with pytest.raises(_cabi.CvvpError):
+            ctx.median_shard_begin(1000, 0, 17)  # too many ranks
+    finally:
+        ctx.close()
