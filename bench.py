@@ -12,8 +12,13 @@ max over ranks); `e2e` is the same metric through the C ABI's host-buffer interf
 timed region.  The stack (2.07 GB per GPU) is ~16x larger than L2, so no L2 flush is needed
 between timed iterations.
 
-N > 1 (one process per GPU under torchrun): see shard_plan() -- the work is partitioned with no
-collective on the data path; the result bands are gathered with one NCCL all_gather per step.
+N > 1 (one process per GPU under torchrun), default `--median-sharding frames`: weak scaling, every
+GPU holds its own 1000-frame chunk and the job is the median of the 1000*N-frame stack, merged by
+the two-round nibble-count exchange of csrc/median_shard.cu (counts are stored into the owner
+rank's memory over NVLink by the counting kernels; see run_gpu_arm_sharded).  `--median-sharding
+rows` instead splits the single C2 stack into row bands (shard_plan(): no collective on the data
+path, one NCCL all_gather of the result bands; strong scaling).  The highlight section shards by
+frame with no collective in both cases.
 """
 from __future__ import annotations
 
@@ -186,32 +191,34 @@ def cpu_median_fn():
     return run, kind
 
 
-def host_sample_frames(rows: int) -> np.ndarray:
+def host_sample_frames(rows: int, nframes: int | None = None) -> np.ndarray:
     """Rows [0, rows) of every frame of the workload, generated on the host (cvvidproc_b200/synth.py)."""
     from cvvidproc_b200 import synth
 
     w = WORKLOAD
-    return synth.synth_frames(0, w["nframes"], w["width"], w["height"], w["seed"], w["ndisks"], row0=0, nrows=rows)
+    return synth.synth_frames(0, nframes or w["nframes"], w["width"], w["height"], w["seed"], w["ndisks"], row0=0, nrows=rows)
 
 
 def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    w = WORKLOAD
+    w = dict(WORKLOAD)
+    if world > 1 and args.median_sharding == "frames":
+        w["nframes"] = WORKLOAD["nframes"] * world  # the cuda arm's job at N GPUs: the 1000*N-frame stack
     cores = os.cpu_count() or 1
     run, kind = cpu_median_fn()
-    # bounded sample: a band of rows of the SAME stack (all 1000 frames), sized from a calibration band so that
+    # bounded sample: a band of rows of the SAME stack (all frames), sized from a calibration band so that
     # the whole run stays within ~2.5 minutes
     calib_rows = 8
-    frames = host_sample_frames(calib_rows)
+    frames = host_sample_frames(calib_rows, w["nframes"])
     t0 = time.perf_counter()
     run(frames, cores)
     t_cal = max(time.perf_counter() - t0, 1e-4)
     per_row = t_cal / calib_rows
     budget = 150.0 / max(1, args.steps + args.warmup)
     rows = int(min(w["height"], max(calib_rows, budget / per_row)))
-    rows = min(rows, 270)  # generation of the sample on the host is itself ~0.1 s per row
-    frames = host_sample_frames(rows)
+    rows = min(rows, max(calib_rows, 270 * WORKLOAD["nframes"] // w["nframes"]))  # host generation: ~0.1 s per row per 1000 frames
+    frames = host_sample_frames(rows, w["nframes"])
     for _ in range(args.warmup):
         run(frames, cores)
     t0 = time.perf_counter()
@@ -224,7 +231,7 @@ def run_reference_arm(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak",
+        "scaling": "strong" if (world > 1 and args.median_sharding == "rows") else "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": w["name"], "width": w["width"], "height": w["height"], "nframes": w["nframes"],
                    "sample": sample},
@@ -569,6 +576,171 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# GPU arm, N > 1: frame-sharded median (BASELINE.json north_star: "the median shards over frame chunks")
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm_sharded(args, rank: int, local_rank: int, world: int):
+    """Weak scaling: every rank holds its own 1000-frame chunk of the 1080p stream (frames [1000*rank, 1000*(rank+1))),
+    so the job is the temporal median of a 1000*world-frame stack.  One step = the four phases of
+    csrc/median_shard.cu with a one-element NCCL all-reduce as the barrier between them; the nibble counts travel by
+    peer stores over NVLink from inside the counting kernels; every rank ends with the full result image."""
+    import torch
+    import torch.distributed as dist
+
+    from cvvidproc_b200 import _cabi, sharded
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOAD
+    W, H, N = w["width"], w["height"], w["nframes"]
+    nelem = W * H
+    ctx = _cabi.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    first, _ = sharded.frame_chunk(N * world, rank, world)
+    stack = torch.empty((N, nelem), dtype=torch.uint8, device=dev)
+    ctx.synth_frames_device(stack.data_ptr(), nelem, W, H, first, N, w["seed"], w["ndisks"])
+    ctx.synchronize()
+    job = sharded.ShardedMedian(ctx, nelem, rank, world)
+    job.connect_processes()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        job.run(stack.data_ptr(), N, nelem)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase_evs = []
+    sampler.active = True
+    ev0.record(stream)
+    for _ in range(args.steps):
+        evs = []
+        for p in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            job.phase(p, stack.data_ptr(), N, nelem)
+            b.record(stream)
+            job.barrier()
+            evs.append((a, b))
+        phase_evs.append(evs)
+    ev1.record(stream)
+    barrier()
+    sampler.active = False
+    launches = ctx.launch_count - launches0
+    total_ms = ev0.elapsed_time(ev1)
+    phase_ms = [float(np.mean([evs[p][0].elapsed_time(evs[p][1]) for evs in phase_evs])) for p in range(4)]
+    t = torch.tensor([total_ms] + phase_ms, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, phase_ms = float(t[0]), [float(v) for v in t[1:]]
+    ms_per_step = total_ms / args.steps
+    job_mpxf = W * H * N * world / 1e6
+    value = job_mpxf / (ms_per_step * 1e-3)
+    result_dev = ctx.copy_to_host(job.result_ptr(), nelem)
+
+    # ---- end to end: this rank's frames start in pinned host memory, the full result ends in host memory
+    pinned = _cabi.PinnedBuffer(N * nelem)
+    host_t = torch.from_numpy(pinned.array).view(N, nelem)
+    chunk = 50
+    for i in range(0, N, chunk):
+        host_t[i : i + chunk].copy_(stack[i : i + chunk])
+    torch.cuda.synchronize()
+    e2e_steps = max(3, min(args.steps, 10))
+    host_out = None
+
+    def e2e_step():
+        nonlocal host_out
+        with torch.cuda.stream(stream):
+            for i in range(0, N, 125):
+                stack[i : i + 125].copy_(host_t[i : i + 125], non_blocking=True)
+        job.run(stack.data_ptr(), N, nelem)
+        host_out = ctx.copy_to_host(job.result_ptr(), nelem)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    sampler.active = True
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    sampler.active = False
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    sampler.stop()
+    clocks = sampler.summary()
+
+    # ---- parity spot check (outside the timed regions): every rank holds the same image, and on sampled elements it
+    # is the order statistic of ALL ranks' frames (gathered through NCCL for the sample only)
+    same = bool(np.array_equal(host_out, result_dev))
+    cols = torch.arange(0, nelem, max(1, nelem // 4096), device=dev)
+    mine = stack[:, cols].contiguous()
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    want = torch.sort(torch.cat(allc, 0), dim=0).values[(N * world) // 2].cpu().numpy()
+    same = same and bool(np.array_equal(want, result_dev[cols.cpu().numpy()]))
+    flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    same = bool(int(flag[0]))
+
+    peak, peak_src = load_peaks()
+    algo_bytes = float(N) * nelem + 32.0 * nelem  # one counting round: every input byte once + 32 B of counts per element
+    k_ms = max(phase_ms[0], phase_ms[2])
+    roofline = {"bound": "hbm", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "median_pipe_kernel (counting round 2, the slower of the two passes over the frames)",
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "phase_ms": {"count_hi": phase_ms[0], "pick_hi": phase_ms[1], "count_lo": phase_ms[2], "pick_lo": phase_ms[3]}}
+    pinned.close()
+    job.close()
+    del stack
+
+    highlight = None
+    if not args.no_highlight:
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
+        try:
+            highlight = run_highlight_section(ctx, torch, dist, rank, local_rank, world, args, sampler2, stream)
+            highlight["clocks"] = sampler2.summary()
+        finally:
+            sampler2.stop()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": w["name"] + f"; N>1: every GPU holds its own {N}-frame chunk, the job is the median of "
+                                               f"the {N * world}-frame stack",
+                       "width": W, "height": H, "nframes": N * world, "frames_per_gpu": N, "seed": w["seed"],
+                       "ndisks": w["ndisks"],
+                       "sharding": f"frame chunks x{world}; two-round nibble-count exchange by NVLink peer stores "
+                                   "(csrc/median_shard.cu), NCCL one-element all-reduce as the inter-phase barrier",
+                       "l2": "input stack (2.07 GB per GPU) exceeds the 126 MB L2; no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": job_mpxf / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(N * nelem) * world,
+                    "d2h_bytes_per_step": int(nelem) * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": None,
+            "parity_spot_check": same,
+            "highlight": highlight,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -577,6 +749,9 @@ def main():
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-highlight", action="store_true", help="skip the highlight-stage section")
+    ap.add_argument("--median-sharding", choices=["frames", "rows"], default="frames",
+                    help="N > 1: frame chunks with the NVLink count exchange (default, weak scaling) or row bands of "
+                         "the single C2 stack with no data-path collective (strong scaling)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
@@ -588,6 +763,8 @@ def main():
               file=sys.stderr)
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+    elif world > 1 and args.median_sharding == "frames":
+        run_gpu_arm_sharded(args, rank, local_rank, world)
     else:
         run_gpu_arm(args, rank, local_rank, world)
 

@@ -23,6 +23,8 @@
 // are needed.  HBM traffic is the algorithmic minimum: every input byte is read exactly once.
 #include "context.hpp"
 
+#include <cstdlib>
+
 namespace cvvp
 {
 int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
@@ -52,6 +54,8 @@ int median_launch_mode(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes
     // slots per 4 KB stage, at most 32 stages per tile
     int log2s = 0;
     uint32_t nst = 0;
+    if (const char *e = getenv("CVVP_MEDIAN_LOG2S")) // development switch: narrowest tile variant to consider
+        log2s = e[0] >= '0' && e[0] <= '3' ? e[0] - '0' : 0;
     for (; log2s <= 3; ++log2s) {
         const long long slots = 32ll << log2s;
         const long long need = (nframes + slots - 1) / slots;

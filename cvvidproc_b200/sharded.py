@@ -115,6 +115,9 @@ class ShardedMedian:
     def phase(self, p: int, d_frames: int = 0, nframes: int = 0, frame_stride: int = 0):
         self.ctx.median_shard_phase(p, d_frames, nframes, frame_stride)
 
+    def barrier(self):
+        self._barrier()
+
     def run(self, d_frames: int, nframes: int, frame_stride: int) -> int:
         """All four phases with the barriers in between (every rank of the group must call it).  Returns the device
         pointer of the full result image (nelem bytes), complete once the stream reaches the last barrier."""
