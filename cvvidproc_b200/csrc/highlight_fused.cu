@@ -105,13 +105,14 @@ struct RunSet {
 
 enum ProfPhase {
     kPBits, kPErodeA, kPDilateA, kPExtract, kPMerge, kPFlatten, kPRso, kPFill, kPHyst, kPErodeB, kPDilateB, kPExpand,
-    kPRuns, kPFrames, kPCount
+    kPCountRuns, kPHook, kPRuns, kPFrames, kPCount
 };
 
 struct Shared {
     unsigned long long prof_last;
     unsigned frame;
     uint32_t wsum[NW];
+    uint32_t wbase[NW + 1]; // exclusive prefix of wsum (run id of every warp's first run)
     uint32_t T[2];
     int white[2];
     int changed; // remove-small-objects cleared at least one pixel of the current image
@@ -818,6 +819,8 @@ struct View {
 struct SmemRuns {
     uint32_t *rowoff, *xinfo, *parent, *fbits;
     uint32_t cap; // runs (incl. the FRAME node) the copy can hold; 0 = the row offsets alone do not fit
+    uint16_t *qoff; // run extraction: per 128-bit quad, the number of run starts, then their offset inside the owning
+                    // warp's range (nullptr: the image has too many quads, the extraction takes the lane-ordered path)
 };
 
 __device__ __forceinline__ SmemRuns smem_runs(const FusedArgs &P, uint32_t *smem)
@@ -825,8 +828,16 @@ __device__ __forceinline__ SmemRuns smem_runs(const FusedArgs &P, uint32_t *smem
     SmemRuns m;
     const uint32_t ro_words = (uint32_t(P.H) + 2 + 3) & ~3u;
     m.rowoff = smem;
+    // the quad offsets sit at the end of the dynamic shared memory when they take at most a third of it
+    const uint32_t qwords = (((P.nwords >> 2) + 1u) / 2u + 3u) & ~3u;
+    uint32_t words = P.smem_words;
+    m.qoff = nullptr;
+    if (qwords * 3u <= P.smem_words) {
+        words -= qwords;
+        m.qoff = reinterpret_cast<uint16_t *>(smem + words);
+    }
     // cap records + cap parents + cap / 32 + 1 flag words
-    m.cap = ro_words + 256 < P.smem_words ? (((P.smem_words - ro_words - 4) * 32u) / 65u) & ~31u : 0;
+    m.cap = ro_words + 256 < words ? (((words - ro_words - 4) * 32u) / 65u) & ~31u : 0;
     m.xinfo = smem + ro_words;
     m.parent = m.xinfo + m.cap;
     m.fbits = m.parent + m.cap;
@@ -857,7 +868,10 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
                     int y, wx0;
                     split(P, 4 * q, y, wx0);
                     uint32_t t[4];
-                    cnt += quad_transitions(P, w[u], (prevs >> u) & 1u, wx0, t);
+                    const uint32_t c = quad_transitions(P, w[u], (prevs >> u) & 1u, wx0, t);
+                    cnt += c;
+                    if (sm.qoff)
+                        sm.qoff[q] = uint16_t(c); // at most 128 run starts per quad
                 }
             }
         }
@@ -868,6 +882,7 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
             sh.wsum[warp] = cnt;
     }
     __syncthreads();
+    prof_tick(P.prof, P.prof, sh, kPCountRuns);
     uint32_t base = 0, T = 0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
@@ -877,7 +892,93 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
         T += c;
     }
     sm_ok = T + 1 <= sm.cap;
-    // pass 2: fill
+    // the warps' ranges hold at most 65535 runs each (else their 16-bit quad offsets overflow: lane-ordered path)
+    bool quick = sm.qoff != nullptr;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        quick = quick && sh.wsum[w] <= 65535u;
+    if (quick) {
+        // ---- pass 2, work proportional to RUNS: counts -> offsets (per warp, in place), then every thread takes
+        // run ids tid, tid + NT, ...: binary search for the quad that holds the run, one 16-byte load of that quad,
+        // n-th set bit of its transition words
+        if (threadIdx.x <= NW) {
+            uint32_t b = 0;
+            for (int w = 0; w < NW; ++w)
+                if (w < int(threadIdx.x))
+                    b += sh.wsum[w];
+            sh.wbase[threadIdx.x] = b;
+        }
+        {
+            uint32_t run = 0;
+            for (uint32_t qb = q0; qb < q1; qb += 32u) {
+                const uint32_t q = qb + lane;
+                const uint32_t c = q < q1 ? sm.qoff[q] : 0u;
+                uint32_t inc = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= d)
+                        inc += n;
+                }
+                if (q < q1)
+                    sm.qoff[q] = uint16_t(run + inc - c);
+                run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            }
+        }
+        __syncthreads();
+        for (uint32_t r = threadIdx.x; r < T; r += NT) {
+            uint32_t lo = 0, hi = NW - 1;
+            while (lo < hi) { // warp range of run r: largest w with wbase[w] <= r
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (sh.wbase[mid] <= r)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            const uint32_t rel = r - sh.wbase[lo];
+            const uint32_t qa = min(lo * per_warp, nq), qz = min(qa + per_warp, nq);
+            lo = qa;
+            hi = qz - 1;
+            while (lo < hi) { // quad of run r: largest q of the range with offset <= rel
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (sm.qoff[mid] <= rel)
+                    lo = mid;
+                else
+                    hi = mid - 1;
+            }
+            const uint32_t q = lo;
+            uint32_t n = rel - sm.qoff[q]; // the run is the n-th run start of its quad
+            int y, wx0;
+            split(P, 4 * q, y, wx0);
+            const uint4 w4 = __ldcg(reinterpret_cast<const uint4 *>(img) + q);
+            const uint32_t prev = wx0 == 0 ? 0u : (ld(img + 4 * size_t(q) - 1) >> 31);
+            uint32_t t[4];
+            quad_transitions(P, w4, prev, wx0, t);
+            const uint32_t c0 = __popc(t[0]), c1 = __popc(t[1]), c2 = __popc(t[2]);
+            uint32_t k, tk, wk;
+            if (n < c0) {
+                k = 0, tk = t[0], wk = w4.x;
+            } else if (n < c0 + c1) {
+                k = 1, tk = t[1], wk = w4.y, n -= c0;
+            } else if (n < c0 + c1 + c2) {
+                k = 2, tk = t[2], wk = w4.z, n -= c0 + c1;
+            } else {
+                k = 3, tk = t[3], wk = w4.w, n -= c0 + c1 + c2;
+            }
+            const uint32_t b = __fns(tk, 0, int(n) + 1);
+            const uint32_t x = 32u * (uint32_t(wx0) + k) + b;
+            const uint32_t rec = x | (uint32_t(y) << 16) | (((wk >> b) & 1u) << 31);
+            rs.xinfo[r] = rec;
+            if (sm_ok)
+                sm.xinfo[r] = rec;
+            if (x == 0) {
+                rs.rowoff[y] = r;
+                if (sm_ok)
+                    sm.rowoff[y] = r;
+            }
+        }
+    } else
+    // pass 2 (lane-ordered): fill
     {
         uint32_t carry = first_carry;
         for (uint32_t qb = q0; qb < q1; qb += step) {
@@ -941,6 +1042,33 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
 // ------------------------------------------------------------------------------------------------------------------
 // labelling of runs
 // ------------------------------------------------------------------------------------------------------------------
+// The union-find starts from a FOREST instead of singletons: every run is hooked (plain store, no atomics) to the first
+// run of the row above that it touches and that has the same value.  Ids grow in raster order, so a hook always
+// points to a smaller id and the "labels only decrease" invariant holds from the start.  Almost every background run
+// of a frame touches exactly one background run above it, so the thousands of contended atomicMin calls on the root
+// of the background component disappear; only a run's SECOND and later neighbours above need a real union.
+template <bool FG8, bool MERGE_FG, bool SM>
+__device__ __forceinline__ uint32_t hook_of(const FusedArgs &P, const View<SM> &V, uint32_t r)
+{
+    const uint32_t xi = V.xi(r);
+    const uint32_t s = run_x(xi), y = run_y(xi), v = run_v(xi);
+    if ((!MERGE_FG && v) || y == 0)
+        return r;
+    const uint32_t e = V.end(r, V.ro(y + 1), P.W);
+    const uint32_t d = (FG8 && v) ? 1u : 0u; // 8-connected runs may touch diagonally
+    const uint32_t a = V.ro(y - 1), b = V.ro(y);
+    const uint32_t c0 = s >= d ? s - d : 0u;
+    const uint32_t c1 = min(e + d, uint32_t(P.W - 1));
+    for (uint32_t j = V.at(a, b, c0); j < b; ++j) {
+        const uint32_t xj = V.xi(j);
+        if (run_x(xj) > c1)
+            break;
+        if (run_v(xj) == v)
+            return j;
+    }
+    return r;
+}
+
 template <bool FG8, bool FRAME, bool MERGE_FG, bool SM>
 __device__ void merge_phase(const FusedArgs &P, const View<SM> &V, uint32_t T)
 {
@@ -956,12 +1084,16 @@ __device__ void merge_phase(const FusedArgs &P, const View<SM> &V, uint32_t T)
             const uint32_t a = V.ro(y - 1), b = V.ro(y);
             const uint32_t c0 = s >= d ? s - d : 0u;
             const uint32_t c1 = min(e + d, uint32_t(P.W - 1));
+            bool hooked = false; // the first same-valued neighbour is this run's hook (label_with)
             for (uint32_t j = V.at(a, b, c0); j < b; ++j) {
                 const uint32_t xj = V.xi(j);
                 if (run_x(xj) > c1)
                     break;
-                if (run_v(xj) == v)
-                    uf_union(par, r, j);
+                if (run_v(xj) == v) {
+                    if (hooked)
+                        uf_union(par, r, j);
+                    hooked = true;
+                }
             }
         }
     }
@@ -972,7 +1104,7 @@ __device__ void label_with(const FusedArgs &P, Shared &sh, const RunSet &rs, con
 {
     const Par<SM> par{V.parent};
     for (uint32_t r = threadIdx.x; r <= T; r += NT)
-        par.set(r, r);
+        par.set(r, r < T ? hook_of<FG8, MERGE_FG>(P, V, r) : r);
     if (FRAME)
         for (uint32_t i = threadIdx.x; i <= (T >> 5); i += NT) {
             if (SM)
@@ -980,6 +1112,23 @@ __device__ void label_with(const FusedArgs &P, Shared &sh, const RunSet &rs, con
             st(rs.fbits + i, 0u);
         }
     __syncthreads();
+    // pointer jumping: a hook goes exactly one row up, so the hooked forest is at most H deep (one chain through the
+    // background of an empty frame); ceil(log2 H) rounds of parent <- grandparent leave every run pointing at its root
+    // and the unions below start from flat trees
+    for (int span = 1; span < P.H; span <<= 1) {
+        int changed = 0;
+        for (uint32_t r = threadIdx.x; r < T; r += NT) {
+            const uint32_t p = par.get(r);
+            const uint32_t gp = par.get(p);
+            if (gp != p) {
+                par.set(r, gp);
+                changed = 1;
+            }
+        }
+        if (!__syncthreads_or(changed))
+            break;
+    }
+    prof_tick(P.prof, P.prof, sh, kPHook);
     merge_phase<FG8, FRAME, MERGE_FG, SM>(P, V, T);
     __syncthreads();
     prof_tick(P.prof, P.prof, sh, kPMerge);
@@ -1264,32 +1413,50 @@ __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) // bit j -> byte
     return (((n & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
 }
 
+__device__ __forceinline__ void expand_word(const FusedArgs &P, uint8_t *dst, uint32_t i, uint32_t w)
+{
+    int y, wx;
+    split(P, i, y, wx);
+    if (wx >= P.WW)
+        return;
+    uint8_t *o = dst + size_t(y) * P.W + 32u * wx;
+    if (P.fast_io) {
+        uint4 lo4, hi4;
+        lo4.x = nibble_to_bytes(w);
+        lo4.y = nibble_to_bytes(w >> 4);
+        lo4.z = nibble_to_bytes(w >> 8);
+        lo4.w = nibble_to_bytes(w >> 12);
+        hi4.x = nibble_to_bytes(w >> 16);
+        hi4.y = nibble_to_bytes(w >> 20);
+        hi4.z = nibble_to_bytes(w >> 24);
+        hi4.w = nibble_to_bytes(w >> 28);
+        __stcs(reinterpret_cast<uint4 *>(o), lo4); // masks are written once: streaming
+        __stcs(reinterpret_cast<uint4 *>(o) + 1, hi4);
+    } else {
+        const int n = min(32, P.W - 32 * wx);
+        for (int k = 0; k < n; ++k)
+            o[k] = ((w >> k) & 1u) ? 255 : 0;
+    }
+}
+
 __device__ void expand_phase(const FusedArgs &P, unsigned f, const uint32_t *A, const uint32_t *B, bool white)
 {
     uint8_t *dst = P.out + size_t(f) * P.out_stride;
-    for (uint32_t i = threadIdx.x; i < P.nwords; i += NT) {
-        int y, wx;
-        split(P, i, y, wx);
-        if (wx >= P.WW)
-            continue;
-        const uint32_t w = white ? 0xFFFFFFFFu : (ld(A + i) | ld(B + i));
-        uint8_t *o = dst + size_t(y) * P.W + 32u * wx;
-        if (P.fast_io) {
-            uint4 lo4, hi4;
-            lo4.x = nibble_to_bytes(w);
-            lo4.y = nibble_to_bytes(w >> 4);
-            lo4.z = nibble_to_bytes(w >> 8);
-            lo4.w = nibble_to_bytes(w >> 12);
-            hi4.x = nibble_to_bytes(w >> 16);
-            hi4.y = nibble_to_bytes(w >> 20);
-            hi4.z = nibble_to_bytes(w >> 24);
-            hi4.w = nibble_to_bytes(w >> 28);
-            __stcs(reinterpret_cast<uint4 *>(o), lo4); // masks are written once: streaming
-            __stcs(reinterpret_cast<uint4 *>(o) + 1, hi4);
-        } else {
-            const int n = min(32, P.W - 32 * wx);
-            for (int k = 0; k < n; ++k)
-                o[k] = ((w >> k) & 1u) ? 255 : 0;
+    constexpr int U = 4; // words in flight per thread: the loads come from L2, one at a time they cost ~1 us each
+    for (uint32_t i0 = threadIdx.x; i0 < P.nwords; i0 += U * NT) {
+        uint32_t w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + u * NT;
+            w[u] = 0xFFFFFFFFu;
+            if (!white && i < P.nwords)
+                w[u] = ld(A + i) | ld(B + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + u * NT;
+            if (i < P.nwords)
+                expand_word(P, dst, i, w[u]);
         }
     }
 }
@@ -1695,8 +1862,8 @@ int highlight_fused_batch(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, 
         cudaStreamSynchronize(stream);
         cudaMemcpy(h, P.prof, sizeof(h), cudaMemcpyDeviceToHost);
         cudaFree(P.prof);
-        static const char *names[] = {"bits", "erodeA", "dilateA", "extract(x6)", "merge(x6)", "flatten(x6)", "rso(x2)",
-                                      "fill(x2)", "hyst", "erodeB", "dilateB", "expand"};
+        static const char *names[] = {"bits", "erodeA", "dilateA", "fill runs(x6)", "merge(x6)", "flatten(x6)", "rso(x2)",
+                                      "fill(x2)", "hyst", "erodeB", "dilateB", "expand", "count runs(x6)", "hook(x6)"};
         const double nf = h[kPFrames] ? double(h[kPFrames]) : 1.0;
         double total = 0;
         for (int k = 0; k < kPRuns; ++k)
