@@ -229,13 +229,6 @@ __device__ __forceinline__ void uf_union(const Par<SM> &lab, uint32_t a, uint32_
     } while (!done);
 }
 
-__device__ __forceinline__ bool bit_at(const uint32_t *img, const FusedArgs &P, int x, int y)
-{
-    if (x < 0 || y < 0 || x >= P.W || y >= P.H)
-        return false;
-    return (ld(img + size_t(y) * P.WWp + (x >> 5)) >> (x & 31)) & 1u;
-}
-
 __device__ __forceinline__ void clear_range(uint32_t *row, int x0, int x1)
 {
     for (int w = x0 >> 5; w <= (x1 >> 5); ++w)
@@ -290,12 +283,12 @@ __device__ __forceinline__ void bits_of_32(const uint4 &f0, const uint4 &f1, con
     const uint32_t tha = ta.t4 | kH, thu = tu.t4 | kH, thl = tl.t4 | kH;
     wa = wu = wl = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 7; k >= 0; --k) { // last group first: each funnel shift pushes the word up by one nibble
         const uint32_t d = sub_sat_u8x4(bk[k], fr[k]);
         const uint32_t d7 = d & ~kH;
-        wa = (wa >> 4) | (gt_nibble_top(d, d7, ta.t4, tha) & 0xF0000000u);
-        wu = (wu >> 4) | (gt_nibble_top(d, d7, tu.t4, thu) & 0xF0000000u);
-        wl = (wl >> 4) | (gt_nibble_top(d, d7, tl.t4, thl) & 0xF0000000u);
+        wa = __funnelshift_l(gt_nibble_top(d, d7, ta.t4, tha), wa, 4); // (wa << 4) | top nibble: one SHF, no mask
+        wu = __funnelshift_l(gt_nibble_top(d, d7, tu.t4, thu), wu, 4);
+        wl = __funnelshift_l(gt_nibble_top(d, d7, tl.t4, thl), wl, 4);
     }
     wa = (wa | ta.force_or) & ta.force_and;
     wu = (wu | tu.force_or) & tu.force_and;
@@ -818,6 +811,11 @@ struct View {
 // shared-memory copy of a run set: [rowoff: H + 2, padded][xinfo: cap][parent: cap]
 struct SmemRuns {
     uint32_t *rowoff, *xinfo, *parent, *fbits;
+    uint32_t *stats;  // remove-small-objects statistics: link, st_s, st_e, st_x, `tp` words each (valid when st_ok)
+    uint32_t tp;      // array pitch of the current run set: T + 1 rounded up to 4
+    uint32_t avail;   // words of the area that starts at rowoff
+    uint32_t ro_words;
+    bool st_ok;       // the statistics arrays of the current run set also fit
     uint32_t cap; // runs (incl. the FRAME node) the copy can hold; 0 = the row offsets alone do not fit
     uint16_t *qoff; // run extraction: per 128-bit quad, the number of run starts, then their offset inside the owning
                     // warp's range (nullptr: the image has too many quads, the extraction takes the lane-ordered path)
@@ -841,11 +839,32 @@ __device__ __forceinline__ SmemRuns smem_runs(const FusedArgs &P, uint32_t *smem
     m.xinfo = smem + ro_words;
     m.parent = m.xinfo + m.cap;
     m.fbits = m.parent + m.cap;
+    m.stats = nullptr;
+    m.tp = 0;
+    m.avail = words;
+    m.ro_words = ro_words;
+    m.st_ok = false;
     return m;
 }
 
+// The arrays behind the run records are placed for the run count T of the set being extracted: parent and the FRAME
+// flags always (when they fit: sm_ok), and -- for the usual few thousand runs -- also the four statistics arrays of
+// the remove-small-objects step, whose atomics and dependent reads then stay on the SM.
+__device__ __forceinline__ bool place_run_arrays(SmemRuns &m, uint32_t T)
+{
+    const uint32_t tp = (T + 1u + 3u) & ~3u;
+    const uint32_t fbw = ((T >> 5) + 1u + 3u) & ~3u;
+    m.tp = tp;
+    m.parent = m.xinfo + tp;
+    m.fbits = m.parent + tp;
+    m.stats = m.fbits + fbw;
+    const bool sm_ok = m.cap != 0 && m.ro_words + 2u * tp + fbw <= m.avail;
+    m.st_ok = sm_ok && m.ro_words + 6u * tp + fbw <= m.avail;
+    return sm_ok;
+}
+
 // Returns T (the run count).  rowoff[H] = T.  sm_ok <- the set also sits in shared memory.
-__device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs, const SmemRuns &sm,
+__device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs, SmemRuns &sm,
                                  bool &sm_ok)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -891,7 +910,7 @@ __device__ uint32_t extract_runs(const FusedArgs &P, Shared &sh, const uint32_t 
             base += c;
         T += c;
     }
-    sm_ok = T + 1 <= sm.cap;
+    sm_ok = place_run_arrays(sm, T);
     // the warps' ranges hold at most 65535 runs each (else their 16-bit quad offsets overflow: lane-ordered path)
     bool quick = sm.qoff != nullptr;
 #pragma unroll
@@ -1158,7 +1177,7 @@ __device__ void label_with(const FusedArgs &P, Shared &sh, const RunSet &rs, con
 
 // labels the runs of `img` into run set rs; returns T; sm_ok <- the set is also resident in shared memory
 template <bool FG8, bool FRAME, bool MERGE_FG>
-__device__ uint32_t label_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs, const SmemRuns &sm,
+__device__ uint32_t label_runs(const FusedArgs &P, Shared &sh, const uint32_t *img, const RunSet &rs, SmemRuns &sm,
                                bool &sm_ok)
 {
     const uint32_t T = extract_runs(P, sh, img, rs, sm, sm_ok);
@@ -1212,7 +1231,31 @@ __device__ void hysteresis_phase(const FusedArgs &P, const View<false> &VU, uint
 // ------------------------------------------------------------------------------------------------------------------
 // remove small objects (RemoveSmallObjects :146-181), in place on img
 // ------------------------------------------------------------------------------------------------------------------
+// statistics arrays: shared memory (ST) or the slot's global scratch (read through L2 only: they are hit by atomics)
+template <bool ST, typename T_>
+__device__ __forceinline__ T_ sld(const T_ *p)
+{
+    return ST ? *reinterpret_cast<const volatile T_ *>(p) : __ldcg(p);
+}
+template <bool ST, typename T_>
+__device__ __forceinline__ void sst(T_ *p, T_ v)
+{
+    if (ST)
+        *reinterpret_cast<volatile T_ *>(p) = v;
+    else
+        __stcg(p, v);
+}
+
+// is pixel (x, yy) foreground?  Answered from the run set (the runs of a row alternate in value); j <- the run.
 template <bool SM>
+__device__ __forceinline__ bool fg_at(const FusedArgs &P, const View<SM> &V, int x, int yy, uint32_t &j, uint32_t &row_end)
+{
+    row_end = V.ro(yy + 1);
+    j = V.at(V.ro(yy), row_end, uint32_t(x));
+    return run_v(V.xi(j)) != 0u;
+}
+
+template <bool SM, bool ST>
 __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, uint32_t T, uint32_t *link, int *st_s, int *st_e,
                           int *st_x, int min_size, int *changed)
 {
@@ -1222,17 +1265,17 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, 
     for (uint32_t r = threadIdx.x; r <= T; r += NT) {
         if (r < T && V.par(r) != r)
             continue;
-        st(st_s + r, 0);
-        st(st_e + r, 0);
-        st(st_x + r, 0);
+        sst<ST>(st_s + r, 0);
+        sst<ST>(st_e + r, 0);
+        sst<ST>(st_x + r, 0);
         if (r == T)
             continue;
         const uint32_t xi = V.xi(r);
         const uint32_t s = run_x(xi);
         if (run_v(xi))
-            st(link + r, s == 0 ? T : V.region(r - 1, T)); // region left of the first pixel
+            sst<ST>(link + r, s == 0 ? T : V.region(r - 1, T)); // region left of the first pixel
         else
-            st(link + r, (s == 0 || V.is_frame(r)) ? kNoLabel : V.par(r - 1)); // component left of the hole
+            sst<ST>(link + r, (s == 0 || V.is_frame(r)) ? kNoLabel : V.par(r - 1)); // component left of the hole
     }
     __syncthreads();
     // contour statistics, accumulated on the contour's owner: the component for its outer contour, the hole's
@@ -1244,21 +1287,33 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, 
         const int s = int(run_x(xi)), y = int(run_y(xi));
         const int e = int(V.end(r, V.ro(y + 1), P.W));
         const uint32_t C = V.par(r);
-        const uint32_t bout = ld(link + C);
+        const uint32_t bout = sld<ST>(link + C);
         auto owner = [&](uint32_t b) { return b == bout ? C : b; };
         const uint32_t own_l = owner(s == 0 ? T : V.region(r - 1, T));
         const uint32_t own_r = owner(e == P.W - 1 ? T : V.region(r + 1, T));
         // horizontal cracks at the two run ends, and the convex corners there: 2x2 blocks in which a run end is the
         // only foreground pixel
         int xl = 0, xr = 0;
-        if (!bit_at(img, P, s, y - 1) && !bit_at(img, P, s - 1, y - 1))
-            ++xl;
-        if (!bit_at(img, P, s, y + 1) && !bit_at(img, P, s - 1, y + 1))
-            ++xl;
-        if (!bit_at(img, P, e, y - 1) && !bit_at(img, P, e + 1, y - 1))
-            ++xr;
-        if (!bit_at(img, P, e, y + 1) && !bit_at(img, P, e + 1, y + 1))
-            ++xr;
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy += 2) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= P.H) { // outside the image: background on both sides of both run ends
+                ++xl;
+                ++xr;
+                continue;
+            }
+            uint32_t j, row_end;
+            // (s, yy) and its left neighbour: the same run unless that run starts exactly at s
+            bool f = fg_at(P, V, s, yy, j, row_end);
+            bool fn = s > 0 && (int(run_x(V.xi(j))) < s ? f : !f);
+            if (!f && !fn)
+                ++xl;
+            // (e, yy) and its right neighbour: the same run unless that run ends exactly at e
+            f = fg_at(P, V, e, yy, j, row_end);
+            fn = e + 1 < P.W && (int(V.end(j, row_end, P.W)) > e ? f : !f);
+            if (!f && !fn)
+                ++xr;
+        }
         if (own_l == own_r) {
             atomicAdd(&st_s[own_l], e + 1 - s);
             atomicAdd(&st_e[own_l], 2);
@@ -1298,11 +1353,11 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, 
     for (uint32_t r = threadIdx.x; r < T; r += NT) {
         if (V.par(r) != r)
             continue;
-        const long long s = ld(st_s + r);
-        const int cracks = ld(st_e + r);
-        const long long len = (long long)cracks - ld(st_x + r);
+        const long long s = sld<ST>(st_s + r);
+        const int cracks = sld<ST>(st_e + r);
+        const long long len = (long long)cracks - sld<ST>(st_x + r);
         const long long two_a = run_v(V.xi(r)) ? 2 * s - len - 2 : 2 * (s < 0 ? -s : s) + len - 2;
-        st(st_e + r, (cracks > 0 && two_a < 2ll * min_size) ? 1 : 0);
+        sst<ST>(st_e + r, (cracks > 0 && two_a < 2ll * min_size) ? 1 : 0);
     }
     __syncthreads();
     // per component: st_x <- parity of the number of consecutive small contours up the nesting chain
@@ -1312,21 +1367,21 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, 
         int count = 0;
         uint32_t cur = r;
         for (;;) {
-            if (!ld(st_e + cur))
+            if (!sld<ST>(st_e + cur))
                 break;
             ++count;
-            const uint32_t b = ld(link + cur);
+            const uint32_t b = sld<ST>(link + cur);
             if (b == T)
                 break;
-            if (!ld(st_e + b))
+            if (!sld<ST>(st_e + b))
                 break;
             ++count;
-            const uint32_t par = ld(link + b);
+            const uint32_t par = sld<ST>(link + b);
             if (par == kNoLabel)
                 break;
             cur = par;
         }
-        st(st_x + r, count & 1);
+        sst<ST>(st_x + r, count & 1);
     }
     __syncthreads();
     // clear the pixels the single filled drawContours call erases (:178)
@@ -1339,13 +1394,13 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, 
         const uint32_t C = V.par(r);
         uint32_t *row = img + size_t(y) * P.WWp;
         bool cleared = false;
-        if (ld(st_x + C)) {
+        if (sld<ST>(st_x + C)) {
             clear_range(row, s, e);
             *changed = 1;
             continue;
         }
-        const uint32_t bout = ld(link + C);
-        auto is_small = [&](uint32_t b) { return ld(st_e + (b == bout ? C : b)) != 0; };
+        const uint32_t bout = sld<ST>(link + C);
+        auto is_small = [&](uint32_t b) { return sld<ST>(st_e + (b == bout ? C : b)) != 0; };
         if (is_small(s == 0 ? T : V.region(r - 1, T))) {
             clear_range(row, s, s);
             cleared = true;
@@ -1378,6 +1433,21 @@ __device__ void rso_phase(const FusedArgs &P, uint32_t *img, const View<SM> &V, 
             *changed = 1;
     }
     __syncthreads();
+}
+
+__device__ void rso_dispatch(const FusedArgs &P, uint32_t *img, const RunSet &ra, const SmemRuns &sm, bool sm_ok, uint32_t T,
+                             uint32_t *link, int *st_s, int *st_e, int *st_x, int min_size, int *changed)
+{
+    if (sm_ok && sm.st_ok)
+        rso_phase<true, true>(P, img, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, sm.stats,
+                              reinterpret_cast<int *>(sm.stats + sm.tp), reinterpret_cast<int *>(sm.stats + 2 * sm.tp),
+                              reinterpret_cast<int *>(sm.stats + 3 * sm.tp), min_size, changed);
+    else if (sm_ok)
+        rso_phase<true, false>(P, img, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link, st_s, st_e, st_x,
+                               min_size, changed);
+    else
+        rso_phase<false, false>(P, img, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link, st_s, st_e, st_x,
+                                min_size, changed);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1413,50 +1483,59 @@ __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) // bit j -> byte
     return (((n & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
 }
 
-__device__ __forceinline__ void expand_word(const FusedArgs &P, uint8_t *dst, uint32_t i, uint32_t w)
+// 16 mask bits -> 16 bytes of 0 / 255
+__device__ __forceinline__ uint4 half_to_bytes(uint32_t h)
 {
-    int y, wx;
-    split(P, i, y, wx);
-    if (wx >= P.WW)
-        return;
-    uint8_t *o = dst + size_t(y) * P.W + 32u * wx;
-    if (P.fast_io) {
-        uint4 lo4, hi4;
-        lo4.x = nibble_to_bytes(w);
-        lo4.y = nibble_to_bytes(w >> 4);
-        lo4.z = nibble_to_bytes(w >> 8);
-        lo4.w = nibble_to_bytes(w >> 12);
-        hi4.x = nibble_to_bytes(w >> 16);
-        hi4.y = nibble_to_bytes(w >> 20);
-        hi4.z = nibble_to_bytes(w >> 24);
-        hi4.w = nibble_to_bytes(w >> 28);
-        __stcs(reinterpret_cast<uint4 *>(o), lo4); // masks are written once: streaming
-        __stcs(reinterpret_cast<uint4 *>(o) + 1, hi4);
-    } else {
-        const int n = min(32, P.W - 32 * wx);
-        for (int k = 0; k < n; ++k)
-            o[k] = ((w >> k) & 1u) ? 255 : 0;
-    }
+    return make_uint4(nibble_to_bytes(h), nibble_to_bytes(h >> 4), nibble_to_bytes(h >> 8), nibble_to_bytes(h >> 12));
 }
 
+// A warp expands 32 consecutive bit words (1024 pixels) per round.  Lane l does not store the 32 bytes of "its" word
+// (that makes every store instruction touch half of 32 sectors); it stores 16-byte chunk l and chunk 32 + l of the
+// warp's 1 KB, taking the bits from the lanes that hold those words, so each store instruction writes 512 contiguous
+// bytes (whole sectors) whenever the 32 words lie in one image row.
 __device__ void expand_phase(const FusedArgs &P, unsigned f, const uint32_t *A, const uint32_t *B, bool white)
 {
     uint8_t *dst = P.out + size_t(f) * P.out_stride;
-    constexpr int U = 4; // words in flight per thread: the loads come from L2, one at a time they cost ~1 us each
-    for (uint32_t i0 = threadIdx.x; i0 < P.nwords; i0 += U * NT) {
+    const int lane = threadIdx.x & 31;
+    constexpr int U = 4; // rounds in flight per warp: the loads come from L2
+    const uint32_t nround = (P.nwords + 31u) / 32u;
+    for (uint32_t r0 = threadIdx.x >> 5; r0 < nround; r0 += U * NW) {
         uint32_t w[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t i = i0 + u * NT;
+            const uint32_t i = (r0 + u * NW) * 32u + lane;
             w[u] = 0xFFFFFFFFu;
-            if (!white && i < P.nwords)
+            if (!white && i < P.nwords && r0 + u * NW < nround)
                 w[u] = ld(A + i) | ld(B + i);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t i = i0 + u * NT;
-            if (i < P.nwords)
-                expand_word(P, dst, i, w[u]);
+            const uint32_t base = (r0 + u * NW) * 32u;
+            if (r0 + u * NW >= nround)
+                break; // warp-uniform
+            if (P.fast_io) {
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const int src_lane = 16 * part + (lane >> 1);
+                    const uint32_t ws = __shfl_sync(0xFFFFFFFFu, w[u], src_lane);
+                    const uint32_t i = base + src_lane;
+                    int y, wx;
+                    split(P, i, y, wx);
+                    if (i < P.nwords && wx < P.WW)
+                        __stcs(reinterpret_cast<uint4 *>(dst + size_t(y) * P.W + 32u * wx + 16u * (lane & 1)),
+                               half_to_bytes(ws >> (16 * (lane & 1)))); // masks are written once: streaming
+                }
+            } else {
+                const uint32_t i = base + lane;
+                int y, wx;
+                split(P, i, y, wx);
+                if (i < P.nwords && wx < P.WW) {
+                    uint8_t *o = dst + size_t(y) * P.W + 32u * wx;
+                    const int n = min(32, P.W - 32 * wx);
+                    for (int k = 0; k < n; ++k)
+                        o[k] = ((w[u] >> k) & 1u) ? 255 : 0;
+                }
+            }
         }
     }
 }
@@ -1490,7 +1569,7 @@ __global__ void __launch_bounds__(NT, 1) highlight_fused_kernel(const FusedArgs 
     int *st_s = reinterpret_cast<int *>(rbase + 5 * size_t(P.cap));
     int *st_e = reinterpret_cast<int *>(rbase + 6 * size_t(P.cap));
     int *st_x = reinterpret_cast<int *>(rbase + 7 * size_t(P.cap));
-    const SmemRuns sm = smem_runs(P, dyn);
+    SmemRuns sm = smem_runs(P, dyn);
 
     for (;;) {
         if (threadIdx.x == 0) {
@@ -1536,12 +1615,7 @@ __global__ void __launch_bounds__(NT, 1) highlight_fused_kernel(const FusedArgs 
         CVVP_DEBUG_STAGE(4, A, false)
         bool sm_ok;
         uint32_t T = label_runs<true, true, true>(P, sh, A, ra, sm, sm_ok);
-        if (sm_ok)
-            rso_phase(P, A, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link, st_s, st_e, st_x, P.min_th,
-                      &sh.changed);
-        else
-            rso_phase(P, A, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link, st_s, st_e, st_x, P.min_th,
-                      &sh.changed);
+        rso_dispatch(P, A, ra, sm, sm_ok, T, link, st_s, st_e, st_x, P.min_th, &sh.changed);
         prof_tick(P.prof, P.prof, sh, kPRso);
         CVVP_DEBUG_STAGE(5, A, false)
         // the hole fill needs the 4-connected background regions of the image: when nothing was cleared they are the
@@ -1584,12 +1658,7 @@ __global__ void __launch_bounds__(NT, 1) highlight_fused_kernel(const FusedArgs 
         prof_tick(P.prof, P.prof, sh, kPDilateB);
         CVVP_DEBUG_STAGE(8, U, false)
         T = label_runs<true, true, true>(P, sh, U, ra, sm, sm_ok);
-        if (sm_ok)
-            rso_phase(P, U, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link, st_s, st_e, st_x, P.min_hyst,
-                      &sh.changed);
-        else
-            rso_phase(P, U, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link, st_s, st_e, st_x, P.min_hyst,
-                      &sh.changed);
+        rso_dispatch(P, U, ra, sm, sm_ok, T, link, st_s, st_e, st_x, P.min_hyst, &sh.changed);
         prof_tick(P.prof, P.prof, sh, kPRso);
         CVVP_DEBUG_STAGE(9, U, false)
         if (sh.changed)
