@@ -274,25 +274,48 @@ __device__ __forceinline__ ThreshSpec make_thresh(int t)
     return s;
 }
 
+// tm: the smallest of the three thresholds (ThreshSpec of it), or force_or != 0 when one of them is negative.  Most
+// 32-pixel groups of a frame have no pixel above even the smallest threshold: one compare per four pixels settles all
+// three bit words.
 __device__ __forceinline__ void bits_of_32(const uint4 &f0, const uint4 &f1, const uint4 &b0, const uint4 &b1,
-                                           const ThreshSpec &ta, const ThreshSpec &tu, const ThreshSpec &tl, uint32_t &wa,
-                                           uint32_t &wu, uint32_t &wl)
+                                           const ThreshSpec &ta, const ThreshSpec &tu, const ThreshSpec &tl,
+                                           const ThreshSpec &tm, uint32_t &wa, uint32_t &wu, uint32_t &wl)
 {
     const uint32_t fr[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
     const uint32_t bk[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const uint32_t tha = ta.t4 | kH, thu = tu.t4 | kH, thl = tl.t4 | kH;
-    wa = wu = wl = 0;
+    const uint32_t tha = ta.t4 | kH, thu = tu.t4 | kH, thl = tl.t4 | kH, thm = tm.t4 | kH;
+    uint32_t d[8];
+    uint32_t any = tm.force_or;
 #pragma unroll
-    for (int k = 7; k >= 0; --k) { // last group first: each funnel shift pushes the word up by one nibble
-        const uint32_t d = sub_sat_u8x4(bk[k], fr[k]);
-        const uint32_t d7 = d & ~kH;
-        wa = __funnelshift_l(gt_nibble_top(d, d7, ta.t4, tha), wa, 4); // (wa << 4) | top nibble: one SHF, no mask
-        wu = __funnelshift_l(gt_nibble_top(d, d7, tu.t4, thu), wu, 4);
-        wl = __funnelshift_l(gt_nibble_top(d, d7, tl.t4, thl), wl, 4);
+    for (int k = 0; k < 8; ++k) {
+        d[k] = sub_sat_u8x4(bk[k], fr[k]);
+        const uint32_t t = thm - (d[k] & ~kH);
+        any |= ~((tm.t4 & ~d[k]) | (~(tm.t4 ^ d[k]) & t)) & kH; // byte MSB: d > smallest threshold
+    }
+    wa = wu = wl = 0;
+    if (any != 0u) {
+#pragma unroll
+        for (int k = 7; k >= 0; --k) { // last group first: each funnel shift pushes the word up by one nibble
+            const uint32_t d7 = d[k] & ~kH;
+            wa = __funnelshift_l(gt_nibble_top(d[k], d7, ta.t4, tha), wa, 4); // (wa << 4) | top nibble: one SHF
+            wu = __funnelshift_l(gt_nibble_top(d[k], d7, tu.t4, thu), wu, 4);
+            wl = __funnelshift_l(gt_nibble_top(d[k], d7, tl.t4, thl), wl, 4);
+        }
     }
     wa = (wa | ta.force_or) & ta.force_and;
     wu = (wu | tu.force_or) & tu.force_and;
     wl = (wl | tl.force_or) & tl.force_and;
+}
+
+// ThreshSpec of the smallest threshold that can still let a pixel pass (see bits_of_32)
+__device__ __forceinline__ ThreshSpec min_thresh(int a, int b, int c)
+{
+    if (a < 0 || b < 0 || c < 0) {
+        ThreshSpec s = make_thresh(0);
+        s.force_or = 0xFFFFFFFFu; // a negative threshold passes every pixel: no shortcut
+        return s;
+    }
+    return make_thresh(min(a, min(b, c)));
 }
 
 __device__ void bits_phase(const FusedArgs &P, unsigned f, uint32_t *A, uint32_t *U, uint32_t *L)
@@ -302,6 +325,7 @@ __device__ void bits_phase(const FusedArgs &P, unsigned f, uint32_t *A, uint32_t
     const int th_a = P.th_a ? __ldg(P.th_a + f) : P.th;
     if (P.fast_io) {
         const ThreshSpec ta = make_thresh(th_a), tu = make_thresh(P.hi), tl = make_thresh(P.lo);
+        const ThreshSpec tm = min_thresh(th_a, P.hi, P.lo);
         // two words per thread per iteration: eight 128-bit loads in flight
         for (uint32_t i0 = tid; i0 < P.nwords; i0 += 2 * NT) {
             const uint32_t i1 = i0 + NT;
@@ -328,14 +352,14 @@ __device__ void bits_phase(const FusedArgs &P, unsigned f, uint32_t *A, uint32_t
             }
             uint32_t wa = 0, wu = 0, wl = 0;
             if (v0)
-                bits_of_32(fa0, fa1, ba0, ba1, ta, tu, tl, wa, wu, wl);
+                bits_of_32(fa0, fa1, ba0, ba1, ta, tu, tl, tm, wa, wu, wl);
             A[i0] = wa;
             U[i0] = wu;
             L[i0] = wl;
             if (i1 < P.nwords) {
                 wa = wu = wl = 0;
                 if (v1)
-                    bits_of_32(fb0, fb1, bb0, bb1, ta, tu, tl, wa, wu, wl);
+                    bits_of_32(fb0, fb1, bb0, bb1, ta, tu, tl, tm, wa, wu, wl);
                 A[i1] = wa;
                 U[i1] = wu;
                 L[i1] = wl;
@@ -525,22 +549,18 @@ __device__ void open_bands(const FusedArgs &P, const short2 *offs, const uint32_
 }
 
 // ---- separable opening (MorphPlan) -----------------------------------------------------------------------------------
+// Thread mapping of every step: a thread keeps ONE quad column (qc = tid % quads-per-row) and walks rows r0, r0 + rstep,
+// ... of the band, so the row / column split, the column masks and the tile addresses are loop invariants.
+
 // horizontal step of one pattern over `rows` tile rows: dst row = AND / OR over the pattern's dx of (src row shifted)
 template <bool ERODE>
-__device__ void morph_rows_h(const FusedArgs &P, int pat, const uint32_t *src, uint32_t *dst, int rows, int pitch)
+__device__ __forceinline__ void morph_rows_h(const FusedArgs &P, int pat, const uint32_t *src, uint32_t *dst, int rows, int pitch,
+                                             int qc, int r0, int rstep)
 {
-    const int qpr = P.WWp >> 2;
     const int k0 = P.plan.pat_start[pat], k1 = P.plan.pat_start[pat + 1];
-    for (int i = threadIdx.x; i < rows * qpr; i += NT) {
-        int tr, qc;
-        if (P.wwp_shift >= 0) {
-            tr = i >> (P.wwp_shift - 2);
-            qc = i & (qpr - 1);
-        } else {
-            tr = i / qpr;
-            qc = i - tr * qpr;
-        }
-        const uint32_t *row = src + tr * pitch + kPadWords + 4 * qc;
+    const int off = kPadWords + 4 * qc;
+    for (int tr = r0; tr < rows; tr += rstep) {
+        const uint32_t *row = src + tr * pitch + off;
         const uint4 c = *reinterpret_cast<const uint4 *>(row);
         const uint32_t w[6] = {row[-1], c.x, c.y, c.z, c.w, row[4]};
         uint4 o = make_uint4(0, 0, 0, 0);
@@ -560,35 +580,8 @@ __device__ void morph_rows_h(const FusedArgs &P, int pat, const uint32_t *src, u
             }
             o = make_uint4(acc[0], acc[1], acc[2], acc[3]);
         }
-        *reinterpret_cast<uint4 *>(dst + tr * pitch + kPadWords + 4 * qc) = o;
+        *reinterpret_cast<uint4 *>(dst + tr * pitch + off) = o;
     }
-}
-
-// vertical step for tile row `trow` (taps read rows trow + dy - dy_min of the pattern tiles)
-template <bool ERODE>
-__device__ __forceinline__ uint4 morph_quad_v(const FusedArgs &P, const uint32_t *tiles, size_t tile_words, int pitch, int trow,
-                                              int qc)
-{
-    uint4 acc = ERODE ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint4(0, 0, 0, 0);
-    for (int k = 0; k < P.plan.nrows; ++k) {
-        const int pat = P.plan.row_pat[k];
-        const uint32_t *t = tiles + (P.plan.pat_ident[pat] ? 0 : size_t(pat + 1) * tile_words);
-        const uint4 v = *reinterpret_cast<const uint4 *>(t + (trow + P.plan.row_dy[k] - P.dy_min) * pitch + kPadWords + 4 * qc);
-        if (ERODE) {
-            acc.x &= v.x;
-            acc.y &= v.y;
-            acc.z &= v.z;
-            acc.w &= v.w;
-            if ((acc.x | acc.y | acc.z | acc.w) == 0)
-                break;
-        } else {
-            acc.x |= v.x;
-            acc.y |= v.y;
-            acc.z |= v.z;
-            acc.w |= v.w;
-        }
-    }
-    return acc;
 }
 
 __device__ __forceinline__ uint4 valid_quad(const FusedArgs &P, int qc)
@@ -598,8 +591,8 @@ __device__ __forceinline__ uint4 valid_quad(const FusedArgs &P, int qc)
     return make_uint4(valid_mask(P, 4 * qc), valid_mask(P, 4 * qc + 1), valid_mask(P, 4 * qc + 2), valid_mask(P, 4 * qc + 3));
 }
 
-// tiles: [0] staged rows (source, later the eroded rows' own tile is separate), [1 + p] pattern p's horizontal result,
-// [1 + npat] the eroded rows.  All tiles share one geometry (BH + 2 * span rows of `pitch` words).
+// tiles: [0] staged rows, [1 + p] pattern p's horizontal result (erosion, then reused for the dilation), [1 + npat] the
+// eroded rows.  All tiles share one geometry (BH + 2 * span rows of `pitch` words).
 __device__ void open_bands_sep(const FusedArgs &P, const uint32_t *src, uint32_t *dst, uint32_t *smem)
 {
     const int tid = threadIdx.x;
@@ -611,7 +604,12 @@ __device__ void open_bands_sep(const FusedArgs &P, const uint32_t *src, uint32_t
     const int npat = P.plan.npat;
     uint32_t *S = smem;
     uint32_t *E = smem + size_t(npat + 1) * tile_words;
-    const int qpr = P.WWp >> 2;
+    const int qpr = P.WWp >> 2;       // quads per row
+    const int rstep = NT / qpr;       // rows in flight per step (threads beyond rstep * qpr idle)
+    const int qc = tid % qpr, r0 = tid / qpr >= rstep ? INT_MAX / 2 : tid / qpr;
+    const int off = kPadWords + 4 * qc;
+    const uint4 vq = valid_quad(P, qc);
+    const int nrows = P.plan.nrows;
     // side pads of the staged rows (set) and of the eroded rows (clear); the pattern tiles' pads are never read
     for (int i = tid; i < rows_max * 2 * kPadWords; i += NT) {
         const int row = i / (2 * kPadWords), c = i - row * (2 * kPadWords);
@@ -624,87 +622,66 @@ __device__ void open_bands_sep(const FusedArgs &P, const uint32_t *src, uint32_t
         const int e0 = y0 + P.dy_min, e1 = y1 + P.dy_max; // eroded rows the band's dilation reads
         const int s0 = e0 + P.dy_min, s1 = e1 + P.dy_max; // source rows their erosion reads
         const int srows = s1 - s0, erows = e1 - e0;
-        for (int i = tid; i < srows * qpr; i += NT) {
-            int tr, qc;
-            if (P.wwp_shift >= 0) {
-                tr = i >> (P.wwp_shift - 2);
-                qc = i & (qpr - 1);
-            } else {
-                tr = i / qpr;
-                qc = i - tr * qpr;
-            }
+        // stage the source rows; invalid columns and out-of-image rows read as set
+        for (int tr = r0; tr < srows; tr += rstep) {
             const int r = s0 + tr;
             uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             if (r >= 0 && r < P.H) {
                 v = __ldcg(reinterpret_cast<const uint4 *>(src + size_t(r) * P.WWp) + qc);
-                const uint4 m = valid_quad(P, qc);
-                v.x |= ~m.x;
-                v.y |= ~m.y;
-                v.z |= ~m.z;
-                v.w |= ~m.w;
+                v.x |= ~vq.x;
+                v.y |= ~vq.y;
+                v.z |= ~vq.z;
+                v.w |= ~vq.w;
             }
-            *reinterpret_cast<uint4 *>(S + tr * pitch + kPadWords + 4 * qc) = v;
+            *reinterpret_cast<uint4 *>(S + tr * pitch + off) = v;
         }
         __syncthreads();
         for (int p = 0; p < npat; ++p)
             if (!P.plan.pat_ident[p])
-                morph_rows_h<true>(P, p, S, smem + size_t(p + 1) * tile_words, srows, pitch);
+                morph_rows_h<true>(P, p, S, smem + size_t(p + 1) * tile_words, srows, pitch, qc, r0, rstep);
         __syncthreads();
-        for (int i = tid; i < erows * qpr; i += NT) {
-            int te, qc;
-            if (P.wwp_shift >= 0) {
-                te = i >> (P.wwp_shift - 2);
-                qc = i & (qpr - 1);
-            } else {
-                te = i / qpr;
-                qc = i - te * qpr;
-            }
+        // erosion, vertical step: eroded tile row te <-> image row e0 + te; tap row k reads tile row te + dy_k - dy_min
+        for (int te = r0; te < erows; te += rstep) {
             const int e = e0 + te;
-            uint4 v = make_uint4(0, 0, 0, 0);
+            uint4 acc = make_uint4(0, 0, 0, 0);
             if (e >= 0 && e < P.H) {
-                v = morph_quad_v<true>(P, smem, tile_words, pitch, te, qc);
-                const uint4 m = valid_quad(P, qc);
-                v.x &= m.x;
-                v.y &= m.y;
-                v.z &= m.z;
-                v.w &= m.w;
+                acc = vq;
+                for (int k = 0; k < nrows; ++k) {
+                    const int pat = P.plan.row_pat[k];
+                    const uint32_t *t = smem + (P.plan.pat_ident[pat] ? 0 : size_t(pat + 1) * tile_words);
+                    const uint4 v = *reinterpret_cast<const uint4 *>(t + (te + P.plan.row_dy[k] - P.dy_min) * pitch + off);
+                    acc.x &= v.x;
+                    acc.y &= v.y;
+                    acc.z &= v.z;
+                    acc.w &= v.w;
+                    if ((acc.x | acc.y | acc.z | acc.w) == 0)
+                        break;
+                }
             }
-            *reinterpret_cast<uint4 *>(E + te * pitch + kPadWords + 4 * qc) = v;
+            *reinterpret_cast<uint4 *>(E + te * pitch + off) = acc;
         }
         __syncthreads();
         // dilation: the pattern tiles are reused for the horizontal results of the eroded rows; an identity pattern
-        // reads the eroded rows themselves, which must then sit where tile 0 is expected: pass E as the tile base
+        // reads the eroded rows themselves
         for (int p = 0; p < npat; ++p)
             if (!P.plan.pat_ident[p])
-                morph_rows_h<false>(P, p, E, smem + size_t(p + 1) * tile_words, erows, pitch);
+                morph_rows_h<false>(P, p, E, smem + size_t(p + 1) * tile_words, erows, pitch, qc, r0, rstep);
         __syncthreads();
-        for (int i = tid; i < (y1 - y0) * qpr; i += NT) {
-            int ty, qc;
-            if (P.wwp_shift >= 0) {
-                ty = i >> (P.wwp_shift - 2);
-                qc = i & (qpr - 1);
-            } else {
-                ty = i / qpr;
-                qc = i - ty * qpr;
-            }
-            // tile base E for identity patterns, smem + (p + 1) * tile_words for the others: expressed through one base
-            // pointer by giving morph_quad_v E as "tile 0" and the offset of the pattern tiles relative to it
+        for (int ty = r0; ty < y1 - y0; ty += rstep) {
             uint4 acc = make_uint4(0, 0, 0, 0);
-            for (int k = 0; k < P.plan.nrows; ++k) {
+            for (int k = 0; k < nrows; ++k) {
                 const int pat = P.plan.row_pat[k];
                 const uint32_t *t = P.plan.pat_ident[pat] ? E : smem + size_t(pat + 1) * tile_words;
-                const uint4 v =
-                    *reinterpret_cast<const uint4 *>(t + (ty + P.plan.row_dy[k] - P.dy_min) * pitch + kPadWords + 4 * qc);
+                const uint4 v = *reinterpret_cast<const uint4 *>(t + (ty + P.plan.row_dy[k] - P.dy_min) * pitch + off);
                 acc.x |= v.x;
                 acc.y |= v.y;
                 acc.z |= v.z;
                 acc.w |= v.w;
             }
-            const uint4 m = valid_quad(P, qc);
-            acc.x &= m.x;
-            acc.y &= m.y;
-            acc.z &= m.z;
-            acc.w &= m.w;
+            acc.x &= vq.x;
+            acc.y &= vq.y;
+            acc.z &= vq.z;
+            acc.w &= vq.w;
             *reinterpret_cast<uint4 *>(dst + size_t(y0 + ty) * P.WWp + 4 * qc) = acc;
         }
         __syncthreads();
@@ -1134,15 +1111,19 @@ __device__ void label_with(const FusedArgs &P, Shared &sh, const RunSet &rs, con
     // pointer jumping: a hook goes exactly one row up, so the hooked forest is at most H deep (one chain through the
     // background of an empty frame); ceil(log2 H) rounds of parent <- grandparent leave every run pointing at its root
     // and the unions below start from flat trees
-    for (int span = 1; span < P.H; span <<= 1) {
+    for (int span = 1; span < P.H; span <<= 2) {
         int changed = 0;
         for (uint32_t r = threadIdx.x; r < T; r += NT) {
-            const uint32_t p = par.get(r);
-            const uint32_t gp = par.get(p);
-            if (gp != p) {
-                par.set(r, gp);
+            uint32_t p = par.get(r);
+#pragma unroll
+            for (int hop = 0; hop < 3; ++hop) { // three jumps per barrier: up to 8x shallower per round
+                const uint32_t gp = par.get(p);
+                if (gp == p)
+                    break;
+                p = gp;
                 changed = 1;
             }
+            par.set(r, p);
         }
         if (!__syncthreads_or(changed))
             break;
