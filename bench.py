@@ -151,6 +151,28 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def bind_near_gpu(device_index: int) -> int:
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that the pinned host buffers it allocates
+    afterwards come from that NUMA node (with 8 ranks streaming 55 GB/s each, remote pages halve the H2D rate).
+    Returns the number of CPUs in the set (0: left unchanged)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def shard_plan(height: int, rank: int, world: int):
     """Row-band partition (the reference's own spatial sharding, cv_vid_frames_generator_algo.h:159-164, with
     horizontal bands instead of vertical strips so that every band is contiguous in memory).  The median is
@@ -364,8 +386,8 @@ def run_highlight_section(ctx, torch, dist, rank, local_rank, world, args, sampl
         "metric": "megapixel-frames/sec (per-frame highlight, 1080p)", "unit": UNIT,
         "value": total_mpx / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": world * nfr, "steps": steps,
         "gpu_launches": int(launches), "scaling": "weak", "sharding": "by frame, no collective",
-        "e2e": {"value": total_mpx / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nfr * npix),
-                "d2h_bytes_per_step": int(nfr * npix), "ms_per_step": e2e_s * 1e3},
+        "e2e": {"value": total_mpx / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(nfr * npix) * world,
+                "d2h_bytes_per_step": int(nfr * npix) * world, "ms_per_step": e2e_s * 1e3},
         "roofline": {"bound": "hbm", "achieved": 2.0 * nfr * npix / (ms * 1e-3) / 1e9, "peak": load_peaks()[0],
                      "unit": "GB/s", "frac": 2.0 * nfr * npix / (ms * 1e-3) / 1e9 / load_peaks()[0],
                      "traffic": load_traffic("highlight_ncu_summary.json") if (world == 1 and nfr == 1024) else None,
@@ -404,6 +426,8 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        bind_near_gpu(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -591,6 +615,7 @@ def run_gpu_arm_sharded(args, rank: int, local_rank: int, world: int):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_near_gpu(local_rank)
     dist.init_process_group("nccl", device_id=dev)
     w = WORKLOAD
     W, H, N = w["width"], w["height"], w["nframes"]

@@ -44,7 +44,8 @@ struct HighlightState; // highlight_state.hpp
 constexpr int kMaxShardRanks = 16;
 struct ShardPush {
     uint32_t *dst[kMaxShardRanks];
-    const uint32_t *sel; // round 2: per element, the globally selected high nibble in bits 0..3
+    const uint32_t *sel;   // round 2: per element, the globally selected high nibble in bits 0..3
+    const uint32_t *accum; // counts of this rank's earlier frame chunks (8 words per element), or nullptr
     uint32_t slice;
 };
 struct MedianShard; // median_shard.cu
@@ -69,6 +70,7 @@ struct cvvp_ctx {
     cvvp::MedianJob med;
     cvvp::HighlightState *hl{nullptr};
     cvvp::MedianShard *shard{nullptr};
+    cvvp::MedianShard *big{nullptr}; // internal one-rank job of the two-pass path for long stacks (median.cu)
     std::vector<cvvp::StagingBuf> staging;
     size_t staging_next{0};
 };
@@ -118,6 +120,9 @@ int median_pipe_launch(cvvp_ctx *ctx, const CUtensorMap &tmap, int log2s, uint8_
                        uint32_t nst, int mode, const ShardPush &push, cudaStream_t stream);
 // median_shard.cu
 void median_shard_release(cvvp_ctx *ctx);
+int median_two_pass(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
+                    uint8_t *d_out, cudaStream_t stream);
+long long median_two_pass_max_frames();
 // highlight.cu
 void highlight_release(cvvp_ctx *ctx);
 int highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, int height, const uint8_t *selem, int kw, int kh,

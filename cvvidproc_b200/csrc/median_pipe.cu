@@ -274,14 +274,29 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
             if ((lane >> kColBits) == 0u && e < nelem) {
                 const uint32_t owner = uint32_t(e) / push.slice;
                 uint32_t *dst = push.dst[owner] + (size_t(e) - size_t(owner) * push.slice) * 8u;
+                // more than one frame chunk on this rank: add the counts of the chunks before this one (packed u16
+                // pairs never carry: a rank holds at most 65535 frames)
+                const uint32_t *prev = push.accum ? push.accum + size_t(e) * 8u : nullptr;
                 if (G == 4) {
-                    const uint2 v = s_g == 0 ? make_uint2(acc[0], acc[1])
-                                  : s_g == 1 ? make_uint2(acc[2], acc[3])
-                                  : s_g == 2 ? make_uint2(acc[4], acc[5])
-                                             : make_uint2(acc[6], acc[7]);
+                    uint2 v = s_g == 0 ? make_uint2(acc[0], acc[1])
+                            : s_g == 1 ? make_uint2(acc[2], acc[3])
+                            : s_g == 2 ? make_uint2(acc[4], acc[5])
+                                       : make_uint2(acc[6], acc[7]);
+                    if (prev) {
+                        const uint2 a = __ldcg(reinterpret_cast<const uint2 *>(prev + 2u * s_g));
+                        v.x += a.x;
+                        v.y += a.y;
+                    }
                     *reinterpret_cast<uint2 *>(dst + 2u * s_g) = v;
                 } else {
-                    const uint4 v = s_g == 0 ? make_uint4(acc[0], acc[1], acc[2], acc[3]) : make_uint4(acc[4], acc[5], acc[6], acc[7]);
+                    uint4 v = s_g == 0 ? make_uint4(acc[0], acc[1], acc[2], acc[3]) : make_uint4(acc[4], acc[5], acc[6], acc[7]);
+                    if (prev) {
+                        const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(prev + 4u * s_g));
+                        v.x += a.x;
+                        v.y += a.y;
+                        v.z += a.z;
+                        v.w += a.w;
+                    }
                     *reinterpret_cast<uint4 *>(dst + 4u * s_g) = v;
                 }
             }

@@ -42,7 +42,12 @@ struct MedianShard {
     uint8_t *peer[kMaxShardRanks]{}; // base of every rank's buffer as mapped into this process (peer[rank] == buf)
     bool ipc_opened[kMaxShardRanks]{};
     bool attached[kMaxShardRanks]{};
+    uint32_t *accum{nullptr}; // [nelem][8 words]: running counts of this rank's frame chunks (allocated on first use)
 };
+
+// frames one launch of the counting kernel takes at full tile width (128-byte TMA boxes): 32 stages x 32 frames
+constexpr long long kChunkFrames = 1024;
+constexpr long long kMaxRankFrames = 65535; // 16-bit counts per rank
 
 namespace
 {
@@ -172,9 +177,8 @@ bool all_peers_known(const MedianShard *sh)
 }
 } // namespace
 
-void median_shard_release(cvvp_ctx *ctx)
+static void shard_destroy(cvvp_ctx *ctx, MedianShard *&sh)
 {
-    MedianShard *sh = ctx->shard;
     if (!sh)
         return;
     cudaStreamSynchronize(ctx->compute);
@@ -183,28 +187,21 @@ void median_shard_release(cvvp_ctx *ctx)
             cudaIpcCloseMemHandle(sh->peer[r]);
     if (sh->buf)
         cudaFree(sh->buf);
+    if (sh->accum)
+        cudaFree(sh->accum);
     cudaGetLastError();
     delete sh;
-    ctx->shard = nullptr;
+    sh = nullptr;
 }
-} // namespace cvvp
 
-using namespace cvvp;
-
-extern "C" {
-
-int cvvp_median_shard_begin(cvvp_ctx *ctx, size_t nelem, int rank, int world)
+void median_shard_release(cvvp_ctx *ctx)
 {
-    if (!ctx)
-        return fail(nullptr, CVVP_ERR_INVALID, "null context");
-    if (ctx->shard)
-        return fail(ctx, CVVP_ERR_STATE, "median shard: a sharded job is already open on this context");
-    if (nelem == 0 || nelem >= (1ull << 31))
-        return fail(ctx, CVVP_ERR_INVALID, "median shard: nelem must be in [1, 2^31)");
-    if (world < 1 || world > kMaxShardRanks || rank < 0 || rank >= world)
-        return fail(ctx, CVVP_ERR_INVALID, "median shard: rank %d / world %d out of range (world <= %d)", rank, world,
-                    kMaxShardRanks);
-    DeviceGuard guard(ctx->device);
+    shard_destroy(ctx, ctx->shard);
+    shard_destroy(ctx, ctx->big);
+}
+
+static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, MedianShard **out)
+{
     MedianShard *sh = new (std::nothrow) MedianShard();
     if (!sh)
         return fail(ctx, CVVP_ERR_NOMEM, "out of host memory");
@@ -231,8 +228,140 @@ int cvvp_median_shard_begin(cvvp_ctx *ctx, size_t nelem, int rank, int world)
         return fail(ctx, CVVP_ERR_CUDA, "median shard: clearing the exchange buffers failed");
     }
     sh->peer[rank] = sh->buf;
-    ctx->shard = sh;
+    *out = sh;
     return CVVP_OK;
+}
+
+// One phase of a sharded job (see the file header).  d_result: where phase 3 stores this rank's copy of the result
+// bytes instead of its own exchange buffer (the one-rank two-pass path writes straight into the caller's image).
+static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t *d_frames, long long nframes,
+                       size_t frame_stride, uint8_t *d_result, cudaStream_t s)
+{
+    if (!all_peers_known(sh))
+        return fail(ctx, CVVP_ERR_STATE, "median shard: not every peer buffer is mapped (import / attach all ranks first)");
+    if (nframes < 0)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: negative frame count");
+    if (nframes > kMaxRankFrames)
+        return fail(ctx, CVVP_ERR_UNSUPPORTED, "median shard: %lld frames on one rank exceed the 16-bit counts (%lld)", nframes,
+                    kMaxRankFrames);
+    if (phase == 0 || phase == 2) {
+        ShardPush push{};
+        const size_t off = (phase == 0 ? sh->off_c1 : sh->off_c2) + size_t(sh->rank) * sh->slice * 32u;
+        for (int r = 0; r < sh->world; ++r)
+            push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
+        push.sel = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_sel);
+        push.slice = sh->slice;
+        if (nframes == 0) {
+            const size_t n = sh->nelem * 2;
+            shard_zero_push_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(push, uint32_t(sh->nelem));
+            CVVP_CUDA_OK(ctx, cudaGetLastError());
+            ctx->launches++;
+            return CVVP_OK;
+        }
+        if (nframes <= kChunkFrames)
+            return median_launch_mode(ctx, d_frames, nframes, sh->nelem, frame_stride, nullptr, phase == 0 ? 1 : 2, push, s);
+        // long chunk of frames: several launches at full tile width; the counts of launch c are added to those of
+        // launches < c in a local array, the last launch pushes the totals to the owners
+        if (!sh->accum && cudaMalloc(reinterpret_cast<void **>(&sh->accum), sh->nelem * 32u) != cudaSuccess) {
+            cudaGetLastError();
+            sh->accum = nullptr;
+            return fail(ctx, CVVP_ERR_NOMEM, "median shard: cudaMalloc of %zu bytes for the running counts failed",
+                        sh->nelem * 32u);
+        }
+        const long long nchunks = (nframes + kChunkFrames - 1) / kChunkFrames;
+        long long per = (nframes + nchunks - 1) / nchunks;
+        per = (per + 31) / 32 * 32; // whole plane words
+        if (per > kChunkFrames)
+            per = kChunkFrames;
+        for (long long first = 0, c = 0; first < nframes; first += per, ++c) {
+            const long long n = nframes - first < per ? nframes - first : per;
+            const bool last = first + n >= nframes;
+            ShardPush cp = push;
+            cp.accum = c == 0 ? nullptr : sh->accum;
+            if (!last) { // every element "belongs" to slot 0 = the local running counts
+                cp.dst[0] = sh->accum;
+                cp.slice = 0x80000000u;
+            }
+            const int rc = median_launch_mode(ctx, d_frames + size_t(first) * frame_stride, n, sh->nelem, frame_stride, nullptr,
+                                              phase == 0 ? 1 : 2, cp, s);
+            if (rc != CVVP_OK)
+                return rc;
+        }
+        return CVVP_OK;
+    }
+    if (phase == 1 || phase == 3) {
+        OwnerArgs A{};
+        A.counts = reinterpret_cast<const uint32_t *>(sh->buf + (phase == 1 ? sh->off_c1 : sh->off_c2));
+        A.slice = sh->slice;
+        A.world = uint32_t(sh->world);
+        A.rank = uint32_t(sh->rank);
+        const size_t first = size_t(sh->rank) * sh->slice;
+        A.owned = first >= sh->nelem ? 0u : uint32_t(sh->nelem - first < sh->slice ? sh->nelem - first : sh->slice);
+        for (int r = 0; r < sh->world; ++r) {
+            A.sel[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_sel);
+            A.result[r] = sh->peer[r] + sh->off_res;
+        }
+        if (d_result)
+            A.result[sh->rank] = d_result;
+        if (A.owned == 0)
+            return CVVP_OK;
+        if (phase == 1)
+            shard_pick_kernel<<<(A.owned + 255) / 256, 256, 0, s>>>(A);
+        else
+            shard_final_kernel<<<((A.owned + 3) / 4 + 255) / 256, 256, 0, s>>>(A);
+        CVVP_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches++;
+        return CVVP_OK;
+    }
+    return fail(ctx, CVVP_ERR_INVALID, "median shard: phase must be 0..3");
+}
+
+long long median_two_pass_max_frames()
+{
+    return kMaxRankFrames;
+}
+
+// Single-GPU median of a stack too long for the on-chip select at full tile width: the sharded job with ONE rank.
+// Two passes over the frames in chunks of <= 1024 at 128-byte tiles beat one pass at the 32- or 16-byte tiles the
+// on-chip select would need beyond 2048 frames.
+int median_two_pass(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
+                    uint8_t *d_out, cudaStream_t stream)
+{
+    if (ctx->big && ctx->big->nelem != nelem)
+        shard_destroy(ctx, ctx->big);
+    if (!ctx->big) {
+        const int rc = shard_create(ctx, nelem, 0, 1, &ctx->big);
+        if (rc != CVVP_OK)
+            return rc;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_out) & 3u) != 0) // phase 3 stores four result bytes at a time
+        return fail(ctx, CVVP_ERR_INVALID, "median: the result pointer of a stack of more than 2048 frames must be 4-byte aligned");
+    for (int phase = 0; phase < 4; ++phase) {
+        const int rc = shard_phase(ctx, ctx->big, phase, d_frames, nframes, frame_stride, d_out, stream);
+        if (rc != CVVP_OK)
+            return rc;
+    }
+    return CVVP_OK;
+}
+} // namespace cvvp
+
+using namespace cvvp;
+
+extern "C" {
+
+int cvvp_median_shard_begin(cvvp_ctx *ctx, size_t nelem, int rank, int world)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    if (ctx->shard)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: a sharded job is already open on this context");
+    if (nelem == 0 || nelem >= (1ull << 31))
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: nelem must be in [1, 2^31)");
+    if (world < 1 || world > kMaxShardRanks || rank < 0 || rank >= world)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: rank %d / world %d out of range (world <= %d)", rank, world,
+                    kMaxShardRanks);
+    DeviceGuard guard(ctx->device);
+    return shard_create(ctx, nelem, rank, world, &ctx->shard);
 }
 
 int cvvp_median_shard_export(cvvp_ctx *ctx, void *handle_out)
@@ -304,54 +433,11 @@ int cvvp_median_shard_phase(cvvp_ctx *ctx, int phase, const uint8_t *d_frames, l
 {
     if (!ctx)
         return fail(nullptr, CVVP_ERR_INVALID, "null context");
-    MedianShard *sh = ctx->shard;
-    if (!sh)
+    if (!ctx->shard)
         return fail(ctx, CVVP_ERR_STATE, "median shard: no sharded job is open");
-    if (!all_peers_known(sh))
-        return fail(ctx, CVVP_ERR_STATE, "median shard: not every peer buffer is mapped (import / attach all ranks first)");
-    if (nframes < 0)
-        return fail(ctx, CVVP_ERR_INVALID, "median shard: negative frame count");
     DeviceGuard guard(ctx->device);
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->compute;
-    if (phase == 0 || phase == 2) {
-        ShardPush push{};
-        const size_t off = (phase == 0 ? sh->off_c1 : sh->off_c2) + size_t(sh->rank) * sh->slice * 32u;
-        for (int r = 0; r < sh->world; ++r)
-            push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
-        push.sel = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_sel);
-        push.slice = sh->slice;
-        if (nframes == 0) {
-            const size_t n = sh->nelem * 2;
-            shard_zero_push_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(push, uint32_t(sh->nelem));
-            CVVP_CUDA_OK(ctx, cudaGetLastError());
-            ctx->launches++;
-            return CVVP_OK;
-        }
-        return median_launch_mode(ctx, d_frames, nframes, sh->nelem, frame_stride, nullptr, phase == 0 ? 1 : 2, push, s);
-    }
-    if (phase == 1 || phase == 3) {
-        OwnerArgs A{};
-        A.counts = reinterpret_cast<const uint32_t *>(sh->buf + (phase == 1 ? sh->off_c1 : sh->off_c2));
-        A.slice = sh->slice;
-        A.world = uint32_t(sh->world);
-        A.rank = uint32_t(sh->rank);
-        const size_t first = size_t(sh->rank) * sh->slice;
-        A.owned = first >= sh->nelem ? 0u : uint32_t(sh->nelem - first < sh->slice ? sh->nelem - first : sh->slice);
-        for (int r = 0; r < sh->world; ++r) {
-            A.sel[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_sel);
-            A.result[r] = sh->peer[r] + sh->off_res;
-        }
-        if (A.owned == 0)
-            return CVVP_OK;
-        if (phase == 1)
-            shard_pick_kernel<<<(A.owned + 255) / 256, 256, 0, s>>>(A);
-        else
-            shard_final_kernel<<<((A.owned + 3) / 4 + 255) / 256, 256, 0, s>>>(A);
-        CVVP_CUDA_OK(ctx, cudaGetLastError());
-        ctx->launches++;
-        return CVVP_OK;
-    }
-    return fail(ctx, CVVP_ERR_INVALID, "median shard: phase must be 0..3");
+    return shard_phase(ctx, ctx->shard, phase, d_frames, nframes, frame_stride, nullptr, s);
 }
 
 int cvvp_median_shard_result(cvvp_ctx *ctx, const uint8_t **d_result)
@@ -369,7 +455,7 @@ int cvvp_median_shard_end(cvvp_ctx *ctx)
     if (!ctx)
         return fail(nullptr, CVVP_ERR_INVALID, "null context");
     DeviceGuard guard(ctx->device);
-    median_shard_release(ctx);
+    shard_destroy(ctx, ctx->shard);
     return CVVP_OK;
 }
 

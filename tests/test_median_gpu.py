@@ -169,15 +169,48 @@ def test_device_resident_full_size_property(gpu_ctx):
 
 
 def test_too_many_frames_is_a_loud_error(gpu_ctx):
+    """65535 frames is the limit of the two-pass path's 16-bit counts; beyond it the call fails, it does not guess"""
     import torch
     from cvvidproc_b200 import _cabi
 
-    n, nelem = 8193, 256
+    n, nelem = 65536, 16
     stack = torch.zeros((n, nelem), dtype=torch.uint8, device="cuda:0")
     out = torch.zeros(nelem, dtype=torch.uint8, device="cuda:0")
     with pytest.raises(_cabi.CvvpError) as ei:
         gpu_ctx.median_device(stack.data_ptr(), n, nelem, nelem, out.data_ptr())
     assert ei.value.code == -5
+
+
+@pytest.mark.parametrize("n", [2049, 3000, 5000, 8193, 10000, 20001, 65535])
+def test_long_stacks_take_the_two_pass_path(gpu_ctx, oracle_median, n):
+    """more than 2048 frames: two counting passes in chunks of <= 1024 frames (csrc/median_shard.cu, one rank)"""
+    rng = np.random.default_rng(n)
+    nelem = 300 if n < 20000 else 130
+    frames = rng.integers(60, 200, (n, 1, nelem), dtype=np.uint8)
+    frames[:, 0, 0] = 0          # value 0 coincides with the zero-filled pad slots of every chunk
+    frames[: n // 2, 0, 1] = 17  # exact 50/50 split: the UPPER median
+    frames[n // 2 :, 0, 1] = 201
+    got = gpu_ctx.median(frames, chunk=4096)
+    assert np.array_equal(got, oracle_median(frames))
+    assert got[0, 1] == 201 and got[0, 0] == 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 100, 1000, 1024, 1025, 2048])
+def test_two_pass_forced_on_short_stacks(gpu_ctx, oracle_median, n, monkeypatch):
+    """CVVP_MEDIAN_TWO_PASS=1 routes short stacks through the counting kernels as well (both must agree)"""
+    monkeypatch.setenv("CVVP_MEDIAN_TWO_PASS", "1")
+    rng = np.random.default_rng(n + 3)
+    frames = rng.integers(0, 256, (n, 3, 211), dtype=np.uint8)
+    assert np.array_equal(gpu_ctx.median(frames, chunk=512), oracle_median(frames))
+
+
+@pytest.mark.parametrize("n", [2049, 4096, 4097, 8192])
+def test_single_pass_forced_on_long_stacks(gpu_ctx, oracle_median, n, monkeypatch):
+    """CVVP_MEDIAN_TWO_PASS=0 keeps the on-chip select with its narrow tile variants covered"""
+    monkeypatch.setenv("CVVP_MEDIAN_TWO_PASS", "0")
+    rng = np.random.default_rng(n + 5)
+    frames = rng.integers(90, 140, (n, 5, 77), dtype=np.uint8)
+    assert np.array_equal(gpu_ctx.median(frames, chunk=512), oracle_median(frames))
 
 
 def test_cuda_reproduces_reference_golden(gpu_ctx):

@@ -96,6 +96,18 @@ def test_every_tile_variant(oracle_median, n_local):
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("world,n", [(2, 5001), (3, 7000)])
+def test_long_chunks_accumulate_over_launches(oracle_median, world, n):
+    """more than 1024 frames per rank: the counting rounds run as several launches whose counts are accumulated
+    locally before the last launch pushes them to the owners"""
+    rng = np.random.default_rng(n)
+    frames = rng.integers(0, 256, (n, 260), dtype=np.uint8)
+    frames[:, 0] = 0
+    want = oracle_median(frames.reshape(n, 1, 260)).reshape(-1)
+    for got in _sharded_median(_split(frames, world), 260):
+        assert np.array_equal(got, want)
+
+
 def test_two_valued_split_pins_upper_median():
     """exact 50/50 split across ranks: rank 0 holds only the low value, rank 1 only the high one"""
     n = 200
