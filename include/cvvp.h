@@ -103,8 +103,12 @@ CVVP_API int cvvp_median_abort(cvvp_ctx *ctx);
 
 /* Device-resident form: d_frames is a DEVICE pointer to nframes frames, frame f at
  * d_frames + f*frame_stride (frame_stride % 16 == 0 and d_frames 16-byte aligned, the TMA
- * tensor-map constraints), d_out a DEVICE pointer to nelem bytes.  Runs on `stream`
- * (a cudaStream_t, NULL = the context's compute stream) and does not synchronize. */
+ * tensor-map constraints), d_out a DEVICE pointer to nelem bytes (4-byte aligned).  Runs on
+ * `stream` (a cudaStream_t, NULL = the context's compute stream) and does not synchronize.
+ * Up to 2048 frames the select happens on chip in one pass over the frames; longer stacks (up to
+ * 65535 frames; more fails with CVVP_ERR_UNSUPPORTED) take two counting passes in chunks of 1024
+ * frames -- the reference's analogue of widening its histogram bins with the frame count
+ * (cv_vid_bg_helpers.cpp:232-253). */
 CVVP_API int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem,
                        size_t frame_stride, uint8_t *d_out, void *stream);
 
