@@ -68,6 +68,8 @@ def load():
         "cvvp_highlight_frames": (i32, [vp, vp, i64, sz, vp, sz]),
         "cvvp_highlight_device": (i32, [vp, vp, i64, sz, vp, sz, vp]),
         "cvvp_highlight_end": (i32, [vp]),
+        "cvvp_highlight_device_cc": (i32, [vp, vp, i64, sz, vp, sz, vp, i32, vp, vp, sz, vp]),
+        "cvvp_highlight_frames_cc": (i32, [vp, vp, i64, sz, vp, sz, vp, i32, vp, vp, sz]),
         "cvvp_highlight_set_path": (i32, [vp, i32]),
         "cvvp_highlight_frames_in_flight": (i32, [vp, C.POINTER(i32)]),
         "cvvp_synth_frames_device": (i32, [vp, vp, sz, i32, i32, i32, i32, i64, i64, u32, i32, vp]),
@@ -293,6 +295,29 @@ class Context:
         out = np.empty_like(frames)
         self._check(self._lib.cvvp_highlight_frames(self._h, frames.ctypes.data, n, npix, out.ctypes.data, npix))
         return out
+
+    # numpy view of struct cvvp_component (include/cvvp.h)
+    COMPONENT_DTYPE = np.dtype([("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4"), ("area", "<i4"),
+                                ("first_x", "<i4"), ("first_y", "<i4"), ("reserved", "<i4"), ("sum_x", "<i8"),
+                                ("sum_y", "<i8")])
+
+    def highlight_frames_cc(self, frames: np.ndarray, max_comps: int = 256, labels: bool = False):
+        """frames uint8 (n, H, W) -> (masks, comps, ncomps[, labels]): the masks plus the 8-connected components of
+        every mask (structured array (n, max_comps) of COMPONENT_DTYPE, raster-first order) and, if asked, the int32
+        label images (0 = background, k = component k of that frame)."""
+        frames = np.ascontiguousarray(frames)
+        if frames.dtype != np.uint8 or frames.ndim != 3 or frames.shape[1:] != self._hl_shape:
+            raise TypeError("frames must be uint8 of shape (n, H, W) matching the background")
+        n = frames.shape[0]
+        npix = frames.shape[1] * frames.shape[2]
+        out = np.empty_like(frames)
+        comps = np.zeros((n, max_comps), self.COMPONENT_DTYPE)
+        ncomps = np.zeros(n, np.int32)
+        lab = np.empty(frames.shape, np.int32) if labels else None
+        self._check(self._lib.cvvp_highlight_frames_cc(self._h, frames.ctypes.data, n, npix, out.ctypes.data, npix,
+                                                       comps.ctypes.data, max_comps, ncomps.ctypes.data,
+                                                       lab.ctypes.data if labels else None, npix))
+        return (out, comps, ncomps, lab) if labels else (out, comps, ncomps)
 
     def highlight_device(self, d_frames: int, n: int, frame_stride: int, d_out: int, out_stride: int, stream: int = 0):
         self._check(self._lib.cvvp_highlight_device(self._h, d_frames, n, frame_stride, d_out, out_stride, stream or None))

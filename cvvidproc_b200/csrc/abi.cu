@@ -519,6 +519,29 @@ int cvvp_highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, s
     return highlight_device(ctx, d_frames, n, frame_stride, d_out, out_stride, s);
 }
 
+int cvvp_highlight_device_cc(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride, uint8_t *d_out,
+                             size_t out_stride, cvvp_component *d_comps, int max_comps, int *d_ncomps, int32_t *d_labels,
+                             size_t labels_stride, void *stream)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->compute;
+    return highlight_device_cc(ctx, d_frames, n, frame_stride, d_out, out_stride, d_comps, max_comps, d_ncomps, d_labels,
+                               labels_stride, s);
+}
+
+int cvvp_highlight_frames_cc(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, uint8_t *masks_out,
+                             size_t out_stride, cvvp_component *comps_out, int max_comps, int *ncomps_out,
+                             int32_t *labels_out, size_t labels_stride)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    return highlight_frames_host_cc(ctx, frames, n, frame_stride, masks_out, out_stride, comps_out, max_comps, ncomps_out,
+                                    labels_out, labels_stride);
+}
+
 int cvvp_highlight_end(cvvp_ctx *ctx)
 {
     if (!ctx)

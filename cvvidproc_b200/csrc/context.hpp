@@ -129,6 +129,12 @@ int highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, int hei
                     int threshold, int threshold_lo, int threshold_hi, int min_size_hyst, int min_size_threshold);
 int highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride, uint8_t *d_out,
                      size_t out_stride, cudaStream_t stream);
+int highlight_device_cc(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride, uint8_t *d_out,
+                        size_t out_stride, cvvp_component *d_comps, int max_comps, int *d_ncomps, int32_t *d_labels,
+                        size_t labels_stride, cudaStream_t stream);
+int highlight_frames_host_cc(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, uint8_t *masks_out,
+                             size_t out_stride, cvvp_component *comps_out, int max_comps, int *ncomps_out,
+                             int32_t *labels_out, size_t labels_stride);
 int highlight_set_path(cvvp_ctx *ctx, int path);
 int highlight_frames_in_flight(cvvp_ctx *ctx, int *out_frames);
 int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, uint8_t *masks_out,

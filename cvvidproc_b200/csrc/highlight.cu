@@ -530,7 +530,7 @@ void free_state(HighlightState *s)
     if (!s)
         return;
     void *ptrs[] = {s->d_bg, s->d_offs, s->m_a, s->m_u, s->m_l, s->m_t, s->m_out, s->lab0, s->lab1,
-                    s->st_s, s->st_e, s->st_x, s->d_th, s->d_hist, s->d_in, s->d_res};
+                    s->st_s, s->st_e, s->st_x, s->d_th, s->d_hist, s->d_in, s->d_res, s->d_comps, s->d_ncomps, s->d_labels};
     for (void *p : ptrs)
         if (p)
             cudaFree(p);
@@ -807,6 +807,104 @@ int highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t
         if ((rc = highlight_fused_batch(ctx, st, in, frame_stride, nb, d_out + size_t(done) * out_stride, out_stride,
                                         stream)) != CVVP_OK)
             return rc;
+    }
+    return CVVP_OK;
+}
+
+static_assert(sizeof(cvvp_component) == 48, "cvvp_component is part of the C ABI (include/cvvp.h, _cabi.COMPONENT_DTYPE)");
+
+int highlight_device_cc(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride, uint8_t *d_out,
+                        size_t out_stride, cvvp_component *d_comps, int max_comps, int *d_ncomps, int32_t *d_labels,
+                        size_t labels_stride, cudaStream_t stream)
+{
+    HighlightState *st = ctx->hl;
+    if (!st)
+        return fail(ctx, CVVP_ERR_STATE, "highlight: no parameters set (call cvvp_highlight_begin first)");
+    if (!d_comps || !d_ncomps || max_comps < 1 || (d_labels && labels_stride < st->g.npix))
+        return fail(ctx, CVVP_ERR_INVALID, "highlight components: bad arguments");
+    if (!use_fused(st))
+        return fail(ctx, CVVP_ERR_UNSUPPORTED, "highlight components: only the fused path labels the final masks");
+    if (n > (1ll << 20))
+        return fail(ctx, CVVP_ERR_UNSUPPORTED, "highlight components: at most 2^20 frames per call");
+    st->cc.comps = d_comps;
+    st->cc.max_comps = max_comps;
+    st->cc.ncomps = d_ncomps;
+    st->cc.labels = d_labels;
+    st->cc.labels_stride = labels_stride;
+    const int rc = highlight_device(ctx, d_frames, n, frame_stride, d_out, out_stride, stream);
+    st->cc = CcOut();
+    return rc;
+}
+
+template <typename T>
+static int grow(cvvp_ctx *ctx, T **p, size_t *cap, size_t need)
+{
+    if (*cap >= need)
+        return CVVP_OK;
+    if (*p)
+        cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    if (cudaMalloc(reinterpret_cast<void **>(p), need * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, CVVP_ERR_NOMEM, "highlight components: cudaMalloc of %zu bytes failed", need * sizeof(T));
+    }
+    *cap = need;
+    return CVVP_OK;
+}
+
+// Host-buffer form with components: chunks run one after another (H2D, one kernel launch, D2H); the label images
+// quadruple the D2H volume, so this entry point is for callers that want the labels more than the last GB/s.
+int highlight_frames_host_cc(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, uint8_t *masks_out,
+                             size_t out_stride, cvvp_component *comps_out, int max_comps, int *ncomps_out,
+                             int32_t *labels_out, size_t labels_stride)
+{
+    HighlightState *st = ctx->hl;
+    if (!st)
+        return fail(ctx, CVVP_ERR_STATE, "highlight: no parameters set (call cvvp_highlight_begin first)");
+    if (!frames || !masks_out || !comps_out || !ncomps_out || max_comps < 1 || n < 0 || frame_stride < st->g.npix ||
+        out_stride < st->g.npix || (labels_out && labels_stride < st->g.npix))
+        return fail(ctx, CVVP_ERR_INVALID, "highlight components: bad arguments");
+    if (n == 0)
+        return CVVP_OK;
+    const size_t np = st->g.npix;
+    const size_t pitch = (np + 127) & ~size_t(127);
+    long long chunk = fused_supports(st) ? fused_frames_in_flight(ctx, st) : 16;
+    if (chunk > n)
+        chunk = n;
+    int rc;
+    if (st->in_bytes < size_t(chunk) * pitch) {
+        if (st->d_in) cudaFree(st->d_in);
+        if (st->d_res) cudaFree(st->d_res);
+        st->d_in = st->d_res = nullptr;
+        st->in_bytes = 0;
+        if ((rc = dev_alloc(ctx, &st->d_in, 2 * size_t(chunk) * pitch)) || (rc = dev_alloc(ctx, &st->d_res, 2 * size_t(chunk) * pitch)))
+            return rc;
+        st->in_bytes = size_t(chunk) * pitch;
+    }
+    if ((rc = grow(ctx, &st->d_comps, &st->comps_cap, size_t(chunk) * size_t(max_comps))) ||
+        (rc = grow(ctx, &st->d_ncomps, &st->ncomps_cap, size_t(chunk))) ||
+        (labels_out && (rc = grow(ctx, &st->d_labels, &st->labels_cap, size_t(chunk) * np))))
+        return rc;
+    cudaStream_t s = ctx->compute;
+    for (long long done = 0; done < n; done += chunk) {
+        const long long nb = n - done < chunk ? n - done : chunk;
+        CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(st->d_in, pitch, frames + size_t(done) * frame_stride, frame_stride, np, size_t(nb),
+                                            cudaMemcpyHostToDevice, s));
+        rc = highlight_device_cc(ctx, st->d_in, nb, pitch, st->d_res, pitch, st->d_comps, max_comps, st->d_ncomps,
+                                 labels_out ? st->d_labels : nullptr, np, s);
+        if (rc != CVVP_OK)
+            return rc;
+        CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(masks_out + size_t(done) * out_stride, out_stride, st->d_res, pitch, np, size_t(nb),
+                                            cudaMemcpyDeviceToHost, s));
+        CVVP_CUDA_OK(ctx, cudaMemcpyAsync(comps_out + size_t(done) * max_comps, st->d_comps,
+                                          size_t(nb) * max_comps * sizeof(cvvp_component), cudaMemcpyDeviceToHost, s));
+        CVVP_CUDA_OK(ctx, cudaMemcpyAsync(ncomps_out + done, st->d_ncomps, size_t(nb) * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (labels_out)
+            CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(labels_out + size_t(done) * labels_stride, labels_stride * sizeof(int32_t),
+                                                st->d_labels, np * sizeof(int32_t), np * sizeof(int32_t), size_t(nb),
+                                                cudaMemcpyDeviceToHost, s));
+        CVVP_CUDA_OK(ctx, cudaStreamSynchronize(s));
     }
     return CVVP_OK;
 }

@@ -92,6 +92,12 @@ struct FusedArgs {
     // opening in shared-memory row bands (0 rows = structuring element too large: global-memory taps instead)
     int band_rows, dy_min, dy_max, pad_words;
     MorphPlan plan;
+    // optional component output of the final masks (cvvp_highlight_device_cc): nullptr = off
+    cvvp_component *comps; // [frame][max_comps]
+    int *ncomps;           // [frame]
+    int max_comps;
+    int32_t *labels;       // [frame][labels_stride] or nullptr
+    size_t labels_stride;
     unsigned long long *prof; // per-phase nanoseconds summed over frames (CVVP_HL_PROF=1), or nullptr
     int debug_stage; // 0 = off; k > 0: write the bit image of intermediate stage k instead of the result (tools/)
 };
@@ -1522,6 +1528,102 @@ __device__ void expand_phase(const FusedArgs &P, unsigned f, const uint32_t *A, 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// components of the final mask (opt-in): what the reference's users compute on the host in their tracker callback with
+// cv2.connectedComponentsWithStats(bw_frame, connectivity=8) (assign_objects_algo.h:124-130 hands them bw_frame; the
+// in-code note highlight_objects_algo.cpp:152-153 weighs that very call).  8-connected components of the mask, numbered
+// 1.. in the raster order of their first pixels (canonical labelling); per component: bounding box, area, first
+// pixel, coordinate sums (centroid = sums / area).  The label image is optional (4 bytes per pixel of output).
+// ------------------------------------------------------------------------------------------------------------------
+template <bool SM>
+__device__ void components_phase(const FusedArgs &P, Shared &sh, unsigned f, const View<SM> &V, uint32_t T, uint32_t *cidx)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // component number of every foreground root = how many foreground roots precede it (ids are in raster order).
+    // Threads take contiguous chunks of run ids so that a block scan of the per-thread counts gives the offsets.
+    const uint32_t per = (T + NT - 1) / NT;
+    const uint32_t r0 = min(threadIdx.x * per, T), r1 = min(r0 + per, T);
+    uint32_t cnt = 0;
+    for (uint32_t r = r0; r < r1; ++r)
+        cnt += (run_v(V.xi(r)) && V.par(r) == r) ? 1u : 0u;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d)
+            inc += n;
+    }
+    if (lane == 31)
+        sh.wsum[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const uint32_t c = sh.wsum[w];
+        if (w < warp)
+            base += c;
+        total += c;
+    }
+    uint32_t k = base + inc - cnt;
+    cvvp_component *comps = P.comps + size_t(f) * P.max_comps;
+    for (uint32_t r = r0; r < r1; ++r) {
+        const uint32_t xi = V.xi(r);
+        if (run_v(xi) && V.par(r) == r) {
+            st(cidx + r, k);
+            if (k < uint32_t(P.max_comps)) {
+                cvvp_component c;
+                c.x0 = INT_MAX, c.y0 = INT_MAX, c.x1 = -1, c.y1 = -1;
+                c.area = 0;
+                c.first_x = int(run_x(xi)), c.first_y = int(run_y(xi));
+                c.reserved = 0;
+                c.sum_x = 0, c.sum_y = 0;
+                comps[k] = c;
+            }
+            ++k;
+        }
+    }
+    if (threadIdx.x == 0)
+        P.ncomps[f] = int(total);
+    __threadfence_block();
+    __syncthreads();
+    int32_t *lab = P.labels ? P.labels + size_t(f) * P.labels_stride : nullptr;
+    if (lab) { // background = 0 everywhere first
+        const uint32_t npix = uint32_t(P.W) * uint32_t(P.H);
+        const bool vec = (reinterpret_cast<uintptr_t>(lab) & 15u) == 0;
+        const uint32_t n4 = vec ? npix / 4u : 0u;
+        for (uint32_t i = threadIdx.x; i < n4; i += NT)
+            __stcs(reinterpret_cast<int4 *>(lab) + i, make_int4(0, 0, 0, 0));
+        for (uint32_t i = 4u * n4 + threadIdx.x; i < npix; i += NT)
+            lab[i] = 0;
+        __syncthreads();
+    }
+    for (uint32_t r = threadIdx.x; r < T; r += NT) {
+        const uint32_t xi = V.xi(r);
+        if (!run_v(xi))
+            continue;
+        const int s = int(run_x(xi)), y = int(run_y(xi));
+        const int e = int(V.end(r, V.ro(y + 1), P.W));
+        const uint32_t kk = ld(cidx + V.par(r));
+        if (kk < uint32_t(P.max_comps)) {
+            cvvp_component *c = comps + kk;
+            const int len = e - s + 1;
+            atomicAdd(&c->area, len);
+            atomicMin(&c->x0, s);
+            atomicMax(&c->x1, e);
+            atomicMin(&c->y0, y);
+            atomicMax(&c->y1, y);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&c->sum_x), (unsigned long long)((long long)(s + e) * len / 2));
+            atomicAdd(reinterpret_cast<unsigned long long *>(&c->sum_y), (unsigned long long)((long long)y * len));
+        }
+        if (lab) {
+            int32_t *row = lab + size_t(y) * P.W;
+            for (int x = s; x <= e; ++x)
+                row[x] = int32_t(kk + 1u);
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kSmemOffs = 256; // structuring-element taps cached in shared memory
@@ -1655,6 +1757,21 @@ __global__ void __launch_bounds__(NT, 1) highlight_fused_kernel(const FusedArgs 
         expand_phase(P, f, A, U, sh.white[0] || sh.white[1]);
         __syncthreads();
         prof_tick(P.prof, P.prof, sh, kPExpand);
+        if (P.comps) {
+            // final mask as a bit image (A and U are not needed any more), labelled 8-connected
+            const bool white = sh.white[0] || sh.white[1];
+            for (uint32_t i = threadIdx.x; i < P.nwords; i += NT) {
+                int y, wx;
+                split(P, i, y, wx);
+                Tm[i] = (white ? 0xFFFFFFFFu : (ld(A + i) | ld(U + i))) & valid_mask(P, wx);
+            }
+            __syncthreads();
+            T = label_runs<true, false, true>(P, sh, Tm, ra, sm, sm_ok);
+            if (sm_ok)
+                components_phase(P, sh, f, View<true>{sm.xinfo, sm.rowoff, sm.parent, sm.fbits}, T, link);
+            else
+                components_phase(P, sh, f, View<false>{ra.xinfo, ra.rowoff, ra.parent, ra.fbits}, T, link);
+        }
         if (P.prof && threadIdx.x == 0)
             atomicAdd(P.prof + kPFrames, 1ull);
     }
@@ -1897,6 +2014,11 @@ int highlight_fused_batch(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, 
                 out_stride % 16 == 0;
     const char *dbg = getenv("CVVP_HL_DEBUG_STAGE");
     P.debug_stage = dbg ? atoi(dbg) : 0;
+    P.comps = st->cc.comps;
+    P.ncomps = st->cc.ncomps;
+    P.max_comps = st->cc.max_comps;
+    P.labels = st->cc.labels;
+    P.labels_stride = st->cc.labels_stride;
     P.prof = nullptr;
     const bool want_prof = getenv("CVVP_HL_PROF") != nullptr;
     if (want_prof && cudaMalloc(reinterpret_cast<void **>(&P.prof), kPCount * sizeof(unsigned long long)) == cudaSuccess)

@@ -28,6 +28,15 @@ struct FusedScratch {
     unsigned queue_next{0};
 };
 
+// optional component output of the call in progress (cvvp_highlight_device_cc); comps == nullptr: off
+struct CcOut {
+    cvvp_component *comps{nullptr};
+    int max_comps{0};
+    int *ncomps{nullptr};
+    int32_t *labels{nullptr};
+    size_t labels_stride{0};
+};
+
 struct HighlightState {
     HlGeom g{};
     int th{}, lo{}, hi{}, min_hyst{}, min_th{};
@@ -48,6 +57,12 @@ struct HighlightState {
     unsigned int *d_hist{nullptr};
     // fused path
     FusedScratch fs;
+    CcOut cc;
+    // staging of the host-buffer component entry point
+    cvvp_component *d_comps{nullptr};
+    int *d_ncomps{nullptr};
+    int32_t *d_labels{nullptr};
+    size_t comps_cap{0}, ncomps_cap{0}, labels_cap{0};
     // staging for the host-buffer entry point
     uint8_t *d_in{nullptr}, *d_res{nullptr};
     size_t in_bytes{0};

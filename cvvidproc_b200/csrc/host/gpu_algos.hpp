@@ -150,6 +150,10 @@ struct GpuHighlightPack { // TokenProcessorPack<HighlightObjectsAlgo> :21-32
     FrameBatch background{};     // 1 frame, 1 channel
     FrameBatch struct_element{}; // 1 "frame" of kh x kw bytes
     int threshold{}, threshold_lo{}, threshold_hi{}, min_size_hyst{}, min_size_threshold{}, width_border{};
+    // opt-in extras (no counterpart in the reference's pack): 8-connected components of every mask for the tracker
+    bool components{false};
+    bool labels{false};
+    int max_components{1024};
 };
 
 class GpuHighlightAlgo
@@ -175,10 +179,26 @@ public:
             return;
         CVVP_ASSERT_MSG(batch->channels == 1 && batch->rows == m_pack.background.rows && batch->cols == m_pack.background.cols,
                         "frame geometry must match the background");
-        m_ctx.check(cvvp_highlight_frames(m_ctx.get(), batch->data.data(), batch->n, batch->frame_bytes(),
-                                          batch->data.data(), batch->frame_bytes()));
+        if (m_pack.components) {
+            m_comps.assign(std::size_t(batch->n) * m_pack.max_components, cvvp_component{});
+            m_ncomps.assign(std::size_t(batch->n), 0);
+            if (m_pack.labels)
+                m_labels.resize(std::size_t(batch->n) * batch->frame_bytes());
+            m_ctx.check(cvvp_highlight_frames_cc(m_ctx.get(), batch->data.data(), batch->n, batch->frame_bytes(),
+                                                 batch->data.data(), batch->frame_bytes(), m_comps.data(),
+                                                 m_pack.max_components, m_ncomps.data(),
+                                                 m_pack.labels ? m_labels.data() : nullptr, batch->frame_bytes()));
+        } else {
+            m_ctx.check(cvvp_highlight_frames(m_ctx.get(), batch->data.data(), batch->n, batch->frame_bytes(),
+                                              batch->data.data(), batch->frame_bytes()));
+        }
         m_result = std::move(batch);
     }
+    // components of frame i of the last result batch (valid until the next Insert)
+    int component_count(int i) const { return m_ncomps.empty() ? 0 : m_ncomps[std::size_t(i)]; }
+    const cvvp_component *components(int i) const { return m_comps.data() + std::size_t(i) * m_pack.max_components; }
+    const std::int32_t *labels(int i, std::size_t npix) const { return m_labels.empty() ? nullptr : m_labels.data() + std::size_t(i) * npix; }
+    int max_components() const { return m_pack.max_components; }
     std::unique_ptr<FrameBatch> TryGetResult() { return std::move(m_result); } // :72-79
     void NotifyNoMoreTokens() {}                                               // :82-85 (tokens are independent)
     bool HasResults() const { return static_cast<bool>(m_result); }            // :88-91
@@ -187,5 +207,8 @@ private:
     GpuHighlightPack m_pack;
     Context m_ctx;
     std::unique_ptr<FrameBatch> m_result{};
+    std::vector<cvvp_component> m_comps{};
+    std::vector<int> m_ncomps{};
+    std::vector<std::int32_t> m_labels{};
 };
 } // namespace cvvp_host

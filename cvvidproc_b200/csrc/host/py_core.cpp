@@ -267,6 +267,18 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
     hp.min_size_hyst = pack.highlight_objects_pack.min_size_hyst;
     hp.min_size_threshold = pack.highlight_objects_pack.min_size_threshold;
     hp.width_border = pack.highlight_objects_pack.width_border;
+    // Opt-in extra of this implementation (the reference has no counterpart): kwargs["cvvp_components"] = True makes
+    // the device label the 8-connected components of every mask and hands the callback one more keyword argument,
+    // `components` = {"count", "stats" (count x 5: x, y, w, h, area -- cv2.connectedComponentsWithStats columns),
+    // "centroids" (count x 2), "first" (count x 2: raster-first pixel x, y)[, "labels" (int32 H x W) with
+    // kwargs["cvvp_labels"] = True]}; components are numbered in the raster order of their first pixels.
+    const py::dict &user_kwargs = pack.assign_objects_pack.kwargs;
+    const bool want_comps = user_kwargs.contains("cvvp_components") && user_kwargs["cvvp_components"].cast<bool>();
+    const bool want_labels = want_comps && user_kwargs.contains("cvvp_labels") && user_kwargs["cvvp_labels"].cast<bool>();
+    hp.components = want_comps;
+    hp.labels = want_labels;
+    if (want_comps && user_kwargs.contains("cvvp_max_components"))
+        hp.max_components = std::max(1, user_kwargs["cvvp_max_components"].cast<int>());
     GpuHighlightAlgo highlighter{std::move(hp)};
 
     // frames per device batch: the reference's batch_size is a thread count; here it is sized for the GPU and bounded by
@@ -315,11 +327,51 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
             py::array_t<std::uint8_t> bw({masks->rows, masks->cols});
             std::memcpy(bw.mutable_data(), masks->data.data() + std::size_t(i) * masks->frame_bytes(), masks->frame_bytes());
             using namespace pybind11::literals;
-            next_id = pack.assign_objects_pack.function("bw_frame"_a = bw, "frames_processed"_a = num_processed,
-                                                        "objects_prev"_a = objects_active,
-                                                        "objects_archive"_a = objects_archive, "next_ID"_a = next_id,
-                                                        "kwargs"_a = pack.assign_objects_pack.kwargs)
-                          .cast<int>();
+            if (want_comps) {
+                const int total = highlighter.component_count(i);
+                const int cnt = std::min(total, highlighter.max_components());
+                const cvvp_component *cs = highlighter.components(i);
+                py::array_t<std::int32_t> stats({cnt, 5});
+                py::array_t<double> cents({cnt, 2});
+                py::array_t<std::int32_t> first({cnt, 2});
+                auto st = stats.mutable_unchecked<2>();
+                auto ce = cents.mutable_unchecked<2>();
+                auto fi = first.mutable_unchecked<2>();
+                for (int k = 0; k < cnt; ++k) {
+                    st(k, 0) = cs[k].x0;
+                    st(k, 1) = cs[k].y0;
+                    st(k, 2) = cs[k].x1 - cs[k].x0 + 1;
+                    st(k, 3) = cs[k].y1 - cs[k].y0 + 1;
+                    st(k, 4) = cs[k].area;
+                    ce(k, 0) = double(cs[k].sum_x) / double(cs[k].area);
+                    ce(k, 1) = double(cs[k].sum_y) / double(cs[k].area);
+                    fi(k, 0) = cs[k].first_x;
+                    fi(k, 1) = cs[k].first_y;
+                }
+                py::dict comps;
+                comps["count"] = total;
+                comps["stats"] = stats;
+                comps["centroids"] = cents;
+                comps["first"] = first;
+                if (want_labels) {
+                    py::array_t<std::int32_t> lab({masks->rows, masks->cols});
+                    std::memcpy(lab.mutable_data(), highlighter.labels(i, masks->frame_bytes()),
+                                masks->frame_bytes() * sizeof(std::int32_t));
+                    comps["labels"] = lab;
+                }
+                next_id = pack.assign_objects_pack.function("bw_frame"_a = bw, "frames_processed"_a = num_processed,
+                                                            "objects_prev"_a = objects_active,
+                                                            "objects_archive"_a = objects_archive, "next_ID"_a = next_id,
+                                                            "kwargs"_a = pack.assign_objects_pack.kwargs,
+                                                            "components"_a = comps)
+                              .cast<int>();
+            } else {
+                next_id = pack.assign_objects_pack.function("bw_frame"_a = bw, "frames_processed"_a = num_processed,
+                                                            "objects_prev"_a = objects_active,
+                                                            "objects_archive"_a = objects_archive, "next_ID"_a = next_id,
+                                                            "kwargs"_a = pack.assign_objects_pack.kwargs)
+                              .cast<int>();
+            }
             ++num_processed;
             any = true;
         }

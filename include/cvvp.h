@@ -176,6 +176,35 @@ CVVP_API int cvvp_highlight_frames(cvvp_ctx *ctx, const uint8_t *frames, long lo
 CVVP_API int cvvp_highlight_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride,
                                    uint8_t *d_out, size_t out_stride, void *stream);
 CVVP_API int cvvp_highlight_end(cvvp_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * components of the highlight masks (opt-in) -- the connected-component labelling that feeds the
+ * object tracker.  In the reference this happens on the host inside the user's tracker callback,
+ * which receives only bw_frame (Sources/ProcessorAlgos/assign_objects_algo.h:124-130) and
+ * typically calls cv2.connectedComponentsWithStats(bw_frame, connectivity=8) (cf. the note at
+ * highlight_objects_algo.cpp:152-153).  Here the fused kernel labels the final mask once more and
+ * returns, per frame, its 8-connected components numbered 1.. in the raster order of their first
+ * pixels (the canonical labelling: the same label SETS as OpenCV's, whose numbering depends on
+ * its scan), with the statistics a tracker needs.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cvvp_component {
+    int32_t x0, y0, x1, y1;   /* bounding box, inclusive */
+    int32_t area;             /* pixels */
+    int32_t first_x, first_y; /* raster-first pixel */
+    int32_t reserved;
+    int64_t sum_x, sum_y;     /* coordinate sums: centroid = (sum_x / area, sum_y / area) */
+} cvvp_component;
+/* Like cvvp_highlight_device, plus: d_comps[f * max_comps + k] = component k + 1 of frame f (the first
+ * min(ncomps, max_comps) of them), d_ncomps[f] = number of components of frame f (may exceed max_comps),
+ * d_labels (may be NULL) = int32 label image of frame f at d_labels + f * labels_stride elements
+ * (0 = background).  All DEVICE pointers.  n <= 2^20 frames per call. */
+CVVP_API int cvvp_highlight_device_cc(cvvp_ctx *ctx, const uint8_t *d_frames, long long n, size_t frame_stride,
+                                      uint8_t *d_out, size_t out_stride, cvvp_component *d_comps, int max_comps,
+                                      int *d_ncomps, int32_t *d_labels, size_t labels_stride, void *stream);
+/* HOST-buffer form (synchronous): masks, components, counts and (optionally, NULL = off) label images */
+CVVP_API int cvvp_highlight_frames_cc(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride,
+                                      uint8_t *masks_out, size_t out_stride, cvvp_component *comps_out, int max_comps,
+                                      int *ncomps_out, int32_t *labels_out, size_t labels_stride);
 /* Device implementation used by the calls above (after cvvp_highlight_begin; both give identical masks):
  *   0 = fused (default): one persistent-CTA kernel launch per batch, run-based labelling (csrc/highlight_fused.cu)
  *   1 = per-pixel kernels (csrc/highlight.cu), ~35 launches per batch; kept as an on-device cross-check.

@@ -97,6 +97,43 @@ def test_track_objects_end_to_end(gray_video):
     assert archive == _reference_track(frames[20:35], p, kwargs)
 
 
+def _tracker_with_components(bw_frame, frames_processed, objects_prev, objects_archive, next_ID, kwargs, components):
+    """the same tracker fed by the device's components (kwargs["cvvp_components"] = True) instead of a host CCL; it
+    also checks them against cv2 on the mask it was handed"""
+    n, lab, stats, cent = cv2.connectedComponentsWithStats(bw_frame, connectivity=8)
+    assert components["count"] == n - 1 == len(components["stats"])
+    if "labels" in components:
+        pairs = np.unique(np.stack([components["labels"].ravel(), lab.ravel()], axis=1), axis=0)
+        assert len(pairs[pairs[:, 0] != 0]) == n - 1 and not np.any((pairs[:, 0] == 0) != (pairs[:, 1] == 0))  # same partition
+    objects_prev.clear()
+    for k in range(components["count"]):
+        x, y, w, h, area = (int(v) for v in components["stats"][k])
+        if area < kwargs["min_area"]:
+            continue
+        cx, cy = components["centroids"][k]
+        objects_prev[next_ID] = (frames_processed, area)
+        objects_archive[next_ID] = {"frame": frames_processed, "area": area, "cx": round(float(cx), 3), "cy": round(float(cy), 3)}
+        next_ID += 1
+    return next_ID
+
+
+def test_track_objects_with_device_components(gray_video):
+    """opt-in: the device labels the masks; cv2 numbers components in its own scan order, so the archives are compared
+    as sets of per-frame records"""
+    path, frames = gray_video
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+    p = ho.canonical_params(bg)
+    hp = cvp.HighlightObjectsPack(bg, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                                  p.min_size_threshold, p.width_border)
+    want = _reference_track(frames, p, {"min_area": 5})
+    for extra in ({}, {"cvvp_labels": True}):
+        kwargs = {"min_area": 5, "cvvp_components": True, **extra}
+        archive = cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(_tracker_with_components, kwargs),
+                                                          vid_is_grayscale=True))
+        key = lambda d: sorted((v["frame"], v["area"], v["cx"], v["cy"]) for v in d.values())  # noqa: E731
+        assert key(archive) == key(want)
+
+
 def test_track_objects_needs_single_channel(color_video):
     path, frames = color_video
     hp = cvp.HighlightObjectsPack(np.zeros((40, 56), np.uint8), np.ones((2, 2), np.uint8), 1, 1, 1, 1, 1, 1)
