@@ -174,6 +174,24 @@ def test_fused_and_pixel_paths_agree_at_full_hd(gpu_ctx):
         assert np.array_equal(fused[i], ho.highlight_objects(frames[i].copy(), p)), f"frame {i} vs oracle"
 
 
+def test_bubble_video_geometry_many_frames(gpu_ctx):
+    """BASELINE configs[3] geometry: 512x256 frames, several times more frames than the kernel keeps in flight; every
+    frame fused vs per-pixel path, every 17th vs the oracle"""
+    from cvvidproc_b200 import synth
+
+    p_ = synth.CONFIG_PARAMS["C4"]
+    w, h = p_["width"], p_["height"]
+    stack = synth.synth_frames(0, 101, w, h, p_["seed"], p_["ndisks"])
+    bg = gpu_ctx.median(stack)
+    p = ho.canonical_params(bg)
+    frames = synth.synth_frames(500, 700, w, h, p_["seed"], p_["ndisks"])
+    fused = _gpu(gpu_ctx, frames, p, FUSED)
+    pixel = _gpu(gpu_ctx, frames, p, PIXEL)
+    assert np.array_equal(fused, pixel)
+    for i in range(0, 700, 17):
+        assert np.array_equal(fused[i], ho.highlight_objects(frames[i].copy(), p)), f"frame {i} vs oracle"
+
+
 def test_argument_errors(gpu_ctx):
     from cvvidproc_b200 import _cabi
 

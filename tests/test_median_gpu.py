@@ -168,6 +168,16 @@ def test_device_resident_full_size_property(gpu_ctx):
     assert torch.equal(out, out2)
 
 
+def test_uhd_geometry_matches_oracle(gpu_ctx, oracle_median):
+    """BASELINE configs[4] geometry (3840x2160) at a reduced frame count: full compare against the oracle"""
+    from cvvidproc_b200 import synth
+
+    p = synth.CONFIG_PARAMS["C5"]
+    frames = synth.synth_frames(0, 41, p["width"], p["height"], p["seed"], p["ndisks"])
+    got = gpu_ctx.median(frames, chunk=8)
+    assert np.array_equal(got, oracle_median(frames, nthreads=8))
+
+
 def test_too_many_frames_is_a_loud_error(gpu_ctx):
     """65535 frames is the limit of the two-pass path's 16-bit counts; beyond it the call fails, it does not guess"""
     import torch
