@@ -55,4 +55,48 @@ __device__ __forceinline__ void transpose32(uint32_t (&r)[32])
         r[i + 1] = bitsel(a >> 1, b, 0x55555555u);
     }
 }
+
+// High nibbles only: afterwards r[8p + 4 .. 8p + 7] hold bit planes 4..7 of element p (the other entries are
+// scratch).  The byte stages are the same as in transpose32; from the 4-bit stage on only the half of every pair that
+// carries the high nibbles is computed (160 instead of 256 instructions).  Used by the counting round that needs the
+// high nibble alone (median_pipe_kernel MODE 1).
+__device__ __forceinline__ void transpose32_hi(uint32_t (&r)[32])
+{
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t a = r[i], b = r[i + 16];
+        r[i] = __byte_perm(a, b, 0x5410);
+        r[i + 16] = __byte_perm(a, b, 0x7632);
+    }
+#pragma unroll
+    for (int h = 0; h < 32; h += 16) {
+#pragma unroll
+        for (int i = h; i < h + 8; ++i) {
+            const uint32_t a = r[i], b = r[i + 8];
+            r[i] = __byte_perm(a, b, 0x6240);
+            r[i + 8] = __byte_perm(a, b, 0x7351);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 32; h += 8) {
+#pragma unroll
+        for (int i = h; i < h + 4; ++i)
+            r[i + 4] = bitsel(r[i] >> 4, r[i + 4], 0x0F0F0F0Fu); // high nibbles of the pair
+    }
+#pragma unroll
+    for (int h = 4; h < 32; h += 8) { // the high-nibble half of every block of eight
+#pragma unroll
+        for (int i = h; i < h + 2; ++i) {
+            const uint32_t a = r[i], b = r[i + 2];
+            r[i] = bitsel(a, b << 2, 0x33333333u);
+            r[i + 2] = bitsel(a >> 2, b, 0x33333333u);
+        }
+#pragma unroll
+        for (int i = h; i < h + 4; i += 2) {
+            const uint32_t a = r[i], b = r[i + 1];
+            r[i] = bitsel(a, b << 1, 0x55555555u);
+            r[i + 1] = bitsel(a >> 1, b, 0x55555555u);
+        }
+    }
+}
 } // namespace cvvp

@@ -169,7 +169,10 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
             if (lane == 0 && gs + 2 * kTrWarps < total_stages)
                 issue(k, ti2, st2);
             advance(ti2, st2);
-            transpose32(r);
+            if (MODE == 1)
+                transpose32_hi(r); // the high-nibble round needs planes 4..7 only
+            else
+                transpose32(r);
             // r[8*p + b] = bit plane b of element 4*c+p over this lane's 32 frame slots.
             // Selectors must be done with the previous fill of this buffer.  Pre-check (almost always already
             // true): the fill before that one is finished, which makes the parity wait at most one phase away.
@@ -182,7 +185,8 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
             uint4 *dst = reinterpret_cast<uint4 *>(planes + buf * kBufWords + st * 1024u) + col;
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-                dst[(p * 2 + 0) * 32] = make_uint4(r[8 * p + 0], r[8 * p + 1], r[8 * p + 2], r[8 * p + 3]);
+                if (MODE != 1)
+                    dst[(p * 2 + 0) * 32] = make_uint4(r[8 * p + 0], r[8 * p + 1], r[8 * p + 2], r[8 * p + 3]);
                 dst[(p * 2 + 1) * 32] = make_uint4(r[8 * p + 4], r[8 * p + 5], r[8 * p + 6], r[8 * p + 7]);
             }
             __syncwarp();
