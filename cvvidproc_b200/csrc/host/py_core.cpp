@@ -13,10 +13,12 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <chrono>
 #include <cstdint>
 #include <iostream>
 #include <limits>
 #include <memory>
+#include <sstream>
 #include <string>
 
 #include "gpu_algos.hpp"
@@ -143,6 +145,40 @@ void array_geometry(const py::array &a, int &rows, int &cols, int &channels)
     channels = a.ndim() == 3 ? int(a.shape(2)) : 1;
 }
 
+// print_timing_report: the reference's report lines (AsyncTokenProcess::GetTimingInfoAndResetTimer,
+// Sources/AsyncTokens/async_token_process.h:273-414; whole milliseconds like its default TimingReportUnitT).  The
+// roles map as: batch generator = the decode loop, unit [1] = the device operator's Insert, consumer = result hand-off.
+struct IntervalTimer {
+    std::chrono::steady_clock::duration total{};
+    long long count{0};
+    std::chrono::steady_clock::time_point t0{};
+    void start() { t0 = std::chrono::steady_clock::now(); }
+    void stop()
+    {
+        total += std::chrono::steady_clock::now() - t0;
+        ++count;
+    }
+    long long ms() const { return std::chrono::duration_cast<std::chrono::milliseconds>(total).count(); }
+    long long avg_ms() const { return count ? std::chrono::duration_cast<std::chrono::milliseconds>(total / count).count() : 0; }
+};
+
+std::string timing_report(const IntervalTimer &batches, const IntervalTimer &gen, const IntervalTimer &consume,
+                          const IntervalTimer &unit)
+{
+    if (!batches.count)
+        return "";
+    std::ostringstream ss;
+    ss << "Batch loading: " << batches.ms() << " ms (" << batches.count << " batches; " << batches.avg_ms()
+       << " ms avg) on time between each generated batch\n";
+    ss << "Batch gen: " << gen.ms() << " ms (" << gen.count << " batches; " << gen.avg_ms() << " ms avg) on generating batches\n";
+    ss << "Result consume: " << consume.ms() << " ms (" << consume.count << " tokens; " << consume.avg_ms()
+       << " ms avg) on handling results\n";
+    if (unit.count)
+        ss << "Unit [1]: " << unit.ms() << " ms (" << unit.count << " tokens; " << unit.avg_ms()
+           << " ms avg) on ingesting tokens in workers\n";
+    return ss.str();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // GetVideoBackground  (cv_vid_bg_helpers.cpp:197-264)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -186,17 +222,26 @@ py::object GetVideoBackground(const VidBgPack &pack)
     GpuMedianAlgo algo{GpuMedianPack{-1, frames_to_analyze}};
     long long consumed = 0;
     int rows = 0, cols = 0, channels = 1;
+    IntervalTimer t_batch, t_gen, t_unit, t_consume;
     while (consumed < frames_to_analyze) { // generator :128-135
+        t_batch.start();
+        t_gen.start();
         py::object f = vid.next();
+        t_gen.stop();
         if (f.is_none())
             break;
         py::array a = f.cast<py::array>();
         array_geometry(a, rows, cols, channels);
+        t_unit.start();
         algo.InsertRaw(static_cast<const std::uint8_t *>(a.data()), 1, rows, cols, channels, std::size_t(rows) * cols * channels);
+        t_unit.stop();
+        t_batch.stop();
         ++consumed;
     }
+    t_consume.start();
     algo.NotifyNoMoreTokens();
     std::unique_ptr<FrameBatch> res = algo.TryGetResult();
+    t_consume.stop();
     if (!res || res->empty())
         return py::none();
     // shape (H, W) for one channel, (H, W, C) otherwise (ndarray_converter.cpp:141-142)
@@ -205,8 +250,8 @@ py::object GetVideoBackground(const VidBgPack &pack)
         shape.push_back(res->channels);
     py::array_t<std::uint8_t> out(shape);
     std::memcpy(out.mutable_data(), res->data.data(), res->data.size());
-    if (pack.print_timing_report)
-        std::cout << "Background: " << consumed << " frames consumed by the device median\n";
+    if (pack.print_timing_report) // cv_vid_bg_helpers.cpp:154-155
+        std::cout << timing_report(t_batch, t_gen, t_consume, t_unit);
     return std::move(out);
 }
 
@@ -296,7 +341,10 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
 
     long long consumed = 0;
     bool eof = false;
+    IntervalTimer h_batch, h_gen, h_unit, h_consume, a_batch, a_gen, a_unit, a_consume;
     while (!eof && consumed < num_frames) {
+        h_batch.start();
+        h_gen.start();
         auto batch = std::make_unique<FrameBatch>();
         batch->rows = crop.height;
         batch->cols = crop.width;
@@ -318,15 +366,25 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
             batch->n++;
             ++consumed;
         }
+        h_gen.stop();
         if (batch->n == 0)
             break;
+        h_unit.start();
         highlighter.Insert(std::move(batch));
+        h_unit.stop();
+        h_consume.start();
         std::unique_ptr<FrameBatch> masks = highlighter.TryGetResult();
+        h_consume.stop();
+        h_batch.stop();
+        a_batch.start();
+        a_gen.start(); // the intermediary hands the ordered masks over (mat_set_intermediary.h:84-114)
+        a_gen.stop();
         // strictly in frame order, one call per frame (assign_objects_algo.h:111-133)
         for (int i = 0; i < masks->n; ++i) {
             py::array_t<std::uint8_t> bw({masks->rows, masks->cols});
             std::memcpy(bw.mutable_data(), masks->data.data() + std::size_t(i) * masks->frame_bytes(), masks->frame_bytes());
             using namespace pybind11::literals;
+            a_unit.start();
             if (want_comps) {
                 const int total = highlighter.component_count(i);
                 const int cnt = std::min(total, highlighter.max_components());
@@ -372,12 +430,18 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
                                                             "kwargs"_a = pack.assign_objects_pack.kwargs)
                               .cast<int>();
             }
+            a_unit.stop();
             ++num_processed;
             any = true;
         }
+        a_batch.stop();
     }
-    if (pack.print_timing_report)
-        std::cout << "TrackObjects: " << num_processed << " frames highlighted on the device and assigned on the host\n";
+    a_consume.start();
+    a_consume.stop();
+    if (pack.print_timing_report) { // cv_vid_objecttrack_helpers.cpp:136-143
+        std::cout << "Highlight objects timing report:\n" << timing_report(h_batch, h_gen, h_consume, h_unit);
+        std::cout << "Assign objects timing report:\n" << timing_report(a_batch, a_gen, a_consume, a_unit);
+    }
     if (!any)
         return py::dict{};
     return objects_archive;

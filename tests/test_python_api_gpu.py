@@ -134,6 +134,29 @@ def test_track_objects_with_device_components(gray_video):
         assert key(archive) == key(want)
 
 
+def test_timing_reports_follow_the_reference_format(gray_video, capfd):
+    """print_timing_report: the report lines of AsyncTokenProcess::GetTimingInfoAndResetTimer
+    (async_token_process.h:273-414) and the two headings of cv_vid_objecttrack_helpers.cpp:136-143"""
+    import re
+
+    path, frames = gray_video
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True, print_timing_report=True))
+    out = capfd.readouterr().out
+    num = r"\d+ ms \(\d+ (batches|tokens); \d+ ms avg\)"
+    for head, tail in (("Batch loading", "on time between each generated batch"), ("Batch gen", "on generating batches"),
+                       ("Result consume", "on handling results"), (r"Unit \[1\]", "on ingesting tokens in workers")):
+        assert re.search(rf"^{head}: {num} {tail}$", out, re.M), (head, out)
+    assert "(60 batches;" in out and "(60 tokens;" in out
+    p = ho.canonical_params(bg)
+    hp = cvp.HighlightObjectsPack(bg, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                                  p.min_size_threshold, p.width_border)
+    cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(_tracker, {"min_area": 5}), vid_is_grayscale=True,
+                                            print_timing_report=True))
+    out = capfd.readouterr().out
+    assert out.index("Highlight objects timing report:") < out.index("Assign objects timing report:")
+    assert len(re.findall(r"^Unit \[1\]: ", out, re.M)) == 2 and "(60 tokens;" in out
+
+
 def test_track_objects_needs_single_channel(color_video):
     path, frames = color_video
     hp = cvp.HighlightObjectsPack(np.zeros((40, 56), np.uint8), np.ones((2, 2), np.uint8), 1, 1, 1, 1, 1, 1)
