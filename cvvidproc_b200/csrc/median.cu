@@ -34,7 +34,7 @@ int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, siz
         return fail(ctx, CVVP_ERR_INVALID, "median: null output pointer");
     // Up to 2048 frames the on-chip select reads every byte once at 128- or 64-byte tiles.  Longer stacks would need
     // 32- / 16-byte tiles (1.5 TB/s and less): two counting passes in chunks of 1024 frames at full tile width are
-    // faster there, and reach 65535 frames (median_shard.cu).  CVVP_MEDIAN_TWO_PASS=0/1 forces either path (tests).
+    // faster there, and reach 16 x 65535 frames (median_shard.cu).  CVVP_MEDIAN_TWO_PASS=0/1 forces either path (tests).
     const char *force = getenv("CVVP_MEDIAN_TWO_PASS");
     const bool two_pass = force ? force[0] == '1' : nframes > 2048;
     if (two_pass || nframes > median_max_frames()) {

@@ -27,6 +27,7 @@
 // passes over the frames stay at HBM speed.
 #include "context.hpp"
 
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -43,17 +44,20 @@ struct MedianShard {
     bool ipc_opened[kMaxShardRanks]{};
     bool attached[kMaxShardRanks]{};
     uint32_t *accum{nullptr}; // [nelem][8 words]: running counts of this rank's frame chunks (allocated on first use)
+    int spr{1}; // count slots per rank: a rank with more than 65535 frames pushes one 16-bit count vector per 65535 frames,
+                // the owners sum world * spr vectors in 32 bits (world * spr <= kMaxShardRanks)
 };
 
 // frames one launch of the counting kernel takes at full tile width (128-byte TMA boxes): 32 stages x 32 frames
 constexpr long long kChunkFrames = 1024;
-constexpr long long kMaxRankFrames = 65535; // 16-bit counts per rank
+constexpr long long kSlotFrames = 65535; // 16-bit counts per slot
 
 namespace
 {
 struct OwnerArgs {
-    const uint32_t *counts; // this rank's receive area of the round: [world][slice][8 words]
+    const uint32_t *counts; // this rank's receive area of the round: [world (count vectors)][slice][8 words]
     uint32_t slice, world, rank;
+    uint32_t nranks;        // ranks the decisions are broadcast to
     uint32_t owned;         // elements this rank owns
     uint32_t *sel[kMaxShardRanks];    // every rank's sel array
     uint8_t *result[kMaxShardRanks];  // every rank's result image
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(256) shard_pick_kernel(const __grid_constant__
             below = total - cnt[15]; // unreachable with exact counts; mirrors the reference's default bin
         const uint32_t v = h | ((k - below) << 8);
         const size_t e = size_t(A.rank) * A.slice + i;
-        for (uint32_t r = 0; r < A.world; ++r)
+        for (uint32_t r = 0; r < A.nranks; ++r)
             A.sel[r][e] = v;
     }
     __threadfence_system();
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(256) shard_final_kernel(const __grid_constant_
             }
             packed |= ((h << 4) | l) << (8u * q);
         }
-        for (uint32_t r = 0; r < A.world; ++r) {
+        for (uint32_t r = 0; r < A.nranks; ++r) {
             uint8_t *dst = A.result[r] + e0;
             if (n == 4u) {
                 *reinterpret_cast<uint32_t *>(dst) = packed; // e0 is a multiple of 4 (slice % 128 == 0)
@@ -200,16 +204,17 @@ void median_shard_release(cvvp_ctx *ctx)
     shard_destroy(ctx, ctx->big);
 }
 
-static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, MedianShard **out)
+static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, int spr, MedianShard **out)
 {
     MedianShard *sh = new (std::nothrow) MedianShard();
     if (!sh)
         return fail(ctx, CVVP_ERR_NOMEM, "out of host memory");
     sh->rank = rank;
     sh->world = world;
+    sh->spr = spr;
     sh->nelem = nelem;
     sh->slice = uint32_t(round_up((nelem + size_t(world) - 1) / size_t(world), 128));
-    const size_t counts_bytes = size_t(world) * sh->slice * 32u;
+    const size_t counts_bytes = size_t(world) * size_t(spr) * sh->slice * 32u;
     sh->off_c1 = 0;
     sh->off_c2 = counts_bytes;
     sh->off_sel = 2 * counts_bytes;
@@ -232,6 +237,48 @@ static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, Median
     return CVVP_OK;
 }
 
+// counting round (phase 0 or 2) of the frames of ONE count slot (at most 65535)
+static int shard_count_slot(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t *d_frames, long long nframes,
+                            size_t frame_stride, const ShardPush &push, cudaStream_t s)
+{
+    if (nframes == 0) {
+        const size_t n = sh->nelem * 2;
+        shard_zero_push_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(push, uint32_t(sh->nelem));
+        CVVP_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches++;
+        return CVVP_OK;
+    }
+    if (nframes <= kChunkFrames)
+        return median_launch_mode(ctx, d_frames, nframes, sh->nelem, frame_stride, nullptr, phase == 0 ? 1 : 2, push, s);
+    // long chunk of frames: several launches at full tile width; the counts of launch c are added to those of
+    // launches < c in a local array, the last launch pushes the totals to the owners
+    if (!sh->accum && cudaMalloc(reinterpret_cast<void **>(&sh->accum), sh->nelem * 32u) != cudaSuccess) {
+        cudaGetLastError();
+        sh->accum = nullptr;
+        return fail(ctx, CVVP_ERR_NOMEM, "median shard: cudaMalloc of %zu bytes for the running counts failed", sh->nelem * 32u);
+    }
+    const long long nchunks = (nframes + kChunkFrames - 1) / kChunkFrames;
+    long long per = (nframes + nchunks - 1) / nchunks;
+    per = (per + 31) / 32 * 32; // whole plane words
+    if (per > kChunkFrames)
+        per = kChunkFrames;
+    for (long long first = 0, c = 0; first < nframes; first += per, ++c) {
+        const long long n = nframes - first < per ? nframes - first : per;
+        const bool last = first + n >= nframes;
+        ShardPush cp = push;
+        cp.accum = c == 0 ? nullptr : sh->accum;
+        if (!last) { // every element "belongs" to slot 0 = the local running counts
+            cp.dst[0] = sh->accum;
+            cp.slice = 0x80000000u;
+        }
+        const int rc = median_launch_mode(ctx, d_frames + size_t(first) * frame_stride, n, sh->nelem, frame_stride, nullptr,
+                                          phase == 0 ? 1 : 2, cp, s);
+        if (rc != CVVP_OK)
+            return rc;
+    }
+    return CVVP_OK;
+}
+
 // One phase of a sharded job (see the file header).  d_result: where phase 3 stores this rank's copy of the result
 // bytes instead of its own exchange buffer (the one-rank two-pass path writes straight into the caller's image).
 static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t *d_frames, long long nframes,
@@ -241,49 +288,22 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
         return fail(ctx, CVVP_ERR_STATE, "median shard: not every peer buffer is mapped (import / attach all ranks first)");
     if (nframes < 0)
         return fail(ctx, CVVP_ERR_INVALID, "median shard: negative frame count");
-    if (nframes > kMaxRankFrames)
-        return fail(ctx, CVVP_ERR_UNSUPPORTED, "median shard: %lld frames on one rank exceed the 16-bit counts (%lld)", nframes,
-                    kMaxRankFrames);
+    if (nframes > kSlotFrames * sh->spr)
+        return fail(ctx, CVVP_ERR_UNSUPPORTED, "median shard: %lld frames on one rank exceed the %d x 16-bit counts (%lld)",
+                    nframes, sh->spr, kSlotFrames * sh->spr);
     if (phase == 0 || phase == 2) {
-        ShardPush push{};
-        const size_t off = (phase == 0 ? sh->off_c1 : sh->off_c2) + size_t(sh->rank) * sh->slice * 32u;
-        for (int r = 0; r < sh->world; ++r)
-            push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
-        push.sel = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_sel);
-        push.slice = sh->slice;
-        if (nframes == 0) {
-            const size_t n = sh->nelem * 2;
-            shard_zero_push_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(push, uint32_t(sh->nelem));
-            CVVP_CUDA_OK(ctx, cudaGetLastError());
-            ctx->launches++;
-            return CVVP_OK;
-        }
-        if (nframes <= kChunkFrames)
-            return median_launch_mode(ctx, d_frames, nframes, sh->nelem, frame_stride, nullptr, phase == 0 ? 1 : 2, push, s);
-        // long chunk of frames: several launches at full tile width; the counts of launch c are added to those of
-        // launches < c in a local array, the last launch pushes the totals to the owners
-        if (!sh->accum && cudaMalloc(reinterpret_cast<void **>(&sh->accum), sh->nelem * 32u) != cudaSuccess) {
-            cudaGetLastError();
-            sh->accum = nullptr;
-            return fail(ctx, CVVP_ERR_NOMEM, "median shard: cudaMalloc of %zu bytes for the running counts failed",
-                        sh->nelem * 32u);
-        }
-        const long long nchunks = (nframes + kChunkFrames - 1) / kChunkFrames;
-        long long per = (nframes + nchunks - 1) / nchunks;
-        per = (per + 31) / 32 * 32; // whole plane words
-        if (per > kChunkFrames)
-            per = kChunkFrames;
-        for (long long first = 0, c = 0; first < nframes; first += per, ++c) {
-            const long long n = nframes - first < per ? nframes - first : per;
-            const bool last = first + n >= nframes;
-            ShardPush cp = push;
-            cp.accum = c == 0 ? nullptr : sh->accum;
-            if (!last) { // every element "belongs" to slot 0 = the local running counts
-                cp.dst[0] = sh->accum;
-                cp.slice = 0x80000000u;
-            }
-            const int rc = median_launch_mode(ctx, d_frames + size_t(first) * frame_stride, n, sh->nelem, frame_stride, nullptr,
-                                              phase == 0 ? 1 : 2, cp, s);
+        // slot j of this rank takes frames [j * 65535, (j + 1) * 65535) (possibly none)
+        for (int j = 0; j < sh->spr; ++j) {
+            const long long f0 = std::min<long long>(nframes, kSlotFrames * j);
+            const long long nf = std::min<long long>(nframes - f0, kSlotFrames);
+            ShardPush push{};
+            const size_t off =
+                (phase == 0 ? sh->off_c1 : sh->off_c2) + (size_t(sh->rank) * sh->spr + size_t(j)) * sh->slice * 32u;
+            for (int r = 0; r < sh->world; ++r)
+                push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
+            push.sel = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_sel);
+            push.slice = sh->slice;
+            const int rc = shard_count_slot(ctx, sh, phase, d_frames + size_t(f0) * frame_stride, nf, frame_stride, push, s);
             if (rc != CVVP_OK)
                 return rc;
         }
@@ -293,8 +313,9 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
         OwnerArgs A{};
         A.counts = reinterpret_cast<const uint32_t *>(sh->buf + (phase == 1 ? sh->off_c1 : sh->off_c2));
         A.slice = sh->slice;
-        A.world = uint32_t(sh->world);
+        A.world = uint32_t(sh->world * sh->spr); // count vectors to sum
         A.rank = uint32_t(sh->rank);
+        A.nranks = uint32_t(sh->world);
         const size_t first = size_t(sh->rank) * sh->slice;
         A.owned = first >= sh->nelem ? 0u : uint32_t(sh->nelem - first < sh->slice ? sh->nelem - first : sh->slice);
         for (int r = 0; r < sh->world; ++r) {
@@ -318,7 +339,7 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
 
 long long median_two_pass_max_frames()
 {
-    return kMaxRankFrames;
+    return kSlotFrames * kMaxShardRanks;
 }
 
 // Single-GPU median of a stack too long for the on-chip select at full tile width: the sharded job with ONE rank.
@@ -327,10 +348,11 @@ long long median_two_pass_max_frames()
 int median_two_pass(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
                     uint8_t *d_out, cudaStream_t stream)
 {
-    if (ctx->big && ctx->big->nelem != nelem)
+    const int spr = int((nframes + kSlotFrames - 1) / kSlotFrames);
+    if (ctx->big && (ctx->big->nelem != nelem || ctx->big->spr < spr))
         shard_destroy(ctx, ctx->big);
     if (!ctx->big) {
-        const int rc = shard_create(ctx, nelem, 0, 1, &ctx->big);
+        const int rc = shard_create(ctx, nelem, 0, 1, spr, &ctx->big);
         if (rc != CVVP_OK)
             return rc;
     }
@@ -361,7 +383,7 @@ int cvvp_median_shard_begin(cvvp_ctx *ctx, size_t nelem, int rank, int world)
         return fail(ctx, CVVP_ERR_INVALID, "median shard: rank %d / world %d out of range (world <= %d)", rank, world,
                     kMaxShardRanks);
     DeviceGuard guard(ctx->device);
-    return shard_create(ctx, nelem, rank, world, &ctx->shard);
+    return shard_create(ctx, nelem, rank, world, 1, &ctx->shard);
 }
 
 int cvvp_median_shard_export(cvvp_ctx *ctx, void *handle_out)

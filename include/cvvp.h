@@ -106,9 +106,9 @@ CVVP_API int cvvp_median_abort(cvvp_ctx *ctx);
  * tensor-map constraints), d_out a DEVICE pointer to nelem bytes (4-byte aligned).  Runs on
  * `stream` (a cudaStream_t, NULL = the context's compute stream) and does not synchronize.
  * Up to 2048 frames the select happens on chip in one pass over the frames; longer stacks (up to
- * 65535 frames; more fails with CVVP_ERR_UNSUPPORTED) take two counting passes in chunks of 1024
- * frames -- the reference's analogue of widening its histogram bins with the frame count
- * (cv_vid_bg_helpers.cpp:232-253). */
+ * 16 x 65535 = 1048560 frames; more fails with CVVP_ERR_UNSUPPORTED) take two counting passes in
+ * chunks of 1024 frames, 16-bit counts per 65535 frames summed in 32 bits -- the reference's
+ * analogue of widening its histogram bins with the frame count (cv_vid_bg_helpers.cpp:232-253). */
 CVVP_API int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem,
                        size_t frame_stride, uint8_t *d_out, void *stream);
 
@@ -142,7 +142,7 @@ CVVP_API int cvvp_median_shard_import(cvvp_ctx *ctx, int peer_rank, const void *
 /* same-process peer (several contexts in one process, on one or several devices) */
 CVVP_API int cvvp_median_shard_attach(cvvp_ctx *ctx, int peer_rank, cvvp_ctx *peer_ctx);
 /* phases 0 and 2 read this rank's frames (device pointer, same layout rules as cvvp_median_device;
- * nframes may be 0, and may differ between ranks); phases 1 and 3 ignore the frame arguments.
+ * nframes may be 0, may differ between ranks, at most 65535 per rank); phases 1 and 3 ignore the frame arguments.
  * Runs on `stream` (NULL = the context's compute stream) and does not synchronize. */
 CVVP_API int cvvp_median_shard_phase(cvvp_ctx *ctx, int phase, const uint8_t *d_frames, long long nframes,
                                      size_t frame_stride, void *stream);

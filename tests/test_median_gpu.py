@@ -179,11 +179,12 @@ def test_uhd_geometry_matches_oracle(gpu_ctx, oracle_median):
 
 
 def test_too_many_frames_is_a_loud_error(gpu_ctx):
-    """65535 frames is the limit of the two-pass path's 16-bit counts; beyond it the call fails, it does not guess"""
+    """16 x 65535 frames is the limit of the two-pass path (16 slots of 16-bit counts, summed in 32 bits); beyond it
+    the call fails, it does not guess"""
     import torch
     from cvvidproc_b200 import _cabi
 
-    n, nelem = 65536, 16
+    n, nelem = 16 * 65535 + 1, 16
     stack = torch.zeros((n, nelem), dtype=torch.uint8, device="cuda:0")
     out = torch.zeros(nelem, dtype=torch.uint8, device="cuda:0")
     with pytest.raises(_cabi.CvvpError) as ei:
@@ -191,7 +192,7 @@ def test_too_many_frames_is_a_loud_error(gpu_ctx):
     assert ei.value.code == -5
 
 
-@pytest.mark.parametrize("n", [2049, 3000, 5000, 8193, 10000, 20001, 65535])
+@pytest.mark.parametrize("n", [2049, 3000, 5000, 8193, 10000, 20001, 65535, 65536, 70001, 140000])
 def test_long_stacks_take_the_two_pass_path(gpu_ctx, oracle_median, n):
     """more than 2048 frames: two counting passes in chunks of <= 1024 frames (csrc/median_shard.cu, one rank)"""
     rng = np.random.default_rng(n)
