@@ -47,6 +47,7 @@ struct ShardPush {
     const uint32_t *sel;   // round 2: per element, the globally selected high nibble in bits 0..3
     const uint32_t *accum; // counts of this rank's earlier frame chunks (8 words per element), or nullptr
     uint32_t slice;
+    uint32_t stage; // 1: round 1 stages a tile's count vectors in shared memory and stores them 512 B per warp (peer owners)
 };
 struct MedianShard; // median_shard.cu
 } // namespace cvvp

@@ -275,7 +275,44 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
             // the zero-filled pad slots were counted as value 0
             if (MODE == 1 || h == 0u)
                 acc[0] -= nst * kSlotsPerStage - nframes;
-            if ((lane >> kColBits) == 0u && e < nelem) {
+            if (MODE == 1 && LOG2S == 0 && nst >= 2u && push.stage) {
+                // Coalesced push.  A warp's elements lie 16 apart, so storing the vectors directly makes every store
+                // instruction write eight scattered 32-byte pieces -- poor packets for NVLink when the owner is a
+                // peer.  This round never touches the LOW-nibble slots of the plane buffer (the transposers do not
+                // fill them, see MODE 1 above), so the tile's 128 count vectors are staged there (8 chunks of 512 B:
+                // stage k / 4, byte k % 4 of chunk k) and written out as 16 bytes per lane, 512 contiguous bytes per
+                // warp.
+                uint4 *stg = reinterpret_cast<uint4 *>(planes + buf * kBufWords);
+                auto slot = [](uint32_t el, uint32_t half) { return (el >> 6) * 256u + ((el >> 4) & 3u) * 64u + (el & 15u) * 2u + half; };
+                if (G == 4) {
+                    const uint2 v = s_g == 0 ? make_uint2(acc[0], acc[1])
+                                  : s_g == 1 ? make_uint2(acc[2], acc[3])
+                                  : s_g == 2 ? make_uint2(acc[4], acc[5])
+                                             : make_uint2(acc[6], acc[7]);
+                    reinterpret_cast<uint2 *>(stg)[slot(s_elem, s_g >> 1) * 2u + (s_g & 1u)] = v;
+                } else {
+                    stg[slot(s_elem, s_g)] = s_g == 0 ? make_uint4(acc[0], acc[1], acc[2], acc[3]) : make_uint4(acc[4], acc[5], acc[6], acc[7]);
+                }
+                named_bar_sync(1, NSELW * 32);
+                for (uint32_t j = tid; j < 256u; j += NSELW * 32u) { // selector threads are tid 0 .. NSELW*32-1
+                    const uint32_t el = j >> 1, half = j & 1u;
+                    const size_t ee = size_t(tile) * P + el;
+                    if (ee < nelem) {
+                        uint4 v = stg[slot(el, half)];
+                        if (push.accum) {
+                            const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(push.accum + ee * 8u + 4u * half));
+                            v.x += a.x;
+                            v.y += a.y;
+                            v.z += a.z;
+                            v.w += a.w;
+                        }
+                        const uint32_t owner = uint32_t(ee) / push.slice;
+                        uint32_t *dst = push.dst[owner] + (ee - size_t(owner) * push.slice) * 8u + 4u * half;
+                        *reinterpret_cast<uint4 *>(dst) = v;
+                    }
+                }
+                named_bar_sync(1, NSELW * 32); // the staging slots are rewritten for the next tile of this buffer
+            } else if ((lane >> kColBits) == 0u && e < nelem) {
                 const uint32_t owner = uint32_t(e) / push.slice;
                 uint32_t *dst = push.dst[owner] + (size_t(e) - size_t(owner) * push.slice) * 8u;
                 // more than one frame chunk on this rank: add the counts of the chunks before this one (packed u16

@@ -28,6 +28,7 @@
 #include "context.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -303,6 +304,10 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
                 push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
             push.sel = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_sel);
             push.slice = sh->slice;
+            {
+                const char *e = getenv("CVVP_SHARD_STAGE"); // development switch; default: stage when owners are peers
+                push.stage = e ? (e[0] == '1') : (sh->world > 1);
+            }
             const int rc = shard_count_slot(ctx, sh, phase, d_frames + size_t(f0) * frame_stride, nf, frame_stride, push, s);
             if (rc != CVVP_OK)
                 return rc;
