@@ -89,6 +89,26 @@ def test_batch_of_synthetic_frames_and_stats_only(gpu_ctx):
     assert np.array_equal(m2, masks) and np.array_equal(n2, ncomps) and np.array_equal(c2, comps)
 
 
+def test_more_frames_than_the_kernel_keeps_in_flight(gpu_ctx):
+    """several chunks through the host-buffer entry point: every scratch slot and staging buffer is reused"""
+    rng = np.random.default_rng(8)
+    h, w = 48, 96
+    bg = np.full((h, w), 180, np.uint8)
+    n = 700
+    frames = np.repeat(bg[None], n, axis=0)
+    for i in range(n):
+        for _ in range(1 + i % 4):
+            y, x = rng.integers(2, h - 12), rng.integers(2, w - 12)
+            frames[i, y : y + rng.integers(4, 10), x : x + rng.integers(4, 10)] = 90
+    p = ho.HighlightParams(background=bg, struct_element=np.ones((2, 2), np.uint8), threshold=14, threshold_lo=7,
+                           threshold_hi=16, min_size_hyst=4, min_size_threshold=4, width_border=0)
+    masks, comps, ncomps, labels = _run(gpu_ctx, frames, p, max_comps=16)
+    for i in range(0, n, 23):
+        assert np.array_equal(masks[i], ho.highlight_objects(frames[i].copy(), p)), i
+        _check_frame(masks[i], comps[i], int(ncomps[i]), labels[i])
+    assert ncomps.min() >= 1
+
+
 def test_more_components_than_slots(gpu_ctx):
     """ncomps reports every component; the first max_comps get statistics, the label image numbers all of them"""
     h, w = 64, 256
