@@ -314,7 +314,7 @@ def cpu_highlight_rate(frames: np.ndarray, bg: np.ndarray, threads: int, seconds
 def run_highlight_section(ctx, torch, dist, rank, local_rank, world, args, sampler, stream):
     """Frames are sharded over ranks by frame (no collective on the data path: frames are independent,
     highlight_objects_algo.h:82-85); each rank processes frames_per_step frames per step."""
-    from oracle import highlight_oracle as ho
+    from cvvidproc_b200 import synth
 
     w = HL_WORKLOAD
     W, H, nfr = w["width"], w["height"], w["frames_per_step"]
@@ -327,13 +327,13 @@ def run_highlight_section(ctx, torch, dist, rank, local_rank, world, args, sampl
     ctx.synchronize()
     del bgstack
     bg_h = bg.cpu().numpy().reshape(H, W)
-    p = ho.canonical_params(bg_h)
+    cp = synth.CANONICAL_HIGHLIGHT  # the workload's parameters (the oracle is only used by the cpu_baseline leg)
     frames = torch.empty((nfr, npix), dtype=torch.uint8, device=dev)
     masks = torch.empty((nfr, npix), dtype=torch.uint8, device=dev)
     first = 1000 + rank * nfr  # this rank's frames of the stream
     ctx.synth_frames_device(frames.data_ptr(), npix, W, H, first, nfr, w["seed"], w["ndisks"])
-    ctx.highlight_begin(p.background, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
-                        p.min_size_threshold, p.width_border)
+    ctx.highlight_begin(bg_h, synth.canonical_struct_element(), cp["threshold"], cp["threshold_lo"], cp["threshold_hi"],
+                        cp["min_size_hyst"], cp["min_size_threshold"], cp["width_border"])
     steps = max(3, min(args.steps, 10))
 
     def barrier():

@@ -96,3 +96,17 @@ def synth_frames(first_frame: int, nframes: int, width: int, height: int, seed: 
     for i in range(nframes):
         out[i] = synth_frame(first_frame + i, width, height, seed, ndisks, row0, nrows)
     return out
+
+
+# The only highlight parameter set the reference ever uses (Sources/rand_tests.cpp:42-51, :333-342): the benchmark's
+# workload definition.  The structuring element is cv2.getStructuringElement(MORPH_ELLIPSE, (4, 4)) as cv2 4.13 produces
+# it, spelled out so that nothing depends on an OpenCV version's ellipse rasteriser.
+CANONICAL_HIGHLIGHT = dict(
+    struct_element=((0, 0, 1, 0), (1, 1, 1, 1), (1, 1, 1, 1), (1, 1, 1, 1)),
+    threshold=14, threshold_lo=7, threshold_hi=16, min_size_hyst=20, min_size_threshold=20, width_border=5,
+)
+
+
+def canonical_struct_element() -> np.ndarray:
+    return np.array(CANONICAL_HIGHLIGHT["struct_element"], np.uint8)
+

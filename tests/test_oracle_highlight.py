@@ -77,3 +77,27 @@ def test_golden_hashes():
         assert hashlib.sha256(frame.tobytes()).hexdigest() == g["input_sha256"], g["name"]
         out = ho.highlight_objects(frame.copy(), p)
         assert hashlib.sha256(out.tobytes()).hexdigest() == g["output_sha256"], g["name"]
+
+
+def test_workload_parameters_match_the_oracle():
+    """cvvidproc_b200.synth.CANONICAL_HIGHLIGHT (what bench.py's GPU arm uses) == oracle.canonical_params"""
+    from cvvidproc_b200 import synth
+
+    p = ho.canonical_params(np.zeros((4, 4), np.uint8))
+    c = synth.CANONICAL_HIGHLIGHT
+    assert np.array_equal(synth.canonical_struct_element(), p.struct_element)
+    for k in ("threshold", "threshold_lo", "threshold_hi", "min_size_hyst", "min_size_threshold", "width_border"):
+        assert c[k] == getattr(p, k)
+
+
+def test_bench_gpu_arm_does_not_touch_the_oracle():
+    """only the cpu_baseline / reference legs of bench.py may use oracle/ (it is the checker, never the product)"""
+    import ast
+    from pathlib import Path
+
+    tree = ast.parse((Path(__file__).resolve().parent.parent / "bench.py").read_text())
+    allowed = {"cpu_median_fn", "cpu_highlight_rate", "run_reference_arm"}
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        uses = [n for n in ast.walk(fn) if (isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n))
+                or (isinstance(n, ast.Constant) and isinstance(n.value, str) and n.value == "oracle")]
+        assert not uses or fn.name in allowed, fn.name

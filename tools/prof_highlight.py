@@ -10,7 +10,6 @@ import torch
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
 from cvvidproc_b200 import _cabi, synth  # noqa: E402
-from oracle import highlight_oracle as ho  # noqa: E402
 
 
 def main():
@@ -33,12 +32,13 @@ def main():
             ctx.median_device(bgstack.data_ptr(), 255, npix, npix, bg.data_ptr())
             ctx.synchronize()
             del bgstack
-            p = ho.canonical_params(bg.cpu().numpy().reshape(H, W))
+            cp = synth.CANONICAL_HIGHLIGHT
             frames = torch.empty((n, npix), dtype=torch.uint8, device="cuda")
             masks = torch.empty((n, npix), dtype=torch.uint8, device="cuda")
             ctx.synth_frames_device(frames.data_ptr(), npix, W, H, 1000, n, p_["seed"], p_["ndisks"])
-            ctx.highlight_begin(p.background, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi,
-                                p.min_size_hyst, p.min_size_threshold, p.width_border)
+            ctx.highlight_begin(bg.cpu().numpy().reshape(H, W), synth.canonical_struct_element(), cp["threshold"],
+                                cp["threshold_lo"], cp["threshold_hi"], cp["min_size_hyst"], cp["min_size_threshold"],
+                                cp["width_border"])
             os.environ.pop("CVVP_HL_PROF", None)
             for _ in range(2):
                 ctx.highlight_device(frames.data_ptr(), n, npix, masks.data_ptr(), npix)
