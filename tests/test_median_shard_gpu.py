@@ -108,6 +108,21 @@ def test_long_chunks_accumulate_over_launches(oracle_median, world, n):
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("stage", ["0", "1"])
+@pytest.mark.parametrize("world", [1, 3])
+def test_both_push_paths(oracle_median, monkeypatch, stage, world):
+    """counting round 1 stores its count vectors directly (32-byte pieces) or staged through shared memory (512 bytes
+    per warp); the default picks by world size, CVVP_SHARD_STAGE forces either -- both must give the same image"""
+    monkeypatch.setenv("CVVP_SHARD_STAGE", stage)
+    rng = np.random.default_rng(17)
+    for n, nelem in ((40, 1000), (700, 257), (2300, 130)):  # one stage pair / double buffer / several launches
+        frames = rng.integers(0, 256, (n, nelem), dtype=np.uint8)
+        frames[:, 0] = 0
+        want = oracle_median(frames.reshape(n, 1, nelem)).reshape(-1)
+        for got in _sharded_median(_split(frames, world), nelem):
+            assert np.array_equal(got, want), (stage, world, n)
+
+
 def test_two_valued_split_pins_upper_median():
     """exact 50/50 split across ranks: rank 0 holds only the low value, rank 1 only the high one"""
     n = 200
