@@ -80,6 +80,16 @@ def load():
         "cvvp_median_shard_phase": (i32, [vp, i32, vp, i64, sz, vp]),
         "cvvp_median_shard_result": (i32, [vp, C.POINTER(vp)]),
         "cvvp_median_shard_end": (i32, [vp]),
+        "cvvp_frame_format_out_bytes": (sz, [vp]),
+        "cvvp_frames_prepare_device": (i32, [vp, vp, i64, sz, vp, vp, sz, vp]),
+        "cvvp_frames_prepare": (i32, [vp, vp, i64, sz, vp, vp, sz]),
+        "cvvp_median_push_source": (i32, [vp, vp, i64, sz, vp]),
+        "cvvp_highlight_queue_begin": (i32, [vp, i32, i64, vp, i32]),
+        "cvvp_highlight_queue_pending": (i32, [vp]),
+        "cvvp_highlight_submit": (i32, [vp, vp, i64, sz]),
+        "cvvp_highlight_queue_ready": (i32, [vp]),
+        "cvvp_highlight_next": (i32, [vp, vp, sz, C.POINTER(i64), vp, vp]),
+        "cvvp_highlight_queue_end": (i32, [vp]),
     }
     global BOUND_SYMBOLS
     BOUND_SYMBOLS = sorted(sigs)
@@ -89,6 +99,32 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+FRAMES_AS_IS, FRAMES_CHANNEL0, FRAMES_RGB2GRAY = 0, 1, 2
+
+
+class FrameFormat(C.Structure):
+    """struct cvvp_frame_format (include/cvvp.h): geometry of the decoded frames, the resolved crop rectangle and
+    the channel reduction of CvVidFramesGeneratorAlgo::GetTokenSet."""
+
+    _fields_ = [("src_width", C.c_int32), ("src_height", C.c_int32), ("src_channels", C.c_int32),
+                ("crop_x", C.c_int32), ("crop_y", C.c_int32), ("crop_width", C.c_int32), ("crop_height", C.c_int32),
+                ("mode", C.c_int32)]
+
+    @classmethod
+    def of(cls, frame_shape, mode: int, crop=None) -> "FrameFormat":
+        """frame_shape: (H, W) or (H, W, C) of one decoded frame; crop: (x, y, w, h) or None for the whole frame"""
+        h, w = int(frame_shape[0]), int(frame_shape[1])
+        c = int(frame_shape[2]) if len(frame_shape) == 3 else 1
+        x, y, cw, ch = crop if crop is not None else (0, 0, w, h)
+        return cls(w, h, c, x, y, cw, ch, mode)
+
+    @property
+    def out_shape(self):
+        if self.mode == FRAMES_AS_IS and self.src_channels > 1:
+            return (self.crop_height, self.crop_width, self.src_channels)
+        return (self.crop_height, self.crop_width)
 
 
 class PinnedBuffer:
@@ -199,6 +235,33 @@ class Context:
             stride = nelem
         self._check(self._lib.cvvp_median_push(self._h, frames.ctypes.data, n, stride))
         self._keepalive = frames
+
+    def median_push_source(self, frames: np.ndarray, fmt: FrameFormat):
+        """frames: DECODED uint8 frames (n, H, W[, C]); cropped / channel-reduced on the device into the stack"""
+        frames = np.ascontiguousarray(frames)
+        if frames.dtype != np.uint8:
+            raise TypeError("frames must be uint8")
+        n = frames.shape[0]
+        stride = int(np.prod(frames.shape[1:]))
+        self._check(self._lib.cvvp_median_push_source(self._h, frames.ctypes.data, n, stride, C.byref(fmt)))
+        self._keepalive = frames
+
+    def frames_prepare(self, frames: np.ndarray, fmt: FrameFormat) -> np.ndarray:
+        """DECODED uint8 frames (n, H, W[, C]) -> prepared frames (n, crop_h, crop_w[, C]) (host in, host out)"""
+        frames = np.ascontiguousarray(frames)
+        if frames.dtype != np.uint8:
+            raise TypeError("frames must be uint8")
+        n = frames.shape[0]
+        stride = int(np.prod(frames.shape[1:]))
+        out = np.empty((n,) + tuple(fmt.out_shape), np.uint8)
+        ob = int(np.prod(fmt.out_shape))
+        self._check(self._lib.cvvp_frames_prepare(self._h, frames.ctypes.data, n, stride, C.byref(fmt), out.ctypes.data, ob))
+        return out
+
+    def frames_prepare_device(self, d_src: int, n: int, src_stride: int, fmt: FrameFormat, d_dst: int, dst_stride: int,
+                              stream: int = 0):
+        self._check(self._lib.cvvp_frames_prepare_device(self._h, d_src, n, src_stride, C.byref(fmt), d_dst, dst_stride,
+                                                         stream or None))
 
     def median_push_raw(self, ptr: int, n: int, stride: int):
         self._check(self._lib.cvvp_median_push(self._h, ptr, n, stride))
@@ -318,6 +381,47 @@ class Context:
                                                        comps.ctypes.data, max_comps, ncomps.ctypes.data,
                                                        lab.ctypes.data if labels else None, npix))
         return (out, comps, ncomps, lab) if labels else (out, comps, ncomps)
+
+    # asynchronous ordered queue (cvvp_highlight_queue_*): the reference's bounded token queues on streams and events
+    def highlight_queue_begin(self, depth: int, max_batch: int, fmt: FrameFormat | None = None, max_comps: int = 0):
+        self._check(self._lib.cvvp_highlight_queue_begin(self._h, depth, max_batch, C.byref(fmt) if fmt is not None else None,
+                                                         max_comps))
+        self._hq = (max_batch, max_comps)
+
+    def highlight_queue_pending(self) -> int:
+        return int(self._lib.cvvp_highlight_queue_pending(self._h))
+
+    def highlight_submit(self, frames: np.ndarray):
+        """frames: uint8 (n, ...) -- prepared (n, H, W) frames, or decoded frames when the queue has a format"""
+        frames = np.ascontiguousarray(frames)
+        if frames.dtype != np.uint8:
+            raise TypeError("frames must be uint8")
+        n = frames.shape[0]
+        stride = int(np.prod(frames.shape[1:]))
+        self._check(self._lib.cvvp_highlight_submit(self._h, frames.ctypes.data, n, stride))
+
+    def highlight_queue_ready(self) -> bool:
+        rc = self._lib.cvvp_highlight_queue_ready(self._h)
+        if rc < 0:
+            self._check(rc)
+        return rc == 1
+
+    def highlight_next(self):
+        """-> masks (n, H, W) of the oldest pending batch [, comps (n, max_comps), ncomps (n,)]"""
+        max_batch, max_comps = self._hq
+        h, w = self._hl_shape
+        out = np.empty((max_batch, h, w), np.uint8)
+        comps = np.zeros((max_batch, max_comps), self.COMPONENT_DTYPE) if max_comps else None
+        ncomps = np.zeros(max_batch, np.int32) if max_comps else None
+        n = C.c_longlong(0)
+        self._check(self._lib.cvvp_highlight_next(self._h, out.ctypes.data, h * w, C.byref(n),
+                                                  comps.ctypes.data if max_comps else None,
+                                                  ncomps.ctypes.data if max_comps else None))
+        k = int(n.value)
+        return (out[:k], comps[:k], ncomps[:k]) if max_comps else out[:k]
+
+    def highlight_queue_end(self):
+        self._check(self._lib.cvvp_highlight_queue_end(self._h))
 
     def highlight_device(self, d_frames: int, n: int, frame_stride: int, d_out: int, out_stride: int, stream: int = 0):
         self._check(self._lib.cvvp_highlight_device(self._h, d_frames, n, frame_stride, d_out, out_stride, stream or None))

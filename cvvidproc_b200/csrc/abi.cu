@@ -75,6 +75,8 @@ int ensure_stack(cvvp_ctx *ctx, long long frames_needed)
             return fail(ctx, CVVP_ERR_NOMEM, "median: cudaMalloc of %zu bytes for the frame stack failed", bytes);
         }
         if (m.d_stack && m.count > 0) {
+            // frames prepared on the device (cvvp_median_push_source) are written by kernels on the compute stream
+            CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->compute));
             CVVP_CUDA_OK(ctx, cudaMemcpyAsync(fresh, m.d_stack, size_t(m.count) * m.stride, cudaMemcpyDeviceToDevice, ctx->copy));
             CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy));
         }
@@ -209,7 +211,9 @@ void cvvp_ctx_destroy(cvvp_ctx *ctx)
         if (b.host)
             cudaFreeHost(b.host);
     }
+    highlight_queue_release(ctx);
     highlight_release(ctx);
+    raw_stage_release(ctx);
     median_shard_release(ctx);
     if (ctx->med.d_stack)
         cudaFree(ctx->med.d_stack);
@@ -451,12 +455,40 @@ int cvvp_median_finish(cvvp_ctx *ctx, uint8_t *out)
     return rc;
 }
 
+int cvvp_median_push_source(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, const cvvp_frame_format *fmt)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    MedianJob &m = ctx->med;
+    if (!m.active)
+        return fail(ctx, CVVP_ERR_STATE, "median: push without begin");
+    int rc = frames_check_format(ctx, fmt);
+    if (rc != CVVP_OK)
+        return rc;
+    if (frames_out_bytes(*fmt) != m.nelem)
+        return fail(ctx, CVVP_ERR_INVALID, "median: prepared frames have %zu bytes, the job was begun with %zu",
+                    frames_out_bytes(*fmt), m.nelem);
+    if (n == 0)
+        return CVVP_OK;
+    const size_t src_frame = size_t(fmt->src_width) * size_t(fmt->src_height) * size_t(fmt->src_channels);
+    if (!frames || n < 0 || frame_stride < src_frame)
+        return fail(ctx, CVVP_ERR_INVALID, "median: bad push arguments");
+    DeviceGuard guard(ctx->device);
+    if ((rc = ensure_stack(ctx, m.count + n)) != CVVP_OK)
+        return rc;
+    if ((rc = frames_upload_prepare(ctx, frames, n, frame_stride, *fmt, m.d_stack + size_t(m.count) * m.stride, m.stride)) != CVVP_OK)
+        return rc;
+    m.count += n;
+    return CVVP_OK;
+}
+
 int cvvp_median_abort(cvvp_ctx *ctx)
 {
     if (!ctx)
         return fail(nullptr, CVVP_ERR_INVALID, "null context");
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->copy);
+    cudaStreamSynchronize(ctx->compute);
     for (auto &b : ctx->staging)
         b.in_flight = false;
     release_median(ctx);
@@ -496,6 +528,7 @@ int cvvp_highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, in
         return fail(nullptr, CVVP_ERR_INVALID, "null context");
     (void)width_border; // accepted and unused, exactly like the reference (FrameAndFill is dead code, :68-71)
     DeviceGuard guard(ctx->device);
+    highlight_queue_release(ctx);
     return highlight_begin(ctx, background, width, height, struct_element, kw, kh, threshold, threshold_lo, threshold_hi,
                            min_size_hyst, min_size_threshold);
 }
@@ -550,6 +583,7 @@ int cvvp_highlight_end(cvvp_ctx *ctx)
     cudaStreamSynchronize(ctx->copy);
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy_out);
+    highlight_queue_release(ctx);
     highlight_release(ctx);
     return CVVP_OK;
 }
@@ -567,6 +601,97 @@ int cvvp_highlight_frames_in_flight(cvvp_ctx *ctx, int *out_frames)
         return fail(ctx, CVVP_ERR_INVALID, "null argument");
     DeviceGuard guard(ctx->device);
     return highlight_frames_in_flight(ctx, out_frames);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* frame source, asynchronous highlight queue                                                  */
+/* ------------------------------------------------------------------------------------------- */
+
+size_t cvvp_frame_format_out_bytes(const cvvp_frame_format *fmt)
+{
+    return fmt ? frames_out_bytes(*fmt) : 0;
+}
+
+int cvvp_frames_prepare_device(cvvp_ctx *ctx, const uint8_t *d_src, long long n, size_t src_stride, const cvvp_frame_format *fmt,
+                               uint8_t *d_dst, size_t dst_stride, void *stream)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    int rc = frames_check_format(ctx, fmt);
+    if (rc != CVVP_OK)
+        return rc;
+    const size_t src_frame = size_t(fmt->src_width) * size_t(fmt->src_height) * size_t(fmt->src_channels);
+    if (!d_src || !d_dst || n < 0 || src_stride < src_frame || dst_stride < frames_out_bytes(*fmt))
+        return fail(ctx, CVVP_ERR_INVALID, "frames: bad arguments");
+    if (n == 0)
+        return CVVP_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->compute;
+    return frames_prepare_launch(ctx, d_src, n, src_stride, size_t(n - 1) * src_stride + src_frame, *fmt, 0, d_dst, dst_stride, s);
+}
+
+int cvvp_frames_prepare(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, const cvvp_frame_format *fmt,
+                        uint8_t *out, size_t out_stride)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    int rc = frames_check_format(ctx, fmt);
+    if (rc != CVVP_OK)
+        return rc;
+    const size_t src_frame = size_t(fmt->src_width) * size_t(fmt->src_height) * size_t(fmt->src_channels);
+    if (!frames || !out || n < 0 || frame_stride < src_frame || out_stride < frames_out_bytes(*fmt))
+        return fail(ctx, CVVP_ERR_INVALID, "frames: bad arguments");
+    if (n == 0)
+        return CVVP_OK;
+    DeviceGuard guard(ctx->device);
+    return frames_prepare_host(ctx, frames, n, frame_stride, *fmt, out, out_stride);
+}
+
+int cvvp_highlight_queue_begin(cvvp_ctx *ctx, int depth, long long max_batch, const cvvp_frame_format *fmt, int max_comps)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    return highlight_queue_begin(ctx, depth, max_batch, fmt, max_comps);
+}
+
+int cvvp_highlight_queue_pending(const cvvp_ctx *ctx)
+{
+    return ctx ? highlight_queue_pending(ctx) : 0;
+}
+
+int cvvp_highlight_submit(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    return highlight_queue_submit(ctx, frames, n, frame_stride);
+}
+
+int cvvp_highlight_queue_ready(cvvp_ctx *ctx)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    return highlight_queue_ready(ctx);
+}
+
+int cvvp_highlight_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_stride, long long *n_out, cvvp_component *comps_out,
+                        int *ncomps_out)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    return highlight_queue_next(ctx, masks_out, out_stride, n_out, comps_out, ncomps_out);
+}
+
+int cvvp_highlight_queue_end(cvvp_ctx *ctx)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    highlight_queue_release(ctx);
+    return CVVP_OK;
 }
 
 int cvvp_synth_frames_device(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width, int height, int row0,

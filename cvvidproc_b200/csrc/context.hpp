@@ -50,6 +50,19 @@ struct ShardPush {
     uint32_t stage; // 1: round 1 stages a tile's count vectors in shared memory and stores them 512 B per warp (peer owners)
 };
 struct MedianShard; // median_shard.cu
+
+// device staging of decoded frames waiting for the preparation kernel (frames.cu), double-buffered
+struct RawStage {
+    uint8_t *d[2]{nullptr, nullptr};
+    size_t cap{0}; // bytes per half
+    cudaEvent_t up[2]{nullptr, nullptr};       // H2D of this half complete
+    cudaEvent_t consumed[2]{nullptr, nullptr}; // the kernel that read this half is complete
+    bool used[2]{false, false};
+    int next{0};
+    uint8_t *d_out{nullptr}; // result staging of the host-buffer form (cvvp_frames_prepare)
+    size_t out_cap{0};
+};
+struct HighlightQueue; // frame_pipeline.cu
 } // namespace cvvp
 
 struct cvvp_ctx {
@@ -74,6 +87,8 @@ struct cvvp_ctx {
     cvvp::MedianShard *big{nullptr}; // internal one-rank job of the two-pass path for long stacks (median.cu)
     std::vector<cvvp::StagingBuf> staging;
     size_t staging_next{0};
+    cvvp::RawStage raw;
+    cvvp::HighlightQueue *hq{nullptr};
 };
 
 namespace cvvp
@@ -140,6 +155,27 @@ int highlight_set_path(cvvp_ctx *ctx, int path);
 int highlight_frames_in_flight(cvvp_ctx *ctx, int *out_frames);
 int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, uint8_t *masks_out,
                           size_t out_stride);
+// frames.cu
+size_t frames_out_bytes(const cvvp_frame_format &f);
+int frames_check_format(cvvp_ctx *ctx, const cvvp_frame_format *f);
+int frames_prepare_launch(cvvp_ctx *ctx, const uint8_t *d_src, long long n, size_t src_stride, size_t src_bytes,
+                          const cvvp_frame_format &f, int band_row0, uint8_t *d_dst, size_t dst_stride, cudaStream_t stream);
+// frame_pipeline.cu
+void raw_stage_release(cvvp_ctx *ctx);
+int raw_stage_ensure(cvvp_ctx *ctx, size_t bytes_per_half);
+int frames_prepare_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, const cvvp_frame_format &f,
+                        uint8_t *out, size_t out_stride);
+int frames_upload_prepare(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride, const cvvp_frame_format &f,
+                          uint8_t *d_dst, size_t dst_stride);
+void highlight_queue_release(cvvp_ctx *ctx);
+int highlight_queue_begin(cvvp_ctx *ctx, int depth, long long max_batch, const cvvp_frame_format *fmt, int max_comps);
+int highlight_queue_pending(const cvvp_ctx *ctx);
+int highlight_queue_submit(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride);
+int highlight_queue_ready(cvvp_ctx *ctx);
+int highlight_queue_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_stride, long long *n_out, cvvp_component *comps_out,
+                         int *ncomps_out);
+// highlight.cu: geometry of the running job (false: no job)
+bool highlight_geometry(const cvvp_ctx *ctx, int *width, int *height);
 // synth.cu
 int synth_launch(cvvp_ctx *ctx, uint8_t *d_frames, size_t frame_stride, int width, int height, int row0, int nrows,
                  long long first_frame, long long nframes, uint32_t seed, int ndisks, cudaStream_t stream);

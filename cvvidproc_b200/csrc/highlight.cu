@@ -604,6 +604,15 @@ void highlight_release(cvvp_ctx *ctx)
     ctx->hl = nullptr;
 }
 
+bool highlight_geometry(const cvvp_ctx *ctx, int *width, int *height)
+{
+    if (!ctx->hl)
+        return false;
+    *width = ctx->hl->g.W;
+    *height = ctx->hl->g.H;
+    return true;
+}
+
 int highlight_begin(cvvp_ctx *ctx, const uint8_t *background, int width, int height, const uint8_t *selem, int kw, int kh,
                     int threshold, int threshold_lo, int threshold_hi, int min_size_hyst, int min_size_threshold)
 {

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVVP_ABI_VERSION 1
+#define CVVP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CVVP_API __attribute__((visibility("default")))
@@ -213,6 +213,73 @@ CVVP_API int cvvp_highlight_frames_cc(cvvp_ctx *ctx, const uint8_t *frames, long
 CVVP_API int cvvp_highlight_set_path(cvvp_ctx *ctx, int path);
 /* Frames the fused kernel keeps in flight on this device (= resident CTAs; one scratch slot each). */
 CVVP_API int cvvp_highlight_frames_in_flight(cvvp_ctx *ctx, int *out_frames);
+
+/* ---------------------------------------------------------------------------------------------
+ * frame source on the device -- replaces the per-frame host work of CvVidFramesGeneratorAlgo::GetTokenSet
+ *   Sources/ProcessorTokenHandlers/cv_vid_frames_generator_algo.h
+ *     frame = frame(crop_rectangle) :141; cv::extractChannel(frame, 0) :149-151 (vid_is_grayscale);
+ *     cv::cvtColor(COLOR_RGB2GRAY) :152-154 (convert_to_grayscale); the frame as is :155-156
+ * Decoded frames are src_height x src_width x src_channels interleaved bytes (what cv::VideoCapture hands
+ * out).  The crop rectangle is the RESOLVED one (GetCroppedFrameDims, Sources/cv_vid_bg_helpers.cpp:39-60, is
+ * host logic and stays with the caller).  Output frames are crop_height x crop_width x (1 | src_channels)
+ * contiguous bytes.  RGB2GRAY is OpenCV's 8-bit fixed point, y = (c0*9798 + c1*19235 + c2*3735 + 16384) >> 15
+ * with c0 the FIRST channel in memory (the reference converts whatever order the decoder produced), a fourth
+ * channel is ignored.
+ * ------------------------------------------------------------------------------------------- */
+#define CVVP_FRAMES_AS_IS 0    /* crop only; output keeps src_channels */
+#define CVVP_FRAMES_CHANNEL0 1 /* crop + cv::extractChannel(frame, 0) */
+#define CVVP_FRAMES_RGB2GRAY 2 /* crop + cv::cvtColor(frame, COLOR_RGB2GRAY); src_channels 3 or 4 */
+typedef struct cvvp_frame_format {
+    int32_t src_width, src_height, src_channels;
+    int32_t crop_x, crop_y, crop_width, crop_height;
+    int32_t mode;
+} cvvp_frame_format;
+/* bytes of one prepared frame (0 if fmt is NULL) */
+CVVP_API size_t cvvp_frame_format_out_bytes(const cvvp_frame_format *fmt);
+/* device-resident form: n decoded frames at d_src + i*src_stride -> prepared frames at d_dst + i*dst_stride;
+ * runs on `stream` (NULL = the context's compute stream), does not synchronize */
+CVVP_API int cvvp_frames_prepare_device(cvvp_ctx *ctx, const uint8_t *d_src, long long n, size_t src_stride,
+                                        const cvvp_frame_format *fmt, uint8_t *d_dst, size_t dst_stride, void *stream);
+/* HOST-buffer form (synchronous): only the crop's rows of every frame cross the link */
+CVVP_API int cvvp_frames_prepare(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride,
+                                 const cvvp_frame_format *fmt, uint8_t *out, size_t out_stride);
+/* cvvp_median_push for DECODED frames: the crop's rows are uploaded and one kernel crops / reduces them straight
+ * into the device frame stack (the job's nelem must equal cvvp_frame_format_out_bytes(fmt)).  `frames` may be
+ * reused when the call returns. */
+CVVP_API int cvvp_median_push_source(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride,
+                                     const cvvp_frame_format *fmt);
+
+/* ---------------------------------------------------------------------------------------------
+ * highlight, asynchronous ordered form -- replaces the token queues around HighlightObjectsAlgo
+ *   Sources/AsyncTokens/token_queue.h:209-214 (bounded by token_storage_limit),
+ *   Sources/AsyncTokens/token_processing_unit.h:293-307 (Insert / TryGetResult from a worker thread),
+ *   Sources/ProcessorTokenHandlers/mat_set_intermediary.h:50-68,84-114 (results handed on in frame order)
+ * rebuilt on CUDA streams and events: a ring of `depth` batch slots, each with pinned input / output staging;
+ * submit copies the caller's frames into the slot (the caller's buffer is free on return, like a moved token),
+ * queues H2D -> [frame preparation] -> highlight kernel -> D2H on three streams and returns; batches complete
+ * and are returned strictly in submission order.  The host is free to decode the next batch and run the tracker
+ * on the previous one meanwhile.
+ *   cvvp_highlight_begin ... cvvp_highlight_queue_begin, { submit | next }*, cvvp_highlight_queue_end
+ * ------------------------------------------------------------------------------------------- */
+/* depth >= 1 batches in flight, each of at most max_batch frames.  fmt != NULL: submitted frames are DECODED
+ * frames prepared on the device (the prepared geometry must be the background's, one channel); NULL: frames are
+ * already width*height bytes.  max_comps > 0 additionally returns the components of every mask (see below). */
+CVVP_API int cvvp_highlight_queue_begin(cvvp_ctx *ctx, int depth, long long max_batch, const cvvp_frame_format *fmt,
+                                        int max_comps);
+/* batches submitted and not yet returned by cvvp_highlight_next */
+CVVP_API int cvvp_highlight_queue_pending(const cvvp_ctx *ctx);
+/* 1 <= n <= max_batch frames.  CVVP_ERR_STATE when `depth` batches are pending (back-pressure: call
+ * cvvp_highlight_next first). */
+CVVP_API int cvvp_highlight_submit(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride);
+/* 1 if the oldest pending batch is complete, 0 if not (or nothing is pending); never blocks */
+CVVP_API int cvvp_highlight_queue_ready(cvvp_ctx *ctx);
+/* Wait for the oldest pending batch; copy its *n_out masks to masks_out (mask i at masks_out + i*out_stride) and,
+ * when the queue was begun with max_comps > 0 and the pointers are not NULL, its components
+ * (comps_out[i*max_comps + k]) and counts (ncomps_out[i]).  CVVP_ERR_STATE when nothing is pending. */
+CVVP_API int cvvp_highlight_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_stride, long long *n_out,
+                                 cvvp_component *comps_out, int *ncomps_out);
+/* drains and frees the ring (pending results are dropped) */
+CVVP_API int cvvp_highlight_queue_end(cvvp_ctx *ctx);
 
 /* ---------------------------------------------------------------------------------------------
  * synthetic input: deterministic integer-hash frames generated directly in

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_table_covers_header():
     lib = _cabi.load()
-    assert lib.cvvp_abi_version() == 1
+    assert lib.cvvp_abi_version() == 2
     assert set(_cabi.declared_symbols()) <= set(_cabi.BOUND_SYMBOLS)
 
 
