@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -44,6 +45,26 @@ struct FrameBatch {
     std::vector<std::uint8_t> data;
     std::size_t frame_bytes() const { return std::size_t(rows) * cols * channels; }
     bool empty() const { return n == 0 || data.empty(); }
+    // highlight results with the opt-in components: max_comps records and one count per frame, optional label images
+    int max_comps{0};
+    std::vector<cvvp_component> comps;
+    std::vector<int> ncomps;
+    std::vector<std::int32_t> labels;
+    int component_count(int i) const { return ncomps.empty() ? 0 : ncomps[std::size_t(i)]; }
+    const cvvp_component *components(int i) const { return comps.data() + std::size_t(i) * max_comps; }
+    const std::int32_t *label_image(int i) const { return labels.empty() ? nullptr : labels.data() + std::size_t(i) * frame_bytes(); }
+};
+
+// How decoded frames become tokens (CvVidFramesGeneratorAlgo::GetTokenSet,
+// Sources/ProcessorTokenHandlers/cv_vid_frames_generator_algo.h:141-156): crop, then channel 0 / RGB2GRAY / as is.
+// With a SourceFormat the operators take DECODED frames and the device does that work (csrc/frames.cu).
+struct SourceFormat {
+    bool enabled{false};
+    cvvp_frame_format fmt{};
+    int out_rows() const { return fmt.crop_height; }
+    int out_cols() const { return fmt.crop_width; }
+    int out_channels() const { return fmt.mode == CVVP_FRAMES_AS_IS ? fmt.src_channels : 1; }
+    std::size_t src_bytes() const { return std::size_t(fmt.src_width) * fmt.src_height * fmt.src_channels; }
 };
 
 class Context
@@ -74,6 +95,7 @@ private:
 struct GpuMedianPack {
     int device{-1};
     long long frames_hint{-1}; // frames_to_analyze of GetVideoBackground (cv_vid_bg_helpers.cpp:226-229)
+    SourceFormat source{};     // enabled: InsertDecoded takes decoded frames
 };
 
 class GpuMedianAlgo
@@ -115,6 +137,22 @@ public:
                         "all frames must have the geometry of the first one");
         m_ctx.check(cvvp_median_push(m_ctx.get(), frames, n, stride));
     }
+    // decoded frames (rows x cols x channels of the decoder): cropped and channel-reduced on the device
+    void InsertDecoded(const std::uint8_t *frames, long long n, std::size_t stride)
+    {
+        CVVP_ASSERT_MSG(m_pack.source.enabled, "InsertDecoded needs a SourceFormat in the pack");
+        if (!frames || n <= 0)
+            return;
+        const SourceFormat &sf = m_pack.source;
+        if (!m_started) {
+            m_rows = sf.out_rows();
+            m_cols = sf.out_cols();
+            m_channels = sf.out_channels();
+            m_ctx.check(cvvp_median_begin(m_ctx.get(), cvvp_frame_format_out_bytes(&sf.fmt), m_pack.frames_hint));
+            m_started = true;
+        }
+        m_ctx.check(cvvp_median_push_source(m_ctx.get(), frames, n, stride, &sf.fmt));
+    }
     // :101-108 -- end of stream: publish the result once, reset
     void NotifyNoMoreTokens()
     {
@@ -154,6 +192,12 @@ struct GpuHighlightPack { // TokenProcessorPack<HighlightObjectsAlgo> :21-32
     bool components{false};
     bool labels{false};
     int max_components{1024};
+    // queue_depth > 0: tokens are processed asynchronously, at most queue_depth batches in flight (the reference's
+    // token_storage_limit, Sources/AsyncTokens/token_queue.h:209-214) of at most max_batch frames each; results come
+    // back in Insert order (mat_set_intermediary.h:50-68).  queue_depth == 0: Insert is synchronous.
+    int queue_depth{0};
+    long long max_batch{0};
+    SourceFormat source{}; // enabled (queue mode only): tokens are DECODED frames, prepared on the device
 };
 
 class GpuHighlightAlgo
@@ -171,44 +215,101 @@ public:
                                          m_pack.struct_element.cols, m_pack.struct_element.rows, m_pack.threshold,
                                          m_pack.threshold_lo, m_pack.threshold_hi, m_pack.min_size_hyst,
                                          m_pack.min_size_threshold, m_pack.width_border));
+        if (m_pack.labels) // label images only travel through the synchronous entry point
+            m_pack.queue_depth = 0;
+        CVVP_ASSERT_MSG(m_pack.queue_depth > 0 || !m_pack.source.enabled, "decoded-frame tokens need the queue");
+        if (m_pack.queue_depth > 0) {
+            CVVP_ASSERT(m_pack.max_batch > 0);
+            m_ctx.check(cvvp_highlight_queue_begin(m_ctx.get(), m_pack.queue_depth, m_pack.max_batch,
+                                                   m_pack.source.enabled ? &m_pack.source.fmt : nullptr,
+                                                   m_pack.components ? m_pack.max_components : 0));
+        }
     }
     // highlight_objects_algo.h:60-69 -- the token is processed in place and becomes the result
     void Insert(std::unique_ptr<FrameBatch> batch)
     {
         if (!batch || batch->empty())
             return;
+        if (m_pack.queue_depth > 0) {
+            if (m_pack.source.enabled)
+                CVVP_ASSERT_MSG(batch->rows == m_pack.source.fmt.src_height && batch->cols == m_pack.source.fmt.src_width &&
+                                    batch->channels == m_pack.source.fmt.src_channels,
+                                "decoded frame geometry must match the source format");
+            else
+                CVVP_ASSERT_MSG(batch->channels == 1 && batch->rows == m_pack.background.rows && batch->cols == m_pack.background.cols,
+                                "frame geometry must match the background");
+            // back-pressure: a full ring first gives up its oldest batch (the reference's TryInsert fails until a
+            // result was taken, token_processing_unit.h:117-135)
+            if (cvvp_highlight_queue_pending(m_ctx.get()) == m_pack.queue_depth)
+                m_ready.push_back(take_next());
+            m_ctx.check(cvvp_highlight_submit(m_ctx.get(), batch->data.data(), batch->n, batch->frame_bytes()));
+            return; // the token's bytes were copied into the slot: it is dropped here like a consumed token
+        }
         CVVP_ASSERT_MSG(batch->channels == 1 && batch->rows == m_pack.background.rows && batch->cols == m_pack.background.cols,
                         "frame geometry must match the background");
         if (m_pack.components) {
-            m_comps.assign(std::size_t(batch->n) * m_pack.max_components, cvvp_component{});
-            m_ncomps.assign(std::size_t(batch->n), 0);
+            batch->max_comps = m_pack.max_components;
+            batch->comps.assign(std::size_t(batch->n) * m_pack.max_components, cvvp_component{});
+            batch->ncomps.assign(std::size_t(batch->n), 0);
             if (m_pack.labels)
-                m_labels.resize(std::size_t(batch->n) * batch->frame_bytes());
+                batch->labels.resize(std::size_t(batch->n) * batch->frame_bytes());
             m_ctx.check(cvvp_highlight_frames_cc(m_ctx.get(), batch->data.data(), batch->n, batch->frame_bytes(),
-                                                 batch->data.data(), batch->frame_bytes(), m_comps.data(),
-                                                 m_pack.max_components, m_ncomps.data(),
-                                                 m_pack.labels ? m_labels.data() : nullptr, batch->frame_bytes()));
+                                                 batch->data.data(), batch->frame_bytes(), batch->comps.data(),
+                                                 m_pack.max_components, batch->ncomps.data(),
+                                                 m_pack.labels ? batch->labels.data() : nullptr, batch->frame_bytes()));
         } else {
             m_ctx.check(cvvp_highlight_frames(m_ctx.get(), batch->data.data(), batch->n, batch->frame_bytes(),
                                               batch->data.data(), batch->frame_bytes()));
         }
-        m_result = std::move(batch);
+        m_ready.push_back(std::move(batch));
     }
-    // components of frame i of the last result batch (valid until the next Insert)
-    int component_count(int i) const { return m_ncomps.empty() ? 0 : m_ncomps[std::size_t(i)]; }
-    const cvvp_component *components(int i) const { return m_comps.data() + std::size_t(i) * m_pack.max_components; }
-    const std::int32_t *labels(int i, std::size_t npix) const { return m_labels.empty() ? nullptr : m_labels.data() + std::size_t(i) * npix; }
     int max_components() const { return m_pack.max_components; }
-    std::unique_ptr<FrameBatch> TryGetResult() { return std::move(m_result); } // :72-79
-    void NotifyNoMoreTokens() {}                                               // :82-85 (tokens are independent)
-    bool HasResults() const { return static_cast<bool>(m_result); }            // :88-91
+    // :72-79 -- null = none.  Queue mode: never blocks before NotifyNoMoreTokens (a batch still on the device is "no
+    // result yet", exactly what a busy worker reports); after it, waits for what is pending, in order.
+    std::unique_ptr<FrameBatch> TryGetResult()
+    {
+        if (!m_ready.empty()) {
+            std::unique_ptr<FrameBatch> r = std::move(m_ready.front());
+            m_ready.pop_front();
+            return r;
+        }
+        if (m_pack.queue_depth > 0 && cvvp_highlight_queue_pending(m_ctx.get()) > 0) {
+            const int ready = cvvp_highlight_queue_ready(m_ctx.get());
+            if (ready < 0)
+                m_ctx.check(ready);
+            if (ready == 1 || m_no_more)
+                return take_next();
+        }
+        return nullptr;
+    }
+    void NotifyNoMoreTokens() { m_no_more = true; } // :82-85 (tokens are independent; nothing is held back)
+    bool HasResults() const { return !m_ready.empty() || (m_pack.queue_depth > 0 && cvvp_highlight_queue_pending(m_ctx.get()) > 0); } // :88-91
 
 private:
+    std::unique_ptr<FrameBatch> take_next()
+    {
+        auto out = std::make_unique<FrameBatch>();
+        out->rows = m_pack.background.rows;
+        out->cols = m_pack.background.cols;
+        out->channels = 1;
+        out->data.resize(std::size_t(m_pack.max_batch) * out->frame_bytes());
+        if (m_pack.components) {
+            out->max_comps = m_pack.max_components;
+            out->comps.resize(std::size_t(m_pack.max_batch) * m_pack.max_components);
+            out->ncomps.resize(std::size_t(m_pack.max_batch));
+        }
+        long long n = 0;
+        m_ctx.check(cvvp_highlight_next(m_ctx.get(), out->data.data(), out->frame_bytes(), &n,
+                                        m_pack.components ? out->comps.data() : nullptr,
+                                        m_pack.components ? out->ncomps.data() : nullptr));
+        out->n = int(n);
+        out->data.resize(std::size_t(n) * out->frame_bytes());
+        return out;
+    }
+
     GpuHighlightPack m_pack;
     Context m_ctx;
-    std::unique_ptr<FrameBatch> m_result{};
-    std::vector<cvvp_component> m_comps{};
-    std::vector<int> m_ncomps{};
-    std::vector<std::int32_t> m_labels{};
+    std::deque<std::unique_ptr<FrameBatch>> m_ready{};
+    bool m_no_more{false};
 };
 } // namespace cvvp_host

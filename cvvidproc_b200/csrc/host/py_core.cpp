@@ -8,13 +8,21 @@
 // OpenCV C++ is not part of this build, so the numpy<->cv::Mat caster (Sources/Utility/ndarray_converter.*) is replaced
 // by py::array_t<uint8_t>, and video decode goes through the Python `cv2` module (the only decoder in the image),
 // reproducing CvVidFramesGeneratorAlgo::GetTokenSet (ProcessorTokenHandlers/cv_vid_frames_generator_algo.h:120-185):
-// crop, then channel 0 (vid_is_grayscale) or RGB2GRAY (grayscale) or the frame as is.
+// crop, then channel 0 (vid_is_grayscale) or RGB2GRAY (grayscale) or the frame as is.  That per-frame work runs on the
+// DEVICE (csrc/frames.cu): the decoded frame is handed over untouched together with a SourceFormat.  CVVP_HOST_PREP=1
+// keeps it on the host through cv2 instead (cross-check; tests hold the two to each other).
+//
+// TrackObjects is a pipeline like the reference's (highlight process || assign process,
+// cv_vid_objecttrack_helpers.cpp:126-133): batches are submitted to the device asynchronously, at most
+// token_storage_limit in flight, while this thread decodes the next batch and runs the tracker callback on the
+// masks that have come back -- strictly in frame order.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <iostream>
 #include <limits>
 #include <memory>
@@ -110,6 +118,34 @@ public:
         if (!m_is_gray)
             set("CAP_PROP_CONVERT_RGB", 1.0);
     }
+    // the decoded frame as the decoder produced it (contiguous uint8), or None at end of stream
+    py::object next_decoded()
+    {
+        py::tuple res = m_vid.attr("read")().cast<py::tuple>();
+        if (!res[0].cast<bool>() || res[1].is_none())
+            return py::none();
+        return m_np.attr("ascontiguousarray")(res[1], py::arg("dtype") = m_np.attr("uint8"));
+    }
+    // what the device has to do with a decoded frame of `channels` channels (:141-156)
+    SourceFormat format_for(int rows, int cols, int channels) const
+    {
+        SourceFormat sf;
+        sf.enabled = true;
+        sf.fmt.src_width = cols;
+        sf.fmt.src_height = rows;
+        sf.fmt.src_channels = channels;
+        sf.fmt.crop_x = m_crop.x;
+        sf.fmt.crop_y = m_crop.y;
+        sf.fmt.crop_width = m_crop.width;
+        sf.fmt.crop_height = m_crop.height;
+        if (m_is_gray)
+            sf.fmt.mode = CVVP_FRAMES_CHANNEL0; // :149-151
+        else if (m_gray && channels >= 3)
+            sf.fmt.mode = CVVP_FRAMES_RGB2GRAY; // :152-154
+        else
+            sf.fmt.mode = CVVP_FRAMES_AS_IS; // :155-156
+        return sf;
+    }
     py::object next()
     {
         py::tuple res = m_vid.attr("read")().cast<py::tuple>();
@@ -136,6 +172,12 @@ private:
     bool m_gray, m_is_gray;
     Rect m_crop{0, 0, 0, 0};
 };
+
+bool host_prep()
+{
+    const char *e = std::getenv("CVVP_HOST_PREP");
+    return e && *e && *e != '0';
+}
 
 void array_geometry(const py::array &a, int &rows, int &cols, int &channels)
 {
@@ -219,28 +261,43 @@ py::object GetVideoBackground(const VidBgPack &pack)
     vid.set_crop(crop);
     vid.configure();
 
-    GpuMedianAlgo algo{GpuMedianPack{-1, frames_to_analyze}};
+    const bool on_device = !host_prep();
+    std::unique_ptr<GpuMedianAlgo> algo_p; // built once the first decoded frame tells the channel count
     long long consumed = 0;
     int rows = 0, cols = 0, channels = 1;
     IntervalTimer t_batch, t_gen, t_unit, t_consume;
     while (consumed < frames_to_analyze) { // generator :128-135
         t_batch.start();
         t_gen.start();
-        py::object f = vid.next();
+        py::object f = on_device ? vid.next_decoded() : vid.next();
         t_gen.stop();
         if (f.is_none())
             break;
         py::array a = f.cast<py::array>();
         array_geometry(a, rows, cols, channels);
+        if (!algo_p) {
+            GpuMedianPack mp{-1, frames_to_analyze, {}};
+            if (on_device)
+                mp.source = vid.format_for(rows, cols, channels);
+            algo_p = std::make_unique<GpuMedianAlgo>(mp);
+        }
         t_unit.start();
-        algo.InsertRaw(static_cast<const std::uint8_t *>(a.data()), 1, rows, cols, channels, std::size_t(rows) * cols * channels);
+        if (on_device) {
+            CVVP_ASSERT(rows == int(fh) && cols == int(fw));
+            algo_p->InsertDecoded(static_cast<const std::uint8_t *>(a.data()), 1, std::size_t(rows) * cols * channels);
+        } else {
+            algo_p->InsertRaw(static_cast<const std::uint8_t *>(a.data()), 1, rows, cols, channels, std::size_t(rows) * cols * channels);
+        }
         t_unit.stop();
         t_batch.stop();
         ++consumed;
     }
     t_consume.start();
-    algo.NotifyNoMoreTokens();
-    std::unique_ptr<FrameBatch> res = algo.TryGetResult();
+    std::unique_ptr<FrameBatch> res;
+    if (algo_p) {
+        algo_p->NotifyNoMoreTokens();
+        res = algo_p->TryGetResult();
+    }
     t_consume.stop();
     if (!res || res->empty())
         return py::none();
@@ -324,71 +381,41 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
     hp.labels = want_labels;
     if (want_comps && user_kwargs.contains("cvvp_max_components"))
         hp.max_components = std::max(1, user_kwargs["cvvp_max_components"].cast<int>());
-    GpuHighlightAlgo highlighter{std::move(hp)};
+    // label images only travel through the synchronous entry point; everything else is queued
+    const bool on_device = !host_prep() && !want_labels;
+    std::unique_ptr<GpuHighlightAlgo> highlighter; // built once the first decoded frame tells the channel count
 
-    // frames per device batch: the reference's batch_size is a thread count; here it is sized for the GPU and bounded by
-    // token_storage_limit batches of host memory like the reference's queues (token_queue.h:209-214)
+    // frames per device batch: the reference's batch_size is a thread count; here it is sized for the GPU, and at most
+    // token_storage_limit batches are in flight like the reference's queues (token_queue.h:209-214)
     const long long npix = static_cast<long long>(crop.width) * crop.height;
     long long batch_frames = (32ll << 20) / npix + 1;
     if (batch_frames > 256)
         batch_frames = 256;
+    if (const char *e = std::getenv("CVVP_TRACK_BATCH")) // developer switch: frames per batch (tests use small batches)
+        batch_frames = std::max(1, std::atoi(e));
+    const int depth = std::min(std::max(pack.token_storage_limit, 1), 3);
 
     // AssignObjectsAlgo state (assign_objects_algo.h:172-178)
     py::dict objects_active, objects_archive;
     long long num_processed = 0;
     int next_id = 0;
     bool any = false;
-
-    long long consumed = 0;
-    bool eof = false;
     IntervalTimer h_batch, h_gen, h_unit, h_consume, a_batch, a_gen, a_unit, a_consume;
-    while (!eof && consumed < num_frames) {
-        h_batch.start();
-        h_gen.start();
-        auto batch = std::make_unique<FrameBatch>();
-        batch->rows = crop.height;
-        batch->cols = crop.width;
-        batch->channels = 1;
-        while (batch->n < batch_frames && consumed < num_frames) {
-            py::object f = vid.next();
-            if (f.is_none()) {
-                eof = true;
-                break;
-            }
-            py::array a = f.cast<py::array>();
-            int r, c, ch;
-            array_geometry(a, r, c, ch);
-            CVVP_ASSERT_MSG(ch == 1, "TrackObjects needs single-channel frames: set grayscale or vid_is_grayscale "
-                                     "(cv::findContours requires 8UC1)");
-            CVVP_ASSERT(r == crop.height && c == crop.width);
-            const auto *src = static_cast<const std::uint8_t *>(a.data());
-            batch->data.insert(batch->data.end(), src, src + std::size_t(r) * c);
-            batch->n++;
-            ++consumed;
-        }
-        h_gen.stop();
-        if (batch->n == 0)
-            break;
-        h_unit.start();
-        highlighter.Insert(std::move(batch));
-        h_unit.stop();
-        h_consume.start();
-        std::unique_ptr<FrameBatch> masks = highlighter.TryGetResult();
-        h_consume.stop();
-        h_batch.stop();
+
+    // the assign stage: strictly in frame order, one call per frame (assign_objects_algo.h:111-133)
+    auto deliver = [&](const FrameBatch &masks) {
         a_batch.start();
         a_gen.start(); // the intermediary hands the ordered masks over (mat_set_intermediary.h:84-114)
         a_gen.stop();
-        // strictly in frame order, one call per frame (assign_objects_algo.h:111-133)
-        for (int i = 0; i < masks->n; ++i) {
-            py::array_t<std::uint8_t> bw({masks->rows, masks->cols});
-            std::memcpy(bw.mutable_data(), masks->data.data() + std::size_t(i) * masks->frame_bytes(), masks->frame_bytes());
+        for (int i = 0; i < masks.n; ++i) {
+            py::array_t<std::uint8_t> bw({masks.rows, masks.cols});
+            std::memcpy(bw.mutable_data(), masks.data.data() + std::size_t(i) * masks.frame_bytes(), masks.frame_bytes());
             using namespace pybind11::literals;
             a_unit.start();
             if (want_comps) {
-                const int total = highlighter.component_count(i);
-                const int cnt = std::min(total, highlighter.max_components());
-                const cvvp_component *cs = highlighter.components(i);
+                const int total = masks.component_count(i);
+                const int cnt = std::min(total, masks.max_comps);
+                const cvvp_component *cs = masks.components(i);
                 py::array_t<std::int32_t> stats({cnt, 5});
                 py::array_t<double> cents({cnt, 2});
                 py::array_t<std::int32_t> first({cnt, 2});
@@ -412,9 +439,8 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
                 comps["centroids"] = cents;
                 comps["first"] = first;
                 if (want_labels) {
-                    py::array_t<std::int32_t> lab({masks->rows, masks->cols});
-                    std::memcpy(lab.mutable_data(), highlighter.labels(i, masks->frame_bytes()),
-                                masks->frame_bytes() * sizeof(std::int32_t));
+                    py::array_t<std::int32_t> lab({masks.rows, masks.cols});
+                    std::memcpy(lab.mutable_data(), masks.label_image(i), masks.frame_bytes() * sizeof(std::int32_t));
                     comps["labels"] = lab;
                 }
                 next_id = pack.assign_objects_pack.function("bw_frame"_a = bw, "frames_processed"_a = num_processed,
@@ -435,6 +461,78 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
             any = true;
         }
         a_batch.stop();
+    };
+
+    long long consumed = 0;
+    bool eof = false;
+    while (!eof && consumed < num_frames) {
+        h_batch.start();
+        h_gen.start();
+        auto batch = std::make_unique<FrameBatch>();
+        while (batch->n < batch_frames && consumed < num_frames) {
+            py::object f = on_device ? vid.next_decoded() : vid.next();
+            if (f.is_none()) {
+                eof = true;
+                break;
+            }
+            py::array a = f.cast<py::array>();
+            int r, c, ch;
+            array_geometry(a, r, c, ch);
+            if (!highlighter) {
+                hp.queue_depth = depth;
+                hp.max_batch = batch_frames;
+                if (on_device) {
+                    CVVP_ASSERT(r == fh && c == fw);
+                    hp.source = vid.format_for(r, c, ch);
+                    CVVP_ASSERT_MSG(hp.source.out_channels() == 1,
+                                    "TrackObjects needs single-channel frames: set grayscale or vid_is_grayscale "
+                                    "(cv::findContours requires 8UC1)");
+                }
+                highlighter = std::make_unique<GpuHighlightAlgo>(std::move(hp));
+            }
+            if (batch->n == 0) {
+                batch->rows = r;
+                batch->cols = c;
+                batch->channels = ch;
+            }
+            if (!on_device) {
+                CVVP_ASSERT_MSG(ch == 1, "TrackObjects needs single-channel frames: set grayscale or vid_is_grayscale "
+                                         "(cv::findContours requires 8UC1)");
+                CVVP_ASSERT(r == crop.height && c == crop.width);
+            }
+            CVVP_ASSERT(r == batch->rows && c == batch->cols && ch == batch->channels);
+            const auto *src = static_cast<const std::uint8_t *>(a.data());
+            batch->data.insert(batch->data.end(), src, src + std::size_t(r) * c * ch);
+            batch->n++;
+            ++consumed;
+        }
+        h_gen.stop();
+        if (batch->n == 0)
+            break;
+        h_unit.start();
+        highlighter->Insert(std::move(batch)); // queued on the device; returns before the masks exist
+        h_unit.stop();
+        h_batch.stop();
+        // masks that have come back meanwhile go to the tracker while the device works on the newer batches
+        for (;;) {
+            h_consume.start();
+            std::unique_ptr<FrameBatch> masks = highlighter->TryGetResult();
+            h_consume.stop();
+            if (!masks)
+                break;
+            deliver(*masks);
+        }
+    }
+    if (highlighter) { // end of stream: drain in order (token_processing_unit.h:334)
+        highlighter->NotifyNoMoreTokens();
+        for (;;) {
+            h_consume.start();
+            std::unique_ptr<FrameBatch> masks = highlighter->TryGetResult();
+            h_consume.stop();
+            if (!masks)
+                break;
+            deliver(*masks);
+        }
     }
     a_consume.start();
     a_consume.stop();

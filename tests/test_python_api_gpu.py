@@ -163,3 +163,70 @@ def test_track_objects_needs_single_channel(color_video):
     ap = cvp.AssignObjectsPack(lambda **kw: 0, {})
     with pytest.raises(RuntimeError, match="single-channel"):
         cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, ap))
+
+
+def test_device_and_host_frame_preparation_agree(color_video, gray_video, oracle_median, monkeypatch):
+    """the generator's crop / channel reduction runs on the device by default (csrc/frames.cu); CVVP_HOST_PREP=1 keeps it
+    on the host through cv2 -- same backgrounds, same archives"""
+    path, frames = color_video
+    packs = [dict(), dict(grayscale=True), dict(vid_is_grayscale=True), dict(grayscale=True, crop_x=3, crop_y=2, crop_width=41, crop_height=30),
+             dict(crop_x=1, crop_y=1, crop_width=50, crop_height=35)]
+    dev = [cvp.GetVideoBackground(cvp.VidBgPack(path, **kw)) for kw in packs]
+    monkeypatch.setenv("CVVP_HOST_PREP", "1")
+    host = [cvp.GetVideoBackground(cvp.VidBgPack(path, **kw)) for kw in packs]
+    monkeypatch.delenv("CVVP_HOST_PREP")
+    for d, h in zip(dev, host):
+        assert d.shape == h.shape and np.array_equal(d, h)
+    gray = np.stack([cv2.cvtColor(np.ascontiguousarray(f[2:32, 3:44]), cv2.COLOR_RGB2GRAY) for f in frames])
+    assert np.array_equal(dev[3], oracle_median(gray))
+
+
+def test_track_objects_pipeline_of_small_batches(gray_video, monkeypatch):
+    """several batches in flight (CVVP_TRACK_BATCH=7, token_storage_limit 1..3): the callback still sees every frame once,
+    in order, and the archive is the reference's"""
+    path, frames = gray_video
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+    p = ho.canonical_params(bg)
+    hp = cvp.HighlightObjectsPack(bg, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                                  p.min_size_threshold, p.width_border)
+    kwargs = {"min_area": 5}
+    want = _reference_track(frames, p, kwargs)
+    monkeypatch.setenv("CVVP_TRACK_BATCH", "7")
+    for limit in (1, 2, 10):
+        seen = []
+
+        def tracker(bw_frame, frames_processed, objects_prev, objects_archive, next_ID, kwargs):
+            seen.append(frames_processed)
+            return _tracker(bw_frame, frames_processed, objects_prev, objects_archive, next_ID, kwargs)
+
+        archive = cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(tracker, kwargs), vid_is_grayscale=True,
+                                                          token_storage_limit=limit))
+        assert seen == list(range(len(frames)))
+        assert archive == want
+    # the same with the device's components, and with the host-side frame preparation
+    archive = cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(_tracker_with_components,
+                                                                                     {"min_area": 5, "cvvp_components": True}),
+                                                      vid_is_grayscale=True))
+    key = lambda d: sorted((v["frame"], v["area"], v["cx"], v["cy"]) for v in d.values())  # noqa: E731
+    assert key(archive) == key(want)
+    monkeypatch.setenv("CVVP_HOST_PREP", "1")
+    archive = cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(_tracker, kwargs), vid_is_grayscale=True))
+    assert archive == want
+
+
+def test_track_objects_on_a_cropped_colour_video(color_video):
+    """grayscale=True on a colour video with a crop window: RGB2GRAY of the decoded frames on the device, masks and
+    archive equal to the cv2 restatement on cv2-prepared frames"""
+    path, frames = color_video
+    crop = dict(crop_x=4, crop_y=2, crop_width=48, crop_height=36)
+    gray = np.stack([cv2.cvtColor(np.ascontiguousarray(f[2:38, 4:52]), cv2.COLOR_RGB2GRAY) for f in frames])
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, grayscale=True, **crop))
+    assert bg.shape == (36, 48)
+    p = ho.HighlightParams(bg, np.ones((2, 2), np.uint8), 40, 25, 60, 2, 2, 0)
+    hp = cvp.HighlightObjectsPack(bg, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                                  p.min_size_threshold, p.width_border)
+    kwargs = {"min_area": 1}
+    archive = cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(_tracker, kwargs), grayscale=True, **crop))
+    want = _reference_track(gray, p, kwargs)
+    assert len(want) > 5
+    assert archive == want
