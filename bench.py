@@ -415,6 +415,65 @@ def run_highlight_section(ctx, torch, dist, rank, local_rank, world, args, sampl
     return out
 
 
+def run_frame_source_section(ctx, torch, local_rank, args, stream):
+    """The stage in front of both operators: decoded 1080p 3-channel frames resident in HBM ->
+    grey frames (crop = whole frame, COLOR_RGB2GRAY; cv_vid_frames_generator_algo.h:141-156) by csrc/frames.cu.
+    Algorithmic bytes = 3 B/px read + 1 B/px written.  CPU baseline = cv2.cvtColor on all host threads."""
+    from cvvidproc_b200 import _cabi
+
+    W, H, n = 1920, 1080, 96  # 597 MB of decoded frames: larger than the 126 MB L2
+    dev = f"cuda:{local_rank}"
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11)
+    src = torch.randint(0, 256, (n, H * W * 3), dtype=torch.uint8, device=dev, generator=gen)
+    dst = torch.empty((n, H * W), dtype=torch.uint8, device=dev)
+    fmt = _cabi.FrameFormat.of((H, W, 3), _cabi.FRAMES_RGB2GRAY)
+    steps = max(3, min(args.steps, 10))
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            ctx.frames_prepare_device(src.data_ptr(), n, H * W * 3, fmt, dst.data_ptr(), H * W)
+        torch.cuda.synchronize()
+        l0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            ctx.frames_prepare_device(src.data_ptr(), n, H * W * 3, fmt, dst.data_ptr(), H * W)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        launches = ctx.launch_count - l0
+    ms = e0.elapsed_time(e1) / steps
+    mpx = n * W * H / 1e6
+    peak = load_peaks()[0]
+    achieved = 4.0 * n * W * H / (ms * 1e-3) / 1e9
+    out = {
+        "metric": "megapixel-frames/sec (frame source: 1080p decoded 3-channel -> grey)", "unit": UNIT,
+        "value": mpx / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": n, "steps": steps, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "frames_prepare_kernel",
+                     "note": "algorithmic bytes = 3 B/px decoded frame in + 1 B/px prepared frame out"},
+    }
+    if not args.no_cpu_baseline:
+        import concurrent.futures as cf
+
+        import cv2
+
+        cv2.setNumThreads(1)
+        host = src[:16].cpu().numpy().reshape(16, H, W, 3)
+        cores = os.cpu_count() or 1
+        done, last = 0, None
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(max_workers=cores) as ex:
+            while time.perf_counter() - t0 < 3.0:
+                res = list(ex.map(lambda i: cv2.cvtColor(host[i % 16], cv2.COLOR_RGB2GRAY), range(done, done + 4 * cores)))
+                done += len(res)
+                last = res[-1]
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": done * W * H / 1e6 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{done} frames in ~3 s, cv2.cvtColor(COLOR_RGB2GRAY), {cores} threads x cv2.setNumThreads(1)"}
+        out["parity_spot_check"] = bool(np.array_equal(last.reshape(-1), dst[(done - 1) % 16].cpu().numpy()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -577,6 +636,10 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
         finally:
             sampler2.stop()
 
+    frame_source = None
+    if world == 1 and not args.no_highlight:
+        frame_source = run_frame_source_section(ctx, torch, local_rank, args, stream)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -593,6 +656,7 @@ def run_gpu_arm(args, rank: int, local_rank: int, world: int):
             "cpu_baseline": cpu_baseline,
             "parity_spot_check": same,
             "highlight": highlight,
+            "frame_source": frame_source,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

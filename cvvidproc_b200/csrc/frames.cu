@@ -13,9 +13,9 @@
 // RGB2GRAY arithmetic (OpenCV is not vendored in the reference; pinned here against cv2 4.13 on all 2^24 triples,
 // tests/test_oracle_frames.py):  y = (c0*9798 + c1*19235 + c2*3735 + 16384) >> 15.
 //
-// HBM-bound byte work: a CTA takes up to 1024 output elements of one row; its source bytes are fetched as aligned
-// 128-bit words into shared memory (coalesced whatever the crop offset), every thread reduces four elements from
-// shared memory (word stride 3*C/4 per thread: odd for C = 3, conflict-free) and stores one 32-bit word.
+// HBM-bound byte work: a CTA takes up to 1024 output elements of four consecutive rows; their source bytes are fetched
+// as aligned 128-bit words into shared memory (coalesced whatever the crop offset), every thread reduces four elements
+// per row from shared memory (byte stride 12 per thread for C = 3: conflict-free) and stores one 32-bit word per row.
 #include "context.hpp"
 
 namespace cvvp
@@ -23,7 +23,9 @@ namespace cvvp
 namespace
 {
 constexpr int kTile = 1024;   // output elements per CTA
-constexpr int kThreads = 256; // 4 elements per thread
+constexpr int kThreads = 256; // 4 elements per thread and row
+constexpr int kRows = 4;      // rows per CTA
+constexpr int kTileWords = (kTile * 4 + 32) / 16; // 128-bit words of one staged row segment (4 channels + alignment slack)
 
 struct PrepArgs {
     const uint8_t *src;
@@ -48,50 +50,75 @@ __device__ __forceinline__ uint32_t reduce_element(const uint8_t *p, uint32_t gr
     return p[0];
 }
 
+// 16 source bytes at offset `at` (a multiple of 16 relative to a.src)
+__device__ __forceinline__ uint4 load_chunk(const PrepArgs &a, size_t at)
+{
+    if (a.aligned && at + 16 <= a.src_bytes)
+        return __ldcs(reinterpret_cast<const uint4 *>(a.src + at)); // read once: streaming
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 16; ++b)
+        if (at + b < a.src_bytes)
+            w[b >> 2] |= uint32_t(a.src[at + b]) << (8 * (b & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// A CTA takes the same tile of kRows consecutive rows.  Every thread first issues its 128-bit load of EVERY row and
+// only then stores them to shared memory, so kRows independent loads per thread (~12 KB per CTA, ~100 KB per SM) are
+// in flight; a load -> store loop per row serialised one DRAM latency per row and left the kernel at 3.4 TB/s.
 __global__ void __launch_bounds__(kThreads) frames_prepare_kernel(const PrepArgs a)
 {
-    __shared__ uint4 tile[(kTile * 4 + 32) / 16];
-    const uint32_t row = blockIdx.x / a.tiles_per_row;
+    __shared__ uint4 tile[kRows][kTileWords];
+    const uint32_t rg = blockIdx.x / a.tiles_per_row;
     const uint32_t x0 = (blockIdx.x % a.tiles_per_row) * kTile;
     const uint32_t f = blockIdx.y;
     const uint32_t n = min(uint32_t(kTile), a.row_elems - x0);
-
-    // source bytes of this tile: [seg, seg + seg_len) relative to a.src
-    const size_t seg = size_t(f) * a.src_stride + size_t(a.first_byte) + size_t(row) * a.src_row_bytes + size_t(x0) * a.step;
+    const uint32_t row0 = rg * kRows;
+    const uint32_t nrows = min(uint32_t(kRows), a.rows - row0);
     const uint32_t seg_len = n * a.step;
-    const size_t a0 = seg & ~size_t(15);
-    const uint32_t off = uint32_t(seg - a0);
-    const uint32_t nchunks = (off + seg_len + 15u) >> 4;
-    for (uint32_t k = threadIdx.x; k < nchunks; k += kThreads) {
-        const size_t at = a0 + size_t(k) * 16;
-        uint4 v;
-        if (a.aligned && at + 16 <= a.src_bytes) {
-            v = __ldcs(reinterpret_cast<const uint4 *>(a.src + at)); // read once: streaming
-        } else {
-            uint32_t w[4] = {0, 0, 0, 0};
-            for (int b = 0; b < 16; ++b)
-                if (at + b < a.src_bytes)
-                    w[b >> 2] |= uint32_t(a.src[at + b]) << (8 * (b & 3));
-            v = make_uint4(w[0], w[1], w[2], w[3]);
+
+    // source bytes of row r's tile: [seg, seg + seg_len) relative to a.src, staged from the aligned address a0 = seg - off
+    uint32_t off[kRows];
+    size_t a0[kRows];
+    uint4 v[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const size_t seg = size_t(f) * a.src_stride + size_t(a.first_byte) + size_t(row0 + r) * a.src_row_bytes + size_t(x0) * a.step;
+        a0[r] = seg & ~size_t(15);
+        off[r] = uint32_t(seg - a0[r]);
+        if (uint32_t(r) < nrows && threadIdx.x < ((off[r] + seg_len + 15u) >> 4))
+            v[r] = load_chunk(a, a0[r] + size_t(threadIdx.x) * 16);
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        if (uint32_t(r) < nrows) {
+            const uint32_t nchunks = (off[r] + seg_len + 15u) >> 4;
+            if (threadIdx.x < nchunks)
+                tile[r][threadIdx.x] = v[r];
+            for (uint32_t k = threadIdx.x + kThreads; k < nchunks; k += kThreads) // only 4-channel tiles get here
+                tile[r][k] = load_chunk(a, a0[r] + size_t(k) * 16);
         }
-        tile[k] = v;
     }
     __syncthreads();
 
-    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(tile) + off;
     const uint32_t e0 = threadIdx.x * 4;
     if (e0 >= n)
         return;
-    uint8_t *out = a.dst + size_t(f) * a.dst_stride + size_t(row) * a.row_elems + x0 + e0;
-    if (e0 + 4 <= n && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
-        uint32_t w = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            w |= reduce_element(bytes + size_t(e0 + i) * a.step, a.gray) << (8 * i);
-        __stcs(reinterpret_cast<uint32_t *>(out), w);
-    } else {
-        for (uint32_t i = 0; i < 4 && e0 + i < n; ++i)
-            out[i] = uint8_t(reduce_element(bytes + size_t(e0 + i) * a.step, a.gray));
+    for (int r = 0; r < kRows; ++r) {
+        if (uint32_t(r) >= nrows)
+            break;
+        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(tile[r]) + off[r];
+        uint8_t *out = a.dst + size_t(f) * a.dst_stride + size_t(row0 + r) * a.row_elems + x0 + e0;
+        if (e0 + 4 <= n && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                w |= reduce_element(bytes + size_t(e0 + i) * a.step, a.gray) << (8 * i);
+            __stcs(reinterpret_cast<uint32_t *>(out), w);
+        } else {
+            for (uint32_t i = 0; i < 4 && e0 + i < n; ++i)
+                out[i] = uint8_t(reduce_element(bytes + size_t(e0 + i) * a.step, a.gray));
+        }
     }
 }
 } // namespace
@@ -141,7 +168,7 @@ int frames_prepare_launch(cvvp_ctx *ctx, const uint8_t *d_src, long long n, size
     a.rows = uint32_t(f.crop_height);
     a.gray = f.mode == CVVP_FRAMES_RGB2GRAY ? 1u : 0u;
     a.aligned = (reinterpret_cast<uintptr_t>(d_src) & 15) == 0 ? 1u : 0u;
-    const unsigned long long ctas = (unsigned long long)a.tiles_per_row * a.rows;
+    const unsigned long long ctas = (unsigned long long)a.tiles_per_row * ((a.rows + kRows - 1) / kRows);
     if (ctas > 0x7fffffffull)
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "frames: frame too large for one launch");
     for (long long done = 0; done < n;) {
