@@ -9,6 +9,7 @@ snapshot to the GPU box (they are git-ignored, not gpurun-ignored).
 from __future__ import annotations
 
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -64,7 +65,9 @@ def build_cuda_lib(force: bool = False, verbose: bool = False) -> Path:
     todo = []
     for src in sources:
         obj = objdir / (src.stem + ".o")
-        if force or not _newer_than(obj, [src] + headers):
+        # a second build of a kernel file includes that .cu (highlight_fused_small.cu): it depends on it like on a header
+        included = [CSRC / m for m in re.findall(r'#include "([^"]+\.cu)"', src.read_text())]
+        if force or not _newer_than(obj, [src] + headers + included):
             todo.append((src, obj))
     if not todo and _newer_than(LIB_PATH, sources + headers):
         return LIB_PATH

@@ -34,7 +34,22 @@ namespace cvvp
 {
 namespace
 {
+// The file is compiled twice (highlight_fused_small.cu includes it with CVVP_HLF_SMALL defined): the same code with
+//   1024 threads, 192 KB of dynamic shared memory, one CTA per SM   -- large frames (1080p: 553 us per frame and CTA);
+//    256 threads,  48 KB,                          four CTAs per SM -- small frames (512x256), where a 1024-thread CTA
+//                                                                      spends its time in block barriers: four frames per
+//                                                                      SM overlap each other's barrier and latency stalls.
+#ifdef CVVP_HLF_SMALL
+#define HLF(name) name##_small
+constexpr int NT = 256;
+constexpr int kCtasPerSm = 4;
+constexpr size_t kDynSmemBytes = 48 * 1024;
+#else
+#define HLF(name) name##_large
 constexpr int NT = 1024; // threads per CTA (one CTA per SM)
+constexpr int kCtasPerSm = 1;
+constexpr size_t kDynSmemBytes = 192 * 1024; // per CTA; one CTA per SM
+#endif
 constexpr int NW = NT / 32;
 constexpr int kImages = 4;    // A, U (later B), L, Tm
 constexpr int kRunArrays = 8; // xinfo0, parent0, xinfo1, parent1, link, st_s, st_e, st_x
@@ -1628,7 +1643,7 @@ __device__ void components_phase(const FusedArgs &P, Shared &sh, unsigned f, con
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kSmemOffs = 256; // structuring-element taps cached in shared memory
 
-__global__ void __launch_bounds__(NT, 1) highlight_fused_kernel(const FusedArgs P)
+__global__ void __launch_bounds__(NT, kCtasPerSm) highlight_fused_kernel(const FusedArgs P)
 {
     extern __shared__ uint4 dyn_smem4[];
     uint32_t *dyn = reinterpret_cast<uint32_t *>(dyn_smem4);
@@ -1797,8 +1812,6 @@ struct FusedGeom {
     uint32_t nwords, cap, rstride;
 };
 
-constexpr size_t kDynSmemBytes = 192 * 1024; // per CTA; one CTA per SM
-
 // rows per band of the shared-memory opening (0: the tiles do not fit, use the global-memory taps)
 int pick_band_rows(const FusedGeom &fg, int dy_min, int dy_max, const MorphPlan &plan)
 {
@@ -1888,6 +1901,15 @@ size_t slot_bytes(const FusedGeom &fg)
 }
 } // namespace
 
+int HLF(fused_frames_in_flight)(cvvp_ctx *ctx, HighlightState *st);
+int HLF(highlight_fused_batch)(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, size_t frame_stride, unsigned nb,
+                               uint8_t *d_out, size_t out_stride, cudaStream_t stream);
+
+#ifndef CVVP_HLF_SMALL
+int fused_frames_in_flight_small(cvvp_ctx *ctx, HighlightState *st);
+int highlight_fused_batch_small(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, size_t frame_stride, unsigned nb,
+                                uint8_t *d_out, size_t out_stride, cudaStream_t stream);
+
 bool fused_supports(const HighlightState *st)
 {
     return st->g.W <= 65535 && st->g.H <= 32767;
@@ -1903,8 +1925,37 @@ void fused_release(HighlightState *st)
     fs = FusedScratch();
 }
 
-// number of frames the kernel keeps in flight = resident CTAs, bounded by a scratch budget
+// Which build of the kernel a job uses (fixed at its first batch): frames of at most 512x512 pixels take the
+// 256-thread CTAs, four to an SM.  CVVP_HL_VARIANT=large|small forces one (tests hold both to the oracle).
+static bool use_small(HighlightState *st)
+{
+    if (st->fused_variant < 0) {
+        st->fused_variant = st->g.npix <= 512u * 512u && st->g.W <= 2048 ? 1 : 0;
+        if (const char *v = getenv("CVVP_HL_VARIANT")) {
+            if (!strcmp(v, "small") && st->g.W <= 8192)
+                st->fused_variant = 1;
+            else if (!strcmp(v, "large"))
+                st->fused_variant = 0;
+        }
+    }
+    return st->fused_variant == 1;
+}
+
 int fused_frames_in_flight(cvvp_ctx *ctx, HighlightState *st)
+{
+    return use_small(st) ? fused_frames_in_flight_small(ctx, st) : fused_frames_in_flight_large(ctx, st);
+}
+
+int highlight_fused_batch(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, size_t frame_stride, unsigned nb,
+                          uint8_t *d_out, size_t out_stride, cudaStream_t stream)
+{
+    return use_small(st) ? highlight_fused_batch_small(ctx, st, in, frame_stride, nb, d_out, out_stride, stream)
+                         : highlight_fused_batch_large(ctx, st, in, frame_stride, nb, d_out, out_stride, stream);
+}
+#endif
+
+// number of frames the kernel keeps in flight = resident CTAs, bounded by a scratch budget
+int HLF(fused_frames_in_flight)(cvvp_ctx *ctx, HighlightState *st)
 {
     if (st->fs.slots > 0)
         return st->fs.slots;
@@ -1943,7 +1994,7 @@ static int ensure_fused(cvvp_ctx *ctx, HighlightState *st)
     FusedScratch &fs = st->fs;
     if (fs.slots > 0)
         return CVVP_OK;
-    const int slots = fused_frames_in_flight(ctx, st);
+    const int slots = HLF(fused_frames_in_flight)(ctx, st);
     const FusedGeom fg = fused_geom(st->g);
     const size_t nb = sizeof(uint32_t) * size_t(slots) * kImages * fg.nwords;
     const size_t nr = sizeof(uint32_t) * size_t(slots) * run_words(fg);
@@ -1966,8 +2017,8 @@ static int ensure_fused(cvvp_ctx *ctx, HighlightState *st)
 
 // One batch of nb frames (device pointers), one kernel launch.  Work in flight on a context's highlight scratch must
 // be on one stream at a time.
-int highlight_fused_batch(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, size_t frame_stride, unsigned nb,
-                          uint8_t *d_out, size_t out_stride, cudaStream_t stream)
+int HLF(highlight_fused_batch)(cvvp_ctx *ctx, HighlightState *st, const uint8_t *in, size_t frame_stride, unsigned nb,
+                               uint8_t *d_out, size_t out_stride, cudaStream_t stream)
 {
     int rc = ensure_fused(ctx, st);
     if (rc != CVVP_OK)

@@ -56,6 +56,7 @@ struct HighlightState {
     int *d_th{nullptr};
     unsigned int *d_hist{nullptr};
     // fused path
+    int fused_variant{-1}; // which build of the fused kernel the job uses: 0 = 1024-thread CTAs, 1 = 256-thread CTAs, -1 = not chosen yet
     FusedScratch fs;
     CcOut cc;
     // staging of the host-buffer component entry point

@@ -192,6 +192,48 @@ def test_bubble_video_geometry_many_frames(gpu_ctx):
         assert np.array_equal(fused[i], ho.highlight_objects(frames[i].copy(), p)), f"frame {i} vs oracle"
 
 
+# The fused kernel is built twice (csrc/highlight_fused.cu): 1024-thread CTAs, one per SM ("large", frames above 512x512)
+# and 256-thread CTAs, four per SM ("small").  The cases above run on whichever the geometry selects -- the small frames
+# on "small", the 1080p ones on "large"; the tests below force the other build through CVVP_HL_VARIANT.
+@pytest.mark.parametrize("t", range(0, 60, 2))
+def test_large_variant_random_frames_match_oracle(gpu_ctx, t, monkeypatch):
+    monkeypatch.setenv("CVVP_HL_VARIANT", "large")
+    frame, p = hl_cases.random_case(t)
+    got = _gpu(gpu_ctx, frame[None], p)[0]
+    want = ho.highlight_objects(frame.copy(), p)
+    assert np.array_equal(got, want), f"{(got != want).sum()} pixels differ"
+
+
+@pytest.mark.parametrize("case", ADV, ids=[c[0] for c in ADV])
+def test_large_variant_adversarial_frames_match_oracle(gpu_ctx, case, monkeypatch):
+    monkeypatch.setenv("CVVP_HL_VARIANT", "large")
+    _, frame, p = case
+    got = _gpu(gpu_ctx, frame[None], p)[0]
+    assert np.array_equal(got, ho.highlight_objects(frame.copy(), p))
+
+
+def test_variants_agree_on_both_baseline_geometries(gpu_ctx, monkeypatch):
+    """512x256 (BASELINE configs[3]) forced onto the 1024-thread build and 1080p (configs[2]) forced onto the 256-thread
+    build: same masks as the build the geometry selects, the noise frames included"""
+    from cvvidproc_b200 import synth
+
+    for cfg, n, other in (("C4", 700, "large"), ("C3", 40, "small")):
+        p_ = synth.CONFIG_PARAMS[cfg]
+        w, h = p_["width"], p_["height"]
+        bg = np.sort(synth.synth_frames(0, 15, w, h, p_["seed"], p_["ndisks"]), axis=0)[7]
+        p = ho.canonical_params(bg)
+        frames = synth.synth_frames(2000, n, w, h, p_["seed"], p_["ndisks"])
+        rng = np.random.default_rng(9)
+        frames[3] = (bg.astype(np.int32) - rng.integers(0, 30, bg.shape)).clip(0, 255).astype(np.uint8)
+        monkeypatch.delenv("CVVP_HL_VARIANT", raising=False)
+        auto = _gpu(gpu_ctx, frames, p)
+        monkeypatch.setenv("CVVP_HL_VARIANT", other)
+        forced = _gpu(gpu_ctx, frames, p)
+        assert np.array_equal(auto, forced), cfg
+        for i in (0, 3, n - 1):
+            assert np.array_equal(auto[i], ho.highlight_objects(frames[i].copy(), p)), f"{cfg} frame {i} vs oracle"
+
+
 def test_argument_errors(gpu_ctx):
     from cvvidproc_b200 import _cabi
 
