@@ -43,9 +43,10 @@ struct PrepArgs {
     uint32_t aligned; // src is 16-byte aligned: 128-bit loads allowed
 };
 
-__device__ __forceinline__ uint32_t reduce_element(const uint8_t *p, uint32_t gray)
+template <bool GRAY>
+__device__ __forceinline__ uint32_t reduce_element(const uint8_t *p)
 {
-    if (gray)
+    if (GRAY)
         return (uint32_t(p[0]) * 9798u + uint32_t(p[1]) * 19235u + uint32_t(p[2]) * 3735u + 16384u) >> 15;
     return p[0];
 }
@@ -65,6 +66,10 @@ __device__ __forceinline__ uint4 load_chunk(const PrepArgs &a, size_t at)
 // A CTA takes the same tile of kRows consecutive rows.  Every thread first issues its 128-bit load of EVERY row and
 // only then stores them to shared memory, so kRows independent loads per thread (~12 KB per CTA, ~100 KB per SM) are
 // in flight; a load -> store loop per row serialised one DRAM latency per row and left the kernel at 3.4 TB/s.
+// STEP (source bytes per output element) and GRAY are template parameters: with them the twelve byte reads of a
+// thread's four pixels are immediate offsets from one shared-memory address (ncu: the first version issued 84 % of
+// all cycles, most of it address arithmetic with a run-time step).
+template <int STEP, bool GRAY>
 __global__ void __launch_bounds__(kThreads) frames_prepare_kernel(const PrepArgs a)
 {
     __shared__ uint4 tile[kRows][kTileWords];
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(kThreads) frames_prepare_kernel(const PrepArgs
     const uint32_t n = min(uint32_t(kTile), a.row_elems - x0);
     const uint32_t row0 = rg * kRows;
     const uint32_t nrows = min(uint32_t(kRows), a.rows - row0);
-    const uint32_t seg_len = n * a.step;
+    const uint32_t seg_len = n * STEP;
 
     // source bytes of row r's tile: [seg, seg + seg_len) relative to a.src, staged from the aligned address a0 = seg - off
     uint32_t off[kRows];
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(kThreads) frames_prepare_kernel(const PrepArgs
     uint4 v[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-        const size_t seg = size_t(f) * a.src_stride + size_t(a.first_byte) + size_t(row0 + r) * a.src_row_bytes + size_t(x0) * a.step;
+        const size_t seg = size_t(f) * a.src_stride + size_t(a.first_byte) + size_t(row0 + r) * a.src_row_bytes + size_t(x0) * STEP;
         a0[r] = seg & ~size_t(15);
         off[r] = uint32_t(seg - a0[r]);
         if (uint32_t(r) < nrows && threadIdx.x < ((off[r] + seg_len + 15u) >> 4))
@@ -103,21 +108,20 @@ __global__ void __launch_bounds__(kThreads) frames_prepare_kernel(const PrepArgs
     const uint32_t e0 = threadIdx.x * 4;
     if (e0 >= n)
         return;
+    uint8_t *out0 = a.dst + size_t(f) * a.dst_stride + size_t(row0) * a.row_elems + x0 + e0;
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
         if (uint32_t(r) >= nrows)
             break;
-        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(tile[r]) + off[r];
-        uint8_t *out = a.dst + size_t(f) * a.dst_stride + size_t(row0 + r) * a.row_elems + x0 + e0;
+        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(tile[r]) + off[r] + e0 * STEP;
+        uint8_t *out = out0 + size_t(r) * a.row_elems;
         if (e0 + 4 <= n && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                w |= reduce_element(bytes + size_t(e0 + i) * a.step, a.gray) << (8 * i);
+            const uint32_t w = reduce_element<GRAY>(bytes) | reduce_element<GRAY>(bytes + STEP) << 8 |
+                               reduce_element<GRAY>(bytes + 2 * STEP) << 16 | reduce_element<GRAY>(bytes + 3 * STEP) << 24;
             __stcs(reinterpret_cast<uint32_t *>(out), w);
         } else {
             for (uint32_t i = 0; i < 4 && e0 + i < n; ++i)
-                out[i] = uint8_t(reduce_element(bytes + size_t(e0 + i) * a.step, a.gray));
+                out[i] = uint8_t(reduce_element<GRAY>(bytes + i * STEP));
         }
     }
 }
@@ -178,7 +182,19 @@ int frames_prepare_launch(cvvp_ctx *ctx, const uint8_t *d_src, long long n, size
         b.src_bytes = src_bytes - size_t(done) * src_stride;
         b.aligned = (reinterpret_cast<uintptr_t>(b.src) & 15) == 0 ? 1u : 0u;
         b.dst = d_dst + size_t(done) * dst_stride;
-        frames_prepare_kernel<<<dim3(unsigned(ctas), unsigned(chunk)), kThreads, 0, stream>>>(b);
+        const dim3 grid{unsigned(ctas), unsigned(chunk), 1u};
+        if (b.gray && b.step == 3)
+            frames_prepare_kernel<3, true><<<grid, kThreads, 0, stream>>>(b);
+        else if (b.gray)
+            frames_prepare_kernel<4, true><<<grid, kThreads, 0, stream>>>(b);
+        else if (b.step == 1)
+            frames_prepare_kernel<1, false><<<grid, kThreads, 0, stream>>>(b);
+        else if (b.step == 2)
+            frames_prepare_kernel<2, false><<<grid, kThreads, 0, stream>>>(b);
+        else if (b.step == 3)
+            frames_prepare_kernel<3, false><<<grid, kThreads, 0, stream>>>(b);
+        else
+            frames_prepare_kernel<4, false><<<grid, kThreads, 0, stream>>>(b);
         CVVP_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches++;
         done += chunk;

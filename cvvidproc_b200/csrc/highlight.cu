@@ -930,11 +930,12 @@ int highlight_frames_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
         return CVVP_OK;
     // chunked, three streams: H2D on `copy`, kernels on `compute`, D2H on `copy_out`, so that both directions of
     // the link stay busy while a chunk is computed.  The device side is far faster than the link, so chunks are
-    // sized for the copies (about n/16 frames, at most one frame per resident CTA) rather than for the kernel.
+    // sized for the copies (about n/32 frames, at most one frame per resident CTA) rather than for the kernel: the
+    // first chunk's upload and the last chunk's download are the only copies that nothing overlaps.
     long long chunk;
     if (use_fused(st)) {
         const long long slots = fused_frames_in_flight(ctx, st);
-        chunk = (n + 15) / 16;
+        chunk = (n + 31) / 32;
         if (chunk < 16) chunk = 16;
         if (chunk > slots) chunk = slots;
         if (chunk > n) chunk = n;
