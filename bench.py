@@ -449,7 +449,7 @@ def run_frame_source_section(ctx, torch, local_rank, args, stream):
         "metric": "megapixel-frames/sec (frame source: 1080p decoded 3-channel -> grey)", "unit": UNIT,
         "value": mpx / (ms * 1e-3), "ms_per_step": ms, "frames_per_step": n, "steps": steps, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "frames_prepare_kernel",
+                     "traffic": load_traffic("frames_ncu_summary.json"), "kernel": "frames_prepare_kernel",
                      "note": "algorithmic bytes = 3 B/px decoded frame in + 1 B/px prepared frame out"},
     }
     if not args.no_cpu_baseline:

@@ -478,6 +478,9 @@ int cvvp_median_push_source(cvvp_ctx *ctx, const uint8_t *frames, long long n, s
         return rc;
     if ((rc = frames_upload_prepare(ctx, frames, n, frame_stride, *fmt, m.d_stack + size_t(m.count) * m.stride, m.stride)) != CVVP_OK)
         return rc;
+    // the caller may reuse `frames` on return: wait for the uploads (not for the kernels) -- a pageable source is
+    // already staged at this point, a pinned one is still being read by the copy engine
+    CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy));
     m.count += n;
     return CVVP_OK;
 }

@@ -33,15 +33,20 @@ def main():
     header, units, data = rows[0], rows[1], rows[2]
     col = {h: i for i, h in enumerate(header)}
     res = {"report": rep, "kernel": data[col["Kernel Name"]], "grid": data[col["Grid Size"]], "block": data[col["Block Size"]]}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte/block": 1.0, "Kbyte/block": 1e3,
+             "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
     for metric, name in WANT.items():
         if metric in col:
             v = data[col[metric]].replace(",", "")
+            unit = units[col[metric]]
             try:
-                res[name] = float(v)
+                res[name] = float(v) * scale.get(unit, 1.0)  # bytes and seconds, whatever unit ncu chose to print
             except ValueError:
                 res[name] = v
-            if units[col[metric]]:
-                res[name + "_unit"] = units[col[metric]]
+    if "gpu_time_duration" in res:
+        res["gpu_time_duration_s"] = res.pop("gpu_time_duration")
+    for k, v in (kv.split("=", 1) for kv in sys.argv[2:]):  # free-form annotations: source=..., workload=..., note=...
+        res[k] = v
     print(json.dumps(res, indent=1))
 
 
