@@ -51,6 +51,28 @@ __device__ __forceinline__ uint32_t reduce_element(const uint8_t *p)
     return p[0];
 }
 
+// RGB2GRAY of four pixels held in STEP aligned words (x[0] byte 0 = first channel of the first pixel) -> four grey bytes.
+// IDP.2A: c + A.lo16 * B.byte{0|2} + A.hi16 * B.byte{1|3}; the coefficient pairs put each pixel's three bytes against
+// 9798 / 19235 / 3735 wherever they fall in the words.  Exactly the closed form of reduce_element.
+template <int STEP>
+__device__ __forceinline__ uint32_t gray4(const uint32_t *x)
+{
+    constexpr uint32_t C0 = 9798u, C1 = 19235u, C2 = 3735u, RND = 16384u;
+    uint32_t y0, y1, y2, y3;
+    if (STEP == 3) {
+        y0 = __dp2a_hi(C2, x[0], __dp2a_lo(C0 | C1 << 16, x[0], RND));             // bytes 0 1 2 of x0
+        y1 = __dp2a_lo(C1 | C2 << 16, x[1], __dp2a_hi(C0 << 16, x[0], RND));       // byte 3 of x0, bytes 0 1 of x1
+        y2 = __dp2a_lo(C2, x[2], __dp2a_hi(C0 | C1 << 16, x[1], RND));             // bytes 2 3 of x1, byte 0 of x2
+        y3 = __dp2a_hi(C1 | C2 << 16, x[2], __dp2a_lo(C0 << 16, x[2], RND));       // bytes 1 2 3 of x2
+    } else { // 4 channels: one pixel per word, the fourth byte is ignored
+        y0 = __dp2a_hi(C2, x[0], __dp2a_lo(C0 | C1 << 16, x[0], RND));
+        y1 = __dp2a_hi(C2, x[1], __dp2a_lo(C0 | C1 << 16, x[1], RND));
+        y2 = __dp2a_hi(C2, x[2], __dp2a_lo(C0 | C1 << 16, x[2], RND));
+        y3 = __dp2a_hi(C2, x[3], __dp2a_lo(C0 | C1 << 16, x[3], RND));
+    }
+    return (y0 >> 15) | (y1 >> 15) << 8 | (y2 >> 15) << 16 | (y3 >> 15) << 24;
+}
+
 // 16 source bytes at offset `at` (a multiple of 16 relative to a.src)
 __device__ __forceinline__ uint4 load_chunk(const PrepArgs &a, size_t at)
 {
@@ -113,11 +135,27 @@ __global__ void __launch_bounds__(kThreads) frames_prepare_kernel(const PrepArgs
     for (int r = 0; r < kRows; ++r) {
         if (uint32_t(r) >= nrows)
             break;
-        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(tile[r]) + off[r] + e0 * STEP;
+        const uint32_t at = off[r] + e0 * STEP; // byte offset of this thread's first element in the staged segment
+        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(tile[r]) + at;
         uint8_t *out = out0 + size_t(r) * a.row_elems;
         if (e0 + 4 <= n && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
-            const uint32_t w = reduce_element<GRAY>(bytes) | reduce_element<GRAY>(bytes + STEP) << 8 |
-                               reduce_element<GRAY>(bytes + 2 * STEP) << 16 | reduce_element<GRAY>(bytes + 3 * STEP) << 24;
+            uint32_t w;
+            if (GRAY) {
+                // four pixels = STEP words: 32-bit reads from the word below `at` (thread stride STEP words: conflict-
+                // free for STEP = 3), funnel-shifted into place, then two 16-bit x 8-bit dot products per pixel
+                uint32_t x[STEP + 1];
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile[r]) + (at >> 2);
+#pragma unroll
+                for (int i = 0; i <= STEP; ++i)
+                    x[i] = wp[i];
+                const uint32_t sh = (at & 3u) * 8u;
+#pragma unroll
+                for (int i = 0; i < STEP; ++i)
+                    x[i] = __funnelshift_r(x[i], x[i + 1], sh);
+                w = gray4<STEP>(x);
+            } else {
+                w = uint32_t(bytes[0]) | uint32_t(bytes[STEP]) << 8 | uint32_t(bytes[2 * STEP]) << 16 | uint32_t(bytes[3 * STEP]) << 24;
+            }
             __stcs(reinterpret_cast<uint32_t *>(out), w);
         } else {
             for (uint32_t i = 0; i < 4 && e0 + i < n; ++i)
