@@ -110,6 +110,19 @@ int frames_upload_prepare(cvvp_ctx *ctx, const uint8_t *frames, long long n, siz
                           uint8_t *d_dst, size_t dst_stride)
 {
     const Band band = crop_band(f);
+    if (f.mode == CVVP_FRAMES_AS_IS && f.crop_x == 0 && f.crop_width == f.src_width) {
+        // full-width rows kept as they are (the default of VidBgPack on a colour video): the band IS the prepared frame,
+        // the copy engine puts it in place and no kernel runs
+        int rc = raw_stage_ensure(ctx, 16);
+        if (rc != CVVP_OK)
+            return rc;
+        RawStage &r = ctx->raw;
+        CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(d_dst, dst_stride, frames + band.offset, frame_stride, band.bytes, size_t(n),
+                                            cudaMemcpyHostToDevice, ctx->copy));
+        CVVP_CUDA_OK(ctx, cudaEventRecord(r.up[0], ctx->copy));
+        CVVP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->compute, r.up[0], 0));
+        return CVVP_OK;
+    }
     long long per = (long long)(kRawChunkBytes / band.pitch);
     if (per < 1)
         per = 1;

@@ -119,6 +119,26 @@ def test_median_of_decoded_frames_matches_oracle(gpu_ctx, oracle_median, mode):
     assert np.array_equal(got, oracle_median(prepared))
 
 
+def test_colour_median_of_full_width_rows_needs_no_kernel(gpu_ctx, oracle_median):
+    """VidBgPack's default on a colour video (no grayscale flag) with a crop that keeps full rows: the copy engine places
+    the band in the stack, no preparation kernel is launched, and the median is the oracle's"""
+    rng = np.random.default_rng(31)
+    n, h, w = 33, 50, 70
+    frames = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    crop = (0, 6, w, 37)
+    fmt = _cabi.FrameFormat.of((h, w, 3), fo.AS_IS, crop)
+    prepared = fo.prepare_frames(frames, crop, fo.AS_IS)
+    assert np.array_equal(gpu_ctx.frames_prepare(frames, fmt), prepared)
+    nelem = 37 * w * 3
+    gpu_ctx.median_begin(nelem, n)
+    l0 = gpu_ctx.launch_count
+    for i in range(0, n, 10):
+        gpu_ctx.median_push_source(frames[i:i + 10], fmt)
+    assert gpu_ctx.launch_count == l0
+    got = gpu_ctx.median_finish(nelem=nelem).reshape(37, w, 3)
+    assert np.array_equal(got, oracle_median(prepared))
+
+
 def test_median_push_source_rejects_a_mismatching_job(gpu_ctx):
     fmt = _cabi.FrameFormat.of((8, 8, 3), fo.RGB2GRAY)
     gpu_ctx.median_begin(65, 4)
