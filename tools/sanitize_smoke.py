@@ -86,6 +86,33 @@ def main():
             ctx.highlight_end()
             assert np.array_equal(got, want), ("highlight", path)
     print("highlight ok", flush=True)
+    # frame source and the asynchronous queue: every mode, odd crops, a misaligned segment end; both highlight builds
+    import frame_cases
+    from oracle import frames_oracle as fo
+
+    for name, frames, crop, mode in frame_cases.cases()[:20]:
+        fmt = _cabi.FrameFormat.of(frames.shape[1:], mode, crop)
+        assert np.array_equal(ctx.frames_prepare(frames, fmt), fo.prepare_frames(frames, crop, mode)), name
+    frame, p = hl_cases.random_case(3)
+    colour = np.stack([frame, frame, frame], axis=-1)[None].repeat(5, axis=0)
+    want = ho.highlight_objects(frame.copy(), p)
+    for variant in ("small", "large"):
+        os.environ["CVVP_HL_VARIANT"] = variant
+        ctx.highlight_begin(p.background, np.ascontiguousarray(p.struct_element), p.threshold, p.threshold_lo,
+                            p.threshold_hi, p.min_size_hyst, p.min_size_threshold, p.width_border)
+        ctx.highlight_queue_begin(2, 2, _cabi.FrameFormat.of(colour.shape[1:], _cabi.FRAMES_CHANNEL0), 16)
+        got = []
+        for i in range(0, 5, 2):
+            if ctx.highlight_queue_pending() == 2:
+                got.append(ctx.highlight_next()[0].copy())
+            ctx.highlight_submit(colour[i:i + 2])
+        while ctx.highlight_queue_pending():
+            got.append(ctx.highlight_next()[0].copy())
+        ctx.highlight_end()
+        got = np.concatenate(got)
+        assert got.shape[0] == 5 and all(np.array_equal(g, want) for g in got), ("queue", variant)
+    os.environ.pop("CVVP_HL_VARIANT")
+    print("frame source and queue ok", flush=True)
     ctx.close()
 
 
