@@ -275,7 +275,8 @@ CVVP_API int cvvp_highlight_submit(cvvp_ctx *ctx, const uint8_t *frames, long lo
 CVVP_API int cvvp_highlight_queue_ready(cvvp_ctx *ctx);
 /* Wait for the oldest pending batch; copy its *n_out masks to masks_out (mask i at masks_out + i*out_stride) and,
  * when the queue was begun with max_comps > 0 and the pointers are not NULL, its components
- * (comps_out[i*max_comps + k]) and counts (ncomps_out[i]).  CVVP_ERR_STATE when nothing is pending. */
+ * (comps_out[i*max_comps + k]) and counts (ncomps_out[i]).  The buffers must have room for max_batch frames (the
+ * batch's size is only known on return).  CVVP_ERR_STATE when nothing is pending. */
 CVVP_API int cvvp_highlight_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_stride, long long *n_out,
                                  cvvp_component *comps_out, int *ncomps_out);
 /* drains and frees the ring (pending results are dropped) */
