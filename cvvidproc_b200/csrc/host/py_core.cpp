@@ -494,6 +494,8 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
                 batch->rows = r;
                 batch->cols = c;
                 batch->channels = ch;
+                // one allocation per batch: a vector that grows frame by frame re-copies every decoded frame
+                batch->data.reserve(std::size_t(std::min(batch_frames, num_frames - consumed)) * r * c * ch);
             }
             if (!on_device) {
                 CVVP_ASSERT_MSG(ch == 1, "TrackObjects needs single-channel frames: set grayscale or vid_is_grayscale "
