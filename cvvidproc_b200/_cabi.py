@@ -74,6 +74,8 @@ def load():
         "cvvp_highlight_frames_in_flight": (i32, [vp, C.POINTER(i32)]),
         "cvvp_synth_frames_device": (i32, [vp, vp, sz, i32, i32, i32, i32, i64, i64, u32, i32, vp]),
         "cvvp_median_shard_begin": (i32, [vp, sz, i32, i32]),
+        "cvvp_median_shard_begin_frames": (i32, [vp, sz, i32, i32, i64]),
+        "cvvp_median_shard_unresolved": (i32, [vp, vp, C.POINTER(i64)]),
         "cvvp_median_shard_export": (i32, [vp, vp]),
         "cvvp_median_shard_import": (i32, [vp, i32, vp]),
         "cvvp_median_shard_attach": (i32, [vp, i32, vp]),
@@ -305,8 +307,17 @@ class Context:
     # -- frame-sharded median (one context per rank) ----------------------------------------
     IPC_HANDLE_BYTES = 64
 
-    def median_shard_begin(self, nelem: int, rank: int, world: int):
-        self._check(self._lib.cvvp_median_shard_begin(self._h, nelem, rank, world))
+    def median_shard_begin(self, nelem: int, rank: int, world: int, max_rank_frames: int | None = None):
+        if max_rank_frames is None:
+            self._check(self._lib.cvvp_median_shard_begin(self._h, nelem, rank, world))
+        else:
+            self._check(self._lib.cvvp_median_shard_begin_frames(self._h, nelem, rank, world, max_rank_frames))
+
+    def median_shard_unresolved(self, stream: int = 0) -> int:
+        """elements the one-pass form (phases 4, 5) left undecided; waits for the stream"""
+        v = C.c_longlong()
+        self._check(self._lib.cvvp_median_shard_unresolved(self._h, stream or None, C.byref(v)))
+        return int(v.value)
 
     def median_shard_export(self) -> bytes:
         buf = C.create_string_buffer(self.IPC_HANDLE_BYTES)

@@ -48,6 +48,7 @@ struct ShardPush {
     const uint32_t *accum; // counts of this rank's earlier frame chunks (8 words per element), or nullptr
     uint32_t slice;
     uint32_t stage; // 1: round 1 stages a tile's count vectors in shared memory and stores them 512 B per warp (peer owners)
+    const uint32_t *gate; // not NULL: the kernel returns at once when *gate == 0 (fallback rounds of a window job)
 };
 struct MedianShard; // median_shard.cu
 
@@ -136,8 +137,8 @@ int median_pipe_launch(cvvp_ctx *ctx, const CUtensorMap &tmap, int log2s, uint8_
                        uint32_t nst, int mode, const ShardPush &push, cudaStream_t stream);
 // median_shard.cu
 void median_shard_release(cvvp_ctx *ctx);
-int median_two_pass(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
-                    uint8_t *d_out, cudaStream_t stream);
+int median_long_stack(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
+                      uint8_t *d_out, cudaStream_t stream, int window);
 long long median_two_pass_max_frames();
 // highlight.cu
 void highlight_release(cvvp_ctx *ctx);

@@ -35,13 +35,19 @@ int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, siz
     // Up to 2048 frames the on-chip select reads every byte once at 128- or 64-byte tiles.  Longer stacks would need
     // 32- / 16-byte tiles (1.5 TB/s and less): two counting passes in chunks of 1024 frames at full tile width are
     // faster there, and reach 16 x 65535 frames (median_shard.cu).  CVVP_MEDIAN_TWO_PASS=0/1 forces either path (tests).
+    // Long stacks first try ONE pass of window counting (median_pipe_kernel MODE 3: every 1024-frame launch counts
+    // its frames in an 8-value window around its own pilot median; the owner kernel names the median wherever it
+    // lies inside every launch's window) and run the two counting passes only for frames whose elements were not all
+    // resolved -- on the device, gated by a flag, so the call stays asynchronous.  CVVP_MEDIAN_WINDOW=0 skips the
+    // window pass (tests hold both to the oracle).
     const char *force = getenv("CVVP_MEDIAN_TWO_PASS");
     const bool two_pass = force ? force[0] == '1' : nframes > 2048;
     if (two_pass || nframes > median_max_frames()) {
         if (nframes > median_two_pass_max_frames())
             return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: %lld frames exceed the supported maximum (%lld)", nframes,
                         median_two_pass_max_frames());
-        return median_two_pass(ctx, d_frames, nframes, nelem, frame_stride, d_out, stream);
+        const char *win = getenv("CVVP_MEDIAN_WINDOW");
+        return median_long_stack(ctx, d_frames, nframes, nelem, frame_stride, d_out, stream, win ? win[0] != '0' : 1);
     }
     return median_launch_mode(ctx, d_frames, nframes, nelem, frame_stride, d_out, 0, ShardPush{}, stream);
 }

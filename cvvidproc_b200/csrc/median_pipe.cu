@@ -25,6 +25,11 @@
 // its own lane id ^ (low column bits held in its warp id).  Both patterns touch 8 distinct 16-byte columns per
 // quarter-warp: bank-conflict free.
 //
+// MODE 3 (window counting, see below) hands the single plane buffer back ROW BY ROW: a selector warp bumps the
+// monotonic counter rows_free[j] as soon as its lanes hold row j (stages G*j .. G*j + G-1) in registers, and the
+// transposer of stage st of the next tile only waits for rows_free[st / G] -- the next tile's transposition runs right
+// behind the selectors instead of after them, and monotonic counters cannot alias the way a parity wait can.
+//
 // Selectors walk through every tile in order, so their planes_full waits are one phase away by induction.  A
 // transposer can reach a buffer two fills ahead when tiles are tiny, so before its planes_empty parity wait it
 // checks a monotonic shared counter of completed selects; after that the parity wait is at most one phase away.
@@ -68,6 +73,52 @@ __device__ __forceinline__ void nibble_counts(uint32_t (&acc)[8], uint32_t p3, u
 #undef CVVP_MT
 }
 
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void red_release_shared_inc(uint32_t *p)
+{
+    asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+}
+
+// Window counting (MODE 3) of one plane row: lo / hi = bit planes 0..3 / 4..7 of one element over 32 frame slots,
+// fb[b] = bit b of the window base replicated over the word.  d = v - base is formed bit-sliced (one LOP3 for the
+// difference bit, one for the borrow); the final borrow marks the slots below the window (v < base), the OR of
+// difference bits 3..7 the slots above it.  acc[c] += count(d == 2c) | count(d == 2c + 1) << 16, below += count(v < base).
+// vm masks rows beyond the tile's stage count (they hold garbage).
+__device__ __forceinline__ void window_row(uint32_t (&acc)[4], uint32_t &below, const uint4 &lo, const uint4 &hi,
+                                           const uint32_t (&fb)[8], uint32_t vm)
+{
+    const uint32_t a[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t d[8];
+    uint32_t bw = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        d[b] = lop3<0x96>(a[b], fb[b], bw); // a ^ f ^ borrow
+        bw = lop3<0x8E>(a[b], fb[b], bw);   // majority(~a, f, borrow)
+    }
+    const uint32_t above = lop3<0xFE>(lop3<0xFE>(d[3], d[4], d[5]), d[6], d[7]);
+    const uint32_t in = lop3<0x01>(above, bw, ~vm); // ~(above | below | invalid)
+    below += __popc(bw & vm);
+    const uint32_t m0 = in & ~d[2], m1 = in & d[2];
+    acc[0] += __popc(lop3<0x10>(m0, d[1], d[0])) + (__popc(lop3<0x20>(m0, d[1], d[0])) << 16);
+    acc[1] += __popc(lop3<0x40>(m0, d[1], d[0])) + (__popc(lop3<0x80>(m0, d[1], d[0])) << 16);
+    acc[2] += __popc(lop3<0x10>(m1, d[1], d[0])) + (__popc(lop3<0x20>(m1, d[1], d[0])) << 16);
+    acc[3] += __popc(lop3<0x40>(m1, d[1], d[0])) + (__popc(lop3<0x80>(m1, d[1], d[0])) << 16);
+}
+
 // LOG2S : log2(32-frame sub-blocks per stage per element); P = 128 >> LOG2S elements per tile
 // JT    : stages per select thread (compile time)
 // NSELW : select warps, 8 (two stage classes, two plane buffers) or 16 (four stage classes, one plane buffer)
@@ -76,6 +127,12 @@ __device__ __forceinline__ void nibble_counts(uint32_t (&acc)[8], uint32_t p3, u
 //             element's owner rank through peer memory
 //         2 = round 2: 16-bin counts of the LOW nibble among the frames whose high nibble equals the globally selected
 //             one (push.sel[e] & 15), pushed the same way
+//         3 = frame-sharded job / long stack in ONE pass over the frames: every element's select threads first pick a
+//             PILOT median of two of their plane rows (256 of the launch's <= 1024 frames) on chip, then count all
+//             frames in the 8-value window [pilot - 4, pilot + 3] (8 bins) and below it, and push
+//             {bins, below, window base, frame count} (32 B) to the element's owner.  The owner can name the median of
+//             ALL sources exactly whenever it lies inside every source's window (shard_window_final_kernel); elements
+//             where it does not are flagged and the job falls back to rounds 1 + 2.  (NSELW = 16 only.)
 template <int LOG2S, int JT, int NSELW, int MODE>
 __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     median_pipe_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ out, const uint32_t nelem,
@@ -100,10 +157,14 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     uint64_t *planes_full = bars + kRing;      // [2]
     uint64_t *planes_empty = bars + kRing + 2; // [2]
     volatile uint32_t *sel_done = reinterpret_cast<volatile uint32_t *>(bars + kRing + 4); // [2] selects completed
+    uint32_t *rows_free = reinterpret_cast<uint32_t *>(bars + kRing + 4) + 4; // [8] MODE 3: select warps done with row j
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
     const uint32_t lane = tid & 31;
+
+    if (MODE != 0 && push.gate && __ldcg(push.gate) == 0u)
+        return; // fallback rounds of a window job in which every element was resolved
 
     if (tid == 0) {
         prefetch_tmap(&tmap);
@@ -114,6 +175,8 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
             mbar_init(&planes_empty[i], NSELW);
             sel_done[i] = 0;
         }
+        for (int i = 0; i < 8; ++i)
+            rows_free[i] = 0;
         fence_mbar_init();
     }
     __syncthreads();
@@ -176,11 +239,31 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
             // r[8*p + b] = bit plane b of element 4*c+p over this lane's 32 frame slots.
             // Selectors must be done with the previous fill of this buffer.  Pre-check (almost always already
             // true): the fill before that one is finished, which makes the parity wait at most one phase away.
-            if (q >= 2u) {
-                while (sel_done[buf] < NSELW * (q - 1u))
-                    __nanosleep(64);
+            if constexpr (MODE == 3) {
+                // every select warp holds row st / G of the previous tile in registers (monotonic counter: no parity)
+                if (q >= 1u) {
+                    if (lane == 0) {
+                        const uint32_t need = NSELW * q;
+                        const uint32_t *cnt = rows_free + st / G;
+                        if (ld_acquire_shared(cnt) < need) {
+                            const uint64_t t0 = global_timer_ns();
+                            uint32_t spins = 0;
+                            while (ld_acquire_shared(cnt) < need) {
+                                __nanosleep(32);
+                                if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > 2000000000ull)
+                                    __trap();
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else {
+                if (q >= 2u) {
+                    while (sel_done[buf] < NSELW * (q - 1u))
+                        __nanosleep(64);
+                }
+                mbar_wait(&planes_empty[buf], (q & 1u) ^ 1u);
             }
-            mbar_wait(&planes_empty[buf], (q & 1u) ^ 1u);
             const uint32_t col = lane ^ (st & (G - 1u));
             uint4 *dst = reinterpret_cast<uint4 *>(planes + buf * kBufWords + st * 1024u) + col;
 #pragma unroll
@@ -216,7 +299,132 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
         const uint32_t q = (NBUF == 2) ? (it >> 1) : it;
         mbar_wait(&planes_full[buf], q & 1u);
         const uint4 *base = reinterpret_cast<const uint4 *>(planes + buf * kBufWords + s_g * 1024u) + s_p * 64u + s_col;
-        if constexpr (MODE != 0) {
+        if constexpr (MODE == 3) {
+            // ---- window counting: pilot median of two plane rows, then 8 bins around it over all rows ----
+            static_assert(MODE != 3 || NSELW == 16, "window counting uses the single plane buffer");
+            constexpr int JP = JT >= 2 ? 2 : 1; // pilot rows: 0 and JT / 2
+            auto pilot_row = [](int i) { return i == 0 ? 0 : JT / 2; };
+            const size_t e = size_t(tile) * P + s_elem;
+            uint4 plo[JP], phi[JP];
+#pragma unroll
+            for (int i = 0; i < JP; ++i) {
+                plo[i] = base[pilot_row(i) * (G * 256)];
+                phi[i] = base[pilot_row(i) * (G * 256) + 32];
+            }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < JP; ++i)
+                    red_release_shared_inc(rows_free + pilot_row(i));
+            }
+            // pilot rank: the pilot stages are G*j .. G*j + G-1 of the pilot rows; their real frames and pad slots
+            uint32_t p_real = 0, p_slots = 0;
+#pragma unroll
+            for (int i = 0; i < JP; ++i) {
+#pragma unroll
+                for (uint32_t g = 0; g < G; ++g) {
+                    const uint32_t stg = G * pilot_row(i) + g;
+                    if (stg < nst) {
+                        const uint32_t f0 = stg * kSlotsPerStage;
+                        p_slots += kSlotsPerStage;
+                        p_real += nframes > f0 ? min(nframes - f0, uint32_t(kSlotsPerStage)) : 0u;
+                    }
+                }
+            }
+            uint32_t med = 0;
+            {
+                uint32_t alive[JP];
+#pragma unroll
+                for (int i = 0; i < JP; ++i)
+                    alive[i] = (G * pilot_row(i) + s_g) < nst ? 0xFFFFFFFFu : 0u;
+                uint32_t k = p_real / 2u + (p_slots - p_real);
+#pragma unroll
+                for (int bit = 7; bit >= 0; --bit) {
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int i = 0; i < JP; ++i) {
+                        const uint4 &q4 = bit >= 4 ? phi[i] : plo[i];
+                        const uint32_t wv = (bit & 3) == 0 ? q4.x : (bit & 3) == 1 ? q4.y : (bit & 3) == 2 ? q4.z : q4.w;
+                        cnt += __popc(alive[i] & ~wv);
+                    }
+                    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
+                    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
+                    if (LOG2S >= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 16);
+                    if (LOG2S >= 2) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 8);
+                    if (LOG2S >= 3) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 4);
+                    const bool one = k >= cnt;
+                    if (one) {
+                        k -= cnt;
+                        med |= 1u << bit;
+                    }
+                    const uint32_t flip = one ? 0u : 0xFFFFFFFFu;
+#pragma unroll
+                    for (int i = 0; i < JP; ++i) {
+                        const uint4 &q4 = bit >= 4 ? phi[i] : plo[i];
+                        const uint32_t wv = (bit & 3) == 0 ? q4.x : (bit & 3) == 1 ? q4.y : (bit & 3) == 2 ? q4.z : q4.w;
+                        alive[i] &= (wv ^ flip);
+                    }
+                }
+            }
+            const uint32_t wbase = med >= 4u ? min(med - 4u, 248u) : 0u; // window = [wbase, wbase + 7]
+            uint32_t fb[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+                fb[b] = 0u - ((wbase >> b) & 1u);
+            uint32_t acc[4] = {0, 0, 0, 0};
+            uint32_t below = 0;
+            // the pilot rows are already in registers
+#pragma unroll
+            for (int i = 0; i < JP; ++i)
+                window_row(acc, below, plo[i], phi[i], fb, (G * pilot_row(i) + s_g) < nst ? 0xFFFFFFFFu : 0u);
+            // the other rows: load (one row ahead), hand the row back, count
+            constexpr int NR = JT - JP; // rows left
+            if constexpr (NR > 0) {
+                auto row_of = [](int r) { return r + 1 + (r + 1 >= JT / 2 ? 1 : 0); }; // skips 0 and JT / 2
+                uint4 nlo = base[row_of(0) * (G * 256)], nhi = base[row_of(0) * (G * 256) + 32];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const int j = row_of(r);
+                    const uint4 clo = nlo, chi = nhi;
+                    if (r + 1 < NR) {
+                        nlo = base[row_of(r + 1) * (G * 256)];
+                        nhi = base[row_of(r + 1) * (G * 256) + 32];
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                        red_release_shared_inc(rows_free + j); // row j was loaded one iteration ago
+                    window_row(acc, below, clo, chi, fb, (G * uint32_t(j) + s_g) < nst ? 0xFFFFFFFFu : 0u);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                uint32_t v = c < 4 ? acc[c] : below;
+                v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+                v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+                if (LOG2S >= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, 16);
+                if (LOG2S >= 2) v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+                if (LOG2S >= 3) v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+                if (c < 4)
+                    acc[c] = v;
+                else
+                    below = v;
+            }
+            // the zero-filled pad slots were counted as value 0: in bin 0 when the window starts at 0, else below it
+            const uint32_t pad = nst * kSlotsPerStage - nframes;
+            if (wbase == 0u)
+                acc[0] -= pad;
+            else
+                below -= pad;
+            if ((lane >> kColBits) == 0u && e < nelem) {
+                const uint32_t owner = uint32_t(e) / push.slice;
+                uint32_t *dst = push.dst[owner] + (size_t(e) - size_t(owner) * push.slice) * 8u;
+                const uint2 v = s_g == 0 ? make_uint2(acc[0], acc[1])
+                              : s_g == 1 ? make_uint2(acc[2], acc[3])
+                              : s_g == 2 ? make_uint2(below, wbase)
+                                         : make_uint2(nframes, 0u);
+                *reinterpret_cast<uint2 *>(dst + 2u * s_g) = v;
+            }
+        } else if constexpr (MODE != 0) {
             // ---- frame-sharded job: nibble counts of this rank's frames, pushed to the owner of the element ----
             const size_t e = size_t(tile) * P + s_elem;
             uint32_t acc[8];
@@ -405,7 +613,7 @@ int launch_pipe_variant(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, 
     constexpr uint32_t G = NSELW / 4;
     constexpr uint32_t NBUF = (NSELW == 8) ? 2 : 1;
     const uint32_t ntiles = (nelem + P - 1) / P;
-    const size_t smem_bytes = size_t(kRing) * kStageBytes + size_t(NBUF) * (G * JT * 4096u) + size_t(kRing + 4) * 8 + 16;
+    const size_t smem_bytes = size_t(kRing) * kStageBytes + size_t(NBUF) * (G * JT * 4096u) + size_t(kRing + 4) * 8 + 16 + 32;
     if (smem_bytes > ctx->smem_optin)
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: tile does not fit shared memory");
     auto kern = median_pipe_kernel<LOG2S, JT, NSELW, MODE>;
@@ -460,6 +668,11 @@ int dispatch_mode(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, uint32
     case 0: return dispatch_bufs<LOG2S, 0>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
     case 1: return dispatch_bufs<LOG2S, 1>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
     case 2: return dispatch_bufs<LOG2S, 2>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
+    case 3:
+        if constexpr (LOG2S == 0)
+            return dispatch_jt<0, 16, 3>(ctx, tmap, d_out, nelem, nframes, nst, push, stream);
+        else
+            return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: window counting takes at most 1024 frames per launch");
     default: return fail(ctx, CVVP_ERR_INVALID, "median: bad kernel mode %d", mode);
     }
 }

@@ -20,6 +20,17 @@
 //   phase 3  owner      : sums, picks the low nibble l with cum(l) > k'; stores the result byte h << 4 | l into
 //                         EVERY rank's result image (all-gather by peer stores)
 //
+// ONE-PASS FORM (phases 4 and 5, tried first).  The two rounds above read every frame twice.  Phase 4
+// (median_pipe_kernel MODE 3) reads them once: each launch (<= 1024 frames of a rank) picks, per element, a pilot
+// median of 256 of its own frames on chip and counts ALL its frames in the 8-value window [pilot - 4, pilot + 3]
+// and below it; the 32-byte record {8 bins, below, window base, frame count} goes to the element's owner like the
+// nibble counts do.  Phase 5 (shard_window_final_kernel, owner): the cumulative count of all sources is exact on the
+// intersection [lo - 1, hi] of their windows, so whenever G(lo - 1) <= N/2 < G(hi) the median is the first value
+// there with G(v) > N/2 -- the reference's rule (:160-166) -- and it is stored into every rank's result image.
+// Elements whose median lies outside some source's window (sources with very different content) are counted into
+// every rank's `unresolved` word, and the job then runs phases 0..3 (exact for any input).  A video background
+// resolves everywhere; the result is bit-identical either way.
+//
 // Between phases the caller places a cross-rank barrier on the stream (a kernel's peer stores are complete when the
 // kernel is; the barrier orders them before the peer's next kernel).  No kernel ever waits for another rank, so ranks
 // can also be emulated one after another on a single device (tests).  Traffic per element per rank: 2 x 32 B out,
@@ -47,6 +58,9 @@ struct MedianShard {
     uint32_t *accum{nullptr}; // [nelem][8 words]: running counts of this rank's frame chunks (allocated on first use)
     int spr{1}; // count slots per rank: a rank with more than 65535 frames pushes one 16-bit count vector per 65535 frames,
                 // the owners sum world * spr vectors in 32 bits (world * spr <= kMaxShardRanks)
+    int wsubs{1}; // window records per rank (one per launch of <= 1024 frames) the first receive area has room for
+    int cslots{1}; // record slots per rank of the first receive area = max(spr, wsubs)
+    size_t off_flag{0}; // one word: elements the window pass left unresolved (summed over all owners)
 };
 
 // frames one launch of the counting kernel takes at full tile width (128-byte TMA boxes): 32 stages x 32 frames
@@ -56,13 +70,22 @@ constexpr long long kSlotFrames = 65535; // 16-bit counts per slot
 namespace
 {
 struct OwnerArgs {
-    const uint32_t *counts; // this rank's receive area of the round: [world (count vectors)][slice][8 words]
-    uint32_t slice, world, rank;
+    const uint32_t *counts; // this rank's receive area of the round: [rank][slot][slice][8 words]
+    uint32_t slice, world, rank; // world = vectors / records to sum = ranks x used slots per rank
+    uint32_t used, slots;        // slots a rank uses this round / slots per rank in the area
     uint32_t nranks;        // ranks the decisions are broadcast to
     uint32_t owned;         // elements this rank owns
     uint32_t *sel[kMaxShardRanks];    // every rank's sel array
     uint8_t *result[kMaxShardRanks];  // every rank's result image
+    uint32_t *flag[kMaxShardRanks];   // window pass: every rank's `unresolved` word
+    const uint32_t *gate;             // not NULL: return at once when *gate == 0 (fallback rounds, nothing unresolved)
 };
+
+// the s-th vector / record of the round lives in slot (s % used) of rank (s / used)
+__device__ __forceinline__ size_t src_slot(const OwnerArgs &A, uint32_t s)
+{
+    return A.used == A.slots ? size_t(s) : size_t(s / A.used) * A.slots + (s % A.used);
+}
 
 __device__ __forceinline__ void add_counts(uint32_t (&cnt)[16], const uint32_t *p)
 {
@@ -79,6 +102,8 @@ __device__ __forceinline__ void add_counts(uint32_t (&cnt)[16], const uint32_t *
 // phase 1: one thread per owned element
 __global__ void __launch_bounds__(256) shard_pick_kernel(const __grid_constant__ OwnerArgs A)
 {
+    if (A.gate && __ldcg(A.gate) == 0u)
+        return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < A.owned) {
         uint32_t cnt[16];
@@ -86,7 +111,7 @@ __global__ void __launch_bounds__(256) shard_pick_kernel(const __grid_constant__
         for (int b = 0; b < 16; ++b)
             cnt[b] = 0;
         for (uint32_t src = 0; src < A.world; ++src)
-            add_counts(cnt, A.counts + (size_t(src) * A.slice + i) * 8u);
+            add_counts(cnt, A.counts + (src_slot(A, src) * A.slice + i) * 8u);
         uint32_t total = 0;
 #pragma unroll
         for (int b = 0; b < 16; ++b)
@@ -116,6 +141,8 @@ __global__ void __launch_bounds__(256) shard_pick_kernel(const __grid_constant__
 // phase 3: one thread per 4 owned elements (one 32-bit store of result bytes per rank)
 __global__ void __launch_bounds__(256) shard_final_kernel(const __grid_constant__ OwnerArgs A)
 {
+    if (A.gate && __ldcg(A.gate) == 0u)
+        return;
     const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
     if (i4 < A.owned) {
         const size_t e0 = size_t(A.rank) * A.slice + i4;
@@ -127,7 +154,7 @@ __global__ void __launch_bounds__(256) shard_final_kernel(const __grid_constant_
             for (int b = 0; b < 16; ++b)
                 cnt[b] = 0;
             for (uint32_t src = 0; src < A.world; ++src)
-                add_counts(cnt, A.counts + (size_t(src) * A.slice + i4 + q) * 8u);
+                add_counts(cnt, A.counts + (src_slot(A, src) * A.slice + i4 + q) * 8u);
             const uint32_t s = __ldcg(A.sel[A.rank] + e0 + q);
             const uint32_t h = s & 15u, k = s >> 8;
             uint32_t l = 15u, cum = 0u;
@@ -152,6 +179,93 @@ __global__ void __launch_bounds__(256) shard_final_kernel(const __grid_constant_
             }
         }
     }
+    __threadfence_system();
+}
+
+// phase 5: window records of every source -> result bytes.  One thread per 4 owned elements.  Record of source s for
+// owned element i: counts[(s * slice + i) * 8 ..]: words 0..3 = bins 0..7 (16 bits each), 4 = frames below the
+// window, 5 = window base, 6 = frames of the source (0: the source is empty and is skipped).
+__global__ void __launch_bounds__(256) shard_window_final_kernel(const __grid_constant__ OwnerArgs A)
+{
+    __shared__ uint32_t delta[9][256]; // per thread: frames whose value first counts at window position i
+    __shared__ uint32_t unresolved;
+    if (threadIdx.x == 0)
+        unresolved = 0;
+    __syncthreads();
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    uint32_t bad = 0;
+    if (i4 < A.owned) {
+        const size_t e0 = size_t(A.rank) * A.slice + i4;
+        uint32_t packed = 0;
+        const uint32_t n = min(4u, A.owned - i4);
+        for (uint32_t q = 0; q < n; ++q) {
+            // pass 1: N, and the intersection [lo, hi] of the sources' windows
+            uint32_t total = 0, lo = 0, hi = 255;
+            for (uint32_t src = 0; src < A.world; ++src) {
+                const uint4 t = __ldcg(reinterpret_cast<const uint4 *>(A.counts + (src_slot(A, src) * A.slice + i4 + q) * 8u) + 1);
+                if (t.z == 0u)
+                    continue;
+                total += t.z;
+                lo = max(lo, t.y);
+                hi = min(hi, t.y + 7u);
+            }
+            const uint32_t k = total / 2u; // halfway rank: first value with cumulative count > N / 2  (:160-166)
+            uint32_t med = 0;
+            bool ok = false;
+            if (total != 0u && lo <= hi) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i)
+                    delta[i][threadIdx.x] = 0;
+                uint32_t cum = 0; // G(lo - 1), then G(lo - 1 + i)
+                for (uint32_t src = 0; src < A.world; ++src) {
+                    const uint4 *rec = reinterpret_cast<const uint4 *>(A.counts + (src_slot(A, src) * A.slice + i4 + q) * 8u);
+                    const uint4 t = __ldcg(rec + 1);
+                    if (t.z == 0u)
+                        continue;
+                    const uint4 b = __ldcg(rec);
+                    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+                    const int o = int(lo - t.y); // window position of lo in this source (0..7)
+                    cum += t.x;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t cnt = (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xFFFFu);
+                        const int pos = c - o + 1; // value base + c is counted by G(lo - 1 + i) for every i >= pos
+                        delta[pos > 0 ? pos : 0][threadIdx.x] += cnt;
+                    }
+                }
+                cum += delta[0][threadIdx.x];
+                const uint32_t span = hi - lo + 1u; // G is exact for i = 0 .. span
+                if (cum <= k) {
+                    for (uint32_t i = 1; i <= span; ++i) {
+                        cum += delta[i][threadIdx.x];
+                        if (cum > k) {
+                            med = lo - 1u + i;
+                            ok = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            if (!ok)
+                ++bad;
+            packed |= med << (8u * q);
+        }
+        for (uint32_t r = 0; r < A.nranks; ++r) {
+            uint8_t *dst = A.result[r] + e0;
+            if (n == 4u) {
+                *reinterpret_cast<uint32_t *>(dst) = packed;
+            } else {
+                for (uint32_t q = 0; q < n; ++q)
+                    dst[q] = uint8_t(packed >> (8u * q));
+            }
+        }
+    }
+    if (bad)
+        atomicAdd(&unresolved, bad);
+    __syncthreads();
+    if (threadIdx.x == 0 && unresolved != 0u)
+        for (uint32_t r = 0; r < A.nranks; ++r)
+            atomicAdd_system(A.flag[r], unresolved);
     __threadfence_system();
 }
 
@@ -205,7 +319,7 @@ void median_shard_release(cvvp_ctx *ctx)
     shard_destroy(ctx, ctx->big);
 }
 
-static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, int spr, MedianShard **out)
+static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, int spr, int wsubs, MedianShard **out)
 {
     MedianShard *sh = new (std::nothrow) MedianShard();
     if (!sh)
@@ -213,14 +327,19 @@ static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, int sp
     sh->rank = rank;
     sh->world = world;
     sh->spr = spr;
+    sh->wsubs = wsubs < 1 ? 1 : wsubs;
+    sh->cslots = std::max(sh->spr, sh->wsubs);
     sh->nelem = nelem;
     sh->slice = uint32_t(round_up((nelem + size_t(world) - 1) / size_t(world), 128));
-    const size_t counts_bytes = size_t(world) * size_t(spr) * sh->slice * 32u;
+    // the first receive area holds the round-1 count vectors (spr per rank) or the window records (wsubs per rank)
+    const size_t counts1_bytes = size_t(world) * size_t(sh->cslots) * sh->slice * 32u;
+    const size_t counts2_bytes = size_t(world) * size_t(spr) * sh->slice * 32u;
     sh->off_c1 = 0;
-    sh->off_c2 = counts_bytes;
-    sh->off_sel = 2 * counts_bytes;
+    sh->off_c2 = counts1_bytes;
+    sh->off_sel = counts1_bytes + counts2_bytes;
     sh->off_res = sh->off_sel + round_up(nelem * 4u, 256);
-    sh->bytes = sh->off_res + round_up(nelem, 256);
+    sh->off_flag = sh->off_res + round_up(nelem, 256);
+    sh->bytes = sh->off_flag + 256;
     if (cudaMalloc(reinterpret_cast<void **>(&sh->buf), sh->bytes) != cudaSuccess) {
         cudaGetLastError();
         const size_t wanted = sh->bytes;
@@ -280,10 +399,48 @@ static int shard_count_slot(cvvp_ctx *ctx, MedianShard *sh, int phase, const uin
     return CVVP_OK;
 }
 
+// Window counting (phase 4) of this rank's frames: launches of <= 1024 frames, each into its own record slot
+// (rank * cslots + j) of every owner; slots beyond the launches receive empty records (frame count 0).
+static int shard_window_count(cvvp_ctx *ctx, MedianShard *sh, const uint8_t *d_frames, long long nframes, size_t frame_stride,
+                              cudaStream_t s)
+{
+    const long long nsub = nframes == 0 ? 0 : (nframes + kChunkFrames - 1) / kChunkFrames;
+    if (nsub > sh->wsubs)
+        return fail(ctx, CVVP_ERR_UNSUPPORTED,
+                    "median shard: %lld frames need %lld window records per rank, the job was begun with room for %d", nframes,
+                    nsub, sh->wsubs);
+    long long per = nsub ? (nframes + nsub - 1) / nsub : 0;
+    per = (per + 31) / 32 * 32; // whole plane words
+    if (per > kChunkFrames)
+        per = kChunkFrames;
+    CVVP_CUDA_OK(ctx, cudaMemsetAsync(sh->buf + sh->off_flag, 0, sizeof(uint32_t), s));
+    for (int j = 0; j < sh->wsubs; ++j) {
+        ShardPush push{};
+        const size_t off = sh->off_c1 + (size_t(sh->rank) * sh->cslots + size_t(j)) * sh->slice * 32u;
+        for (int r = 0; r < sh->world; ++r)
+            push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
+        push.slice = sh->slice;
+        const long long first = std::min<long long>(nframes, per * j);
+        const long long n = std::min<long long>(nframes - first, per);
+        if (n <= 0) {
+            const size_t cnt = sh->nelem * 2;
+            shard_zero_push_kernel<<<unsigned((cnt + 255) / 256), 256, 0, s>>>(push, uint32_t(sh->nelem));
+            CVVP_CUDA_OK(ctx, cudaGetLastError());
+            ctx->launches++;
+            continue;
+        }
+        const int rc = median_launch_mode(ctx, d_frames + size_t(first) * frame_stride, n, sh->nelem, frame_stride, nullptr, 3,
+                                          push, s);
+        if (rc != CVVP_OK)
+            return rc;
+    }
+    return CVVP_OK;
+}
+
 // One phase of a sharded job (see the file header).  d_result: where phase 3 stores this rank's copy of the result
 // bytes instead of its own exchange buffer (the one-rank two-pass path writes straight into the caller's image).
 static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t *d_frames, long long nframes,
-                       size_t frame_stride, uint8_t *d_result, cudaStream_t s)
+                       size_t frame_stride, uint8_t *d_result, cudaStream_t s, bool gated = false)
 {
     if (!all_peers_known(sh))
         return fail(ctx, CVVP_ERR_STATE, "median shard: not every peer buffer is mapped (import / attach all ranks first)");
@@ -292,18 +449,22 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
     if (nframes > kSlotFrames * sh->spr)
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "median shard: %lld frames on one rank exceed the %d x 16-bit counts (%lld)",
                     nframes, sh->spr, kSlotFrames * sh->spr);
+    const uint32_t *gate = gated ? reinterpret_cast<const uint32_t *>(sh->buf + sh->off_flag) : nullptr;
+    if (phase == 4)
+        return shard_window_count(ctx, sh, d_frames, nframes, frame_stride, s);
     if (phase == 0 || phase == 2) {
         // slot j of this rank takes frames [j * 65535, (j + 1) * 65535) (possibly none)
         for (int j = 0; j < sh->spr; ++j) {
             const long long f0 = std::min<long long>(nframes, kSlotFrames * j);
             const long long nf = std::min<long long>(nframes - f0, kSlotFrames);
             ShardPush push{};
-            const size_t off =
-                (phase == 0 ? sh->off_c1 : sh->off_c2) + (size_t(sh->rank) * sh->spr + size_t(j)) * sh->slice * 32u;
+            const size_t off = phase == 0 ? sh->off_c1 + (size_t(sh->rank) * sh->cslots + size_t(j)) * sh->slice * 32u
+                                          : sh->off_c2 + (size_t(sh->rank) * sh->spr + size_t(j)) * sh->slice * 32u;
             for (int r = 0; r < sh->world; ++r)
                 push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
             push.sel = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_sel);
             push.slice = sh->slice;
+            push.gate = gate;
             {
                 const char *e = getenv("CVVP_SHARD_STAGE"); // development switch; default: stage when owners are peers
                 push.stage = e ? (e[0] == '1') : (sh->world > 1);
@@ -314,11 +475,17 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
         }
         return CVVP_OK;
     }
-    if (phase == 1 || phase == 3) {
+    if (phase == 1 || phase == 3 || phase == 5) {
         OwnerArgs A{};
-        A.counts = reinterpret_cast<const uint32_t *>(sh->buf + (phase == 1 ? sh->off_c1 : sh->off_c2));
+        A.counts = reinterpret_cast<const uint32_t *>(sh->buf + (phase == 3 ? sh->off_c2 : sh->off_c1));
         A.slice = sh->slice;
-        A.world = uint32_t(sh->world * sh->spr); // count vectors to sum
+        // round 1 shares its receive area with the window records: cslots slots per rank, of which it uses spr
+        A.used = uint32_t(phase == 5 ? sh->wsubs : sh->spr);
+        A.slots = uint32_t(phase == 3 ? sh->spr : sh->cslots);
+        A.world = uint32_t(sh->world) * A.used;
+        A.gate = gate;
+        for (int r = 0; r < sh->world; ++r)
+            A.flag[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_flag);
         A.rank = uint32_t(sh->rank);
         A.nranks = uint32_t(sh->world);
         const size_t first = size_t(sh->rank) * sh->slice;
@@ -333,13 +500,15 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
             return CVVP_OK;
         if (phase == 1)
             shard_pick_kernel<<<(A.owned + 255) / 256, 256, 0, s>>>(A);
-        else
+        else if (phase == 3)
             shard_final_kernel<<<((A.owned + 3) / 4 + 255) / 256, 256, 0, s>>>(A);
+        else
+            shard_window_final_kernel<<<((A.owned + 3) / 4 + 255) / 256, 256, 0, s>>>(A);
         CVVP_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches++;
         return CVVP_OK;
     }
-    return fail(ctx, CVVP_ERR_INVALID, "median shard: phase must be 0..3");
+    return fail(ctx, CVVP_ERR_INVALID, "median shard: phase must be 0..5");
 }
 
 long long median_two_pass_max_frames()
@@ -348,23 +517,34 @@ long long median_two_pass_max_frames()
 }
 
 // Single-GPU median of a stack too long for the on-chip select at full tile width: the sharded job with ONE rank.
-// Two passes over the frames in chunks of <= 1024 at 128-byte tiles beat one pass at the 32- or 16-byte tiles the
-// on-chip select would need beyond 2048 frames.
-int median_two_pass(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
-                    uint8_t *d_out, cudaStream_t stream)
+// window != 0: one pass of window counting first (phases 4, 5); the two counting passes (phases 0..3) follow on the
+// stream GATED by the device-side `unresolved` word, i.e. they return at once when every element was resolved -- no
+// host round trip, the call stays asynchronous.  window == 0: the two counting passes only.  Either way two passes
+// over the frames in chunks of <= 1024 at 128-byte tiles beat one pass at the 32- or 16-byte tiles the on-chip
+// select would need beyond 2048 frames.
+int median_long_stack(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
+                      uint8_t *d_out, cudaStream_t stream, int window)
 {
     const int spr = int((nframes + kSlotFrames - 1) / kSlotFrames);
-    if (ctx->big && (ctx->big->nelem != nelem || ctx->big->spr < spr))
+    const int wsubs = window ? int((nframes + kChunkFrames - 1) / kChunkFrames) : 1;
+    if (ctx->big && (ctx->big->nelem != nelem || ctx->big->spr < spr || ctx->big->wsubs < wsubs))
         shard_destroy(ctx, ctx->big);
     if (!ctx->big) {
-        const int rc = shard_create(ctx, nelem, 0, 1, spr, &ctx->big);
+        const int rc = shard_create(ctx, nelem, 0, 1, spr, wsubs, &ctx->big);
         if (rc != CVVP_OK)
             return rc;
     }
-    if ((reinterpret_cast<uintptr_t>(d_out) & 3u) != 0) // phase 3 stores four result bytes at a time
+    if ((reinterpret_cast<uintptr_t>(d_out) & 3u) != 0) // the owner kernels store four result bytes at a time
         return fail(ctx, CVVP_ERR_INVALID, "median: the result pointer of a stack of more than 2048 frames must be 4-byte aligned");
+    if (window) {
+        for (int phase = 4; phase <= 5; ++phase) {
+            const int rc = shard_phase(ctx, ctx->big, phase, d_frames, nframes, frame_stride, d_out, stream);
+            if (rc != CVVP_OK)
+                return rc;
+        }
+    }
     for (int phase = 0; phase < 4; ++phase) {
-        const int rc = shard_phase(ctx, ctx->big, phase, d_frames, nframes, frame_stride, d_out, stream);
+        const int rc = shard_phase(ctx, ctx->big, phase, d_frames, nframes, frame_stride, d_out, stream, window != 0);
         if (rc != CVVP_OK)
             return rc;
     }
@@ -388,7 +568,43 @@ int cvvp_median_shard_begin(cvvp_ctx *ctx, size_t nelem, int rank, int world)
         return fail(ctx, CVVP_ERR_INVALID, "median shard: rank %d / world %d out of range (world <= %d)", rank, world,
                     kMaxShardRanks);
     DeviceGuard guard(ctx->device);
-    return shard_create(ctx, nelem, rank, world, 1, &ctx->shard);
+    return shard_create(ctx, nelem, rank, world, 1, 1, &ctx->shard);
+}
+
+int cvvp_median_shard_begin_frames(cvvp_ctx *ctx, size_t nelem, int rank, int world, long long max_rank_frames)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    if (ctx->shard)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: a sharded job is already open on this context");
+    if (nelem == 0 || nelem >= (1ull << 31))
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: nelem must be in [1, 2^31)");
+    if (world < 1 || world > kMaxShardRanks || rank < 0 || rank >= world)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: rank %d / world %d out of range (world <= %d)", rank, world,
+                    kMaxShardRanks);
+    if (max_rank_frames < 1)
+        max_rank_frames = 1;
+    const long long spr = (max_rank_frames + kSlotFrames - 1) / kSlotFrames;
+    if (spr * world > kMaxShardRanks)
+        return fail(ctx, CVVP_ERR_UNSUPPORTED, "median shard: %lld frames per rank on %d ranks exceed %d count slots",
+                    max_rank_frames, world, kMaxShardRanks);
+    DeviceGuard guard(ctx->device);
+    return shard_create(ctx, nelem, rank, world, int(spr), int((max_rank_frames + kChunkFrames - 1) / kChunkFrames), &ctx->shard);
+}
+
+int cvvp_median_shard_unresolved(cvvp_ctx *ctx, void *stream, long long *out_elements)
+{
+    if (!ctx || !out_elements)
+        return fail(ctx, CVVP_ERR_INVALID, "median shard: null argument");
+    if (!ctx->shard)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: no sharded job is open");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->compute;
+    uint32_t v = 0;
+    CVVP_CUDA_OK(ctx, cudaMemcpyAsync(&v, ctx->shard->buf + ctx->shard->off_flag, sizeof(v), cudaMemcpyDeviceToHost, s));
+    CVVP_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    *out_elements = (long long)v;
+    return CVVP_OK;
 }
 
 int cvvp_median_shard_export(cvvp_ctx *ctx, void *handle_out)

@@ -1,9 +1,11 @@
 """Host-side plumbing of the multi-GPU forms of the hot path (one process per GPU, torch.distributed).
 
     ShardedMedian     frame-sharded temporal median: every rank holds a chunk of the frames; the merge is the
-                      two-round nibble-count exchange of csrc/median_shard.cu (counts are written straight into the
-                      owner rank's memory over NVLink by the counting kernels; torch.distributed only carries the
-                      64-byte buffer handles once and a one-element all-reduce as the barrier between phases).
+                      count exchange of csrc/median_shard.cu -- ONE pass of window counting around per-launch pilot
+                      medians, and the two-round nibble-count exchange when that leaves an element undecided (counts
+                      are written straight into the owner rank's memory over NVLink by the counting kernels;
+                      torch.distributed only carries the 64-byte buffer handles once and a one-element all-reduce as
+                      the barrier between phases).
     frame_chunk       which frames of a job a rank takes (contiguous ranges, like the reference's per-generator
                       frame ranges, /root/reference/Sources/cv_vid_bg_helpers.cpp:84-120)
     element_slices    which elements a rank owns in the exchange
@@ -60,7 +62,8 @@ class ShardedMedian:
     the context's stream (default: a one-element all-reduce on `group`, issued on the context's stream).
     """
 
-    def __init__(self, ctx, nelem: int, rank: int, world: int, barrier: Callable[[], None] | None = None, group=None):
+    def __init__(self, ctx, nelem: int, rank: int, world: int, barrier: Callable[[], None] | None = None, group=None,
+                 max_rank_frames: int | None = None):
         if world > MAX_RANKS:
             raise ValueError(f"at most {MAX_RANKS} ranks")
         self.ctx, self.nelem, self.rank, self.world = ctx, nelem, rank, world
@@ -68,7 +71,9 @@ class ShardedMedian:
         self._barrier = barrier
         self._flag = None
         self._stream = None
-        ctx.median_shard_begin(nelem, rank, world)
+        self.max_rank_frames = max_rank_frames
+        self.last_unresolved = None  # elements the one-pass form left undecided in the last run()
+        ctx.median_shard_begin(nelem, rank, world, max_rank_frames)
         self._open = True
 
     # -- wiring ----------------------------------------------------------------------------------------------------
@@ -118,12 +123,33 @@ class ShardedMedian:
     def barrier(self):
         self._barrier()
 
-    def run(self, d_frames: int, nframes: int, frame_stride: int) -> int:
-        """All four phases with the barriers in between (every rank of the group must call it).  Returns the device
-        pointer of the full result image (nelem bytes), complete once the stream reaches the last barrier."""
+    def window_capacity(self) -> int:
+        """frames per rank the one-pass form has record slots for"""
+        return max(1024, -(-(self.max_rank_frames or 1024) // 1024) * 1024)
+
+    def run_window(self, d_frames: int, nframes: int, frame_stride: int) -> int:
+        """The one-pass form: phase 4, barrier, phase 5, barrier; returns the number of undecided elements (waits for
+        the stream; the same number on every rank)."""
+        for p in (4, 5):
+            self.phase(p, d_frames, nframes, frame_stride)
+            self._barrier()
+        self.last_unresolved = self.ctx.median_shard_unresolved()
+        return self.last_unresolved
+
+    def run_two_round(self, d_frames: int, nframes: int, frame_stride: int):
+        """The four phases of the two-round nibble exchange with the barriers in between (exact for any input)."""
         for p in range(4):
             self.phase(p, d_frames, nframes, frame_stride)
             self._barrier()
+
+    def run(self, d_frames: int, nframes: int, frame_stride: int, window: bool = True) -> int:
+        """One job (every rank of the group must call it with the same `window`): the one-pass form when every rank's
+        frames fit its record slots, then -- only if it left elements undecided, which every rank learns as the same
+        number -- the two-round exchange.  Returns the device pointer of the full result image (nelem bytes), complete
+        once the stream reaches the last barrier."""
+        if window and self.run_window(d_frames, nframes, frame_stride) == 0:
+            return self.ctx.median_shard_result()
+        self.run_two_round(d_frames, nframes, frame_stride)
         return self.ctx.median_shard_result()
 
     def result_ptr(self) -> int:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CVVP_ABI_VERSION 2
+#define CVVP_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CVVP_API __attribute__((visibility("default")))
@@ -106,9 +106,11 @@ CVVP_API int cvvp_median_abort(cvvp_ctx *ctx);
  * tensor-map constraints), d_out a DEVICE pointer to nelem bytes (4-byte aligned).  Runs on
  * `stream` (a cudaStream_t, NULL = the context's compute stream) and does not synchronize.
  * Up to 2048 frames the select happens on chip in one pass over the frames; longer stacks (up to
- * 16 x 65535 = 1048560 frames; more fails with CVVP_ERR_UNSUPPORTED) take two counting passes in
- * chunks of 1024 frames, 16-bit counts per 65535 frames summed in 32 bits -- the reference's
- * analogue of widening its histogram bins with the frame count (cv_vid_bg_helpers.cpp:232-253). */
+ * 16 x 65535 = 1048560 frames; more fails with CVVP_ERR_UNSUPPORTED) are counted in chunks of 1024
+ * frames: one pass of window counting around per-chunk pilot medians, and -- only if that leaves an
+ * element undecided, checked on the device -- two passes of nibble counting, 16-bit counts per
+ * 65535 frames summed in 32 bits: the reference's analogue of widening its histogram bins with the
+ * frame count (cv_vid_bg_helpers.cpp:232-253). */
 CVVP_API int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem,
                        size_t frame_stride, uint8_t *d_out, void *stream);
 
@@ -131,22 +133,39 @@ CVVP_API int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long lon
  *   BARRIER = a cross-rank barrier ordered on the stream (e.g. a one-element NCCL all-reduce):
  *   phase p+1 of any rank must not start before phase p of every rank has completed.  No kernel
  *   of this library waits for another rank.
+ *
+ *   One-pass form (reads every frame once instead of twice; try it first):
+ *     per job: phase 4, BARRIER, phase 5, BARRIER, cvvp_median_shard_unresolved
+ *   Phase 4 counts each rank's frames in an 8-value window around a pilot median the kernel picks
+ *   on chip from 256 of its own frames (per launch of <= 1024 frames), phase 5 lets the owner name
+ *   the median of ALL frames wherever it lies inside every window.  The result is exact where it
+ *   is given; cvvp_median_shard_unresolved returns how many elements could NOT be decided (the
+ *   same number on every rank; 0 for an ordinary video).  When it is not 0 run phases 0..3, which
+ *   are exact for any input and rewrite the whole image.
  * ------------------------------------------------------------------------------------------- */
 #define CVVP_IPC_HANDLE_BYTES 64
 /* rank in [0, world), world <= 16; allocates this rank's exchange buffers (64 B per element and
  * rank for the counts + 5 B per element) */
 CVVP_API int cvvp_median_shard_begin(cvvp_ctx *ctx, size_t nelem, int rank, int world);
+/* same, for ranks that hold up to max_rank_frames frames each: room for one window record per 1024 frames
+ * (phase 4) and one 16-bit count vector per 65535 frames (phases 0 / 2).  cvvp_median_shard_begin is this call with
+ * max_rank_frames = 1024 for the window records and 65535 for the counts. */
+CVVP_API int cvvp_median_shard_begin_frames(cvvp_ctx *ctx, size_t nelem, int rank, int world, long long max_rank_frames);
 /* CVVP_IPC_HANDLE_BYTES bytes that let another PROCESS on the same box map this rank's buffers */
 CVVP_API int cvvp_median_shard_export(cvvp_ctx *ctx, void *handle_out);
 CVVP_API int cvvp_median_shard_import(cvvp_ctx *ctx, int peer_rank, const void *handle);
 /* same-process peer (several contexts in one process, on one or several devices) */
 CVVP_API int cvvp_median_shard_attach(cvvp_ctx *ctx, int peer_rank, cvvp_ctx *peer_ctx);
-/* phases 0 and 2 read this rank's frames (device pointer, same layout rules as cvvp_median_device;
- * nframes may be 0, may differ between ranks, at most 65535 per rank); phases 1 and 3 ignore the frame arguments.
+/* phases 0, 2 and 4 read this rank's frames (device pointer, same layout rules as cvvp_median_device;
+ * nframes may be 0, may differ between ranks, at most what the job was begun for); phases 1, 3 and 5 ignore the
+ * frame arguments.
  * Runs on `stream` (NULL = the context's compute stream) and does not synchronize. */
 CVVP_API int cvvp_median_shard_phase(cvvp_ctx *ctx, int phase, const uint8_t *d_frames, long long nframes,
                                      size_t frame_stride, void *stream);
-/* device pointer to the nelem result bytes (complete on every rank after the barrier that follows phase 3) */
+/* after the barrier that follows phase 5: waits for `stream` (NULL = the context's compute stream) and returns the
+ * number of elements the one-pass form left undecided, summed over all owners (identical on every rank) */
+CVVP_API int cvvp_median_shard_unresolved(cvvp_ctx *ctx, void *stream, long long *out_elements);
+/* device pointer to the nelem result bytes (complete on every rank after the barrier that follows phase 3 / 5) */
 CVVP_API int cvvp_median_shard_result(cvvp_ctx *ctx, const uint8_t **d_result);
 CVVP_API int cvvp_median_shard_end(cvvp_ctx *ctx);
 

@@ -20,7 +20,7 @@ def main():
     W, H, N = 1920, 1080, 1000
     nelem = W * H
     ctxs = [_cabi.Context(0) for _ in range(world)]
-    jobs = [sharded.ShardedMedian(ctxs[r], nelem, r, world) for r in range(world)]
+    jobs = [sharded.ShardedMedian(ctxs[r], nelem, r, world, max_rank_frames=N) for r in range(world)]
     sharded.ShardedMedian.connect_local(jobs)
     stack = torch.empty((N, nelem), dtype=torch.uint8, device="cuda:0")
     ctxs[0].synth_frames_device(stack.data_ptr(), nelem, W, H, 0, N, 2, 30)
@@ -28,7 +28,7 @@ def main():
     single = torch.empty(nelem, dtype=torch.uint8, device="cuda:0")
     streams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", 0)) for c in ctxs]
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    times = {p: [] for p in range(4)}
+    times = {p: [] for p in range(6)}
     t_single = []
     for it in range(6):
         a, b = ev(), ev()
@@ -37,7 +37,7 @@ def main():
         b.record(streams[0])
         torch.cuda.synchronize()
         t_single.append(a.elapsed_time(b))
-        for p in range(4):
+        for p in (4, 5, 0, 1, 2, 3):
             a, b = ev(), ev()
             a.record(streams[0])
             jobs[0].phase(p, stack.data_ptr(), N, nelem)
@@ -46,8 +46,13 @@ def main():
                 jobs[r].phase(p, stack.data_ptr(), N, nelem)
             torch.cuda.synchronize()
             times[p].append(a.elapsed_time(b))
+            if p == 5:
+                left = jobs[0].ctx.median_shard_unresolved()
+                win = np.array_equal(ctxs[0].copy_to_host(jobs[0].result_ptr(), nelem), single.cpu().numpy())
     got = ctxs[0].copy_to_host(jobs[0].result_ptr(), nelem)
     same = np.array_equal(got, single.cpu().numpy())
+    print(f"world {world}: one-pass form p4 {np.median(times[4][1:]):.3f} ms, p5 {np.median(times[5][1:]):.3f} ms; "
+          f"undecided elements {left}; result == single-GPU: {win}")
     print(f"world {world}: single-GPU select {np.median(t_single[1:]):.3f} ms; rank-0 phases "
           + ", ".join(f"p{p} {np.median(times[p][1:]):.3f} ms" for p in range(4))
           + f"; sum {sum(np.median(times[p][1:]) for p in range(4)):.3f} ms; result == single-GPU: {same}")
