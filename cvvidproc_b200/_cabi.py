@@ -60,6 +60,7 @@ def load():
         "cvvp_median_begin": (i32, [vp, sz, i64]),
         "cvvp_median_push": (i32, [vp, vp, i64, sz]),
         "cvvp_median_count": (i64, [vp]),
+        "cvvp_median_stack_device": (i32, [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(i64)]),
         "cvvp_median_finish": (i32, [vp, vp]),
         "cvvp_median_abort": (i32, [vp]),
         "cvvp_median_device": (i32, [vp, vp, i64, sz, sz, vp, vp]),
@@ -92,6 +93,10 @@ def load():
         "cvvp_highlight_queue_ready": (i32, [vp]),
         "cvvp_highlight_next": (i32, [vp, vp, sz, C.POINTER(i64), vp, vp]),
         "cvvp_highlight_queue_end": (i32, [vp]),
+        "cvvp_highlight_slot_acquire": (i32, [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(i64)]),
+        "cvvp_highlight_slot_commit": (i32, [vp, i64]),
+        "cvvp_highlight_next_view": (i32, [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp)]),
+        "cvvp_highlight_view_release": (i32, [vp]),
     }
     global BOUND_SYMBOLS
     BOUND_SYMBOLS = sorted(sigs)
@@ -268,6 +273,13 @@ class Context:
     def median_push_raw(self, ptr: int, n: int, stride: int):
         self._check(self._lib.cvvp_median_push(self._h, ptr, n, stride))
 
+    def median_stack_device(self):
+        """(device pointer, frame stride, frames) of the running job's stack; pushes so far are ordered before later work
+        on the compute stream"""
+        p, st, n = C.c_void_p(), C.c_size_t(), C.c_longlong()
+        self._check(self._lib.cvvp_median_stack_device(self._h, C.byref(p), C.byref(st), C.byref(n)))
+        return int(p.value or 0), int(st.value), int(n.value)
+
     def median_count(self) -> int:
         return int(self._lib.cvvp_median_count(self._h))
 
@@ -430,6 +442,36 @@ class Context:
                                                   ncomps.ctypes.data if max_comps else None))
         k = int(n.value)
         return (out[:k], comps[:k], ncomps[:k]) if max_comps else out[:k]
+
+    # zero-copy forms: the decoder writes into the slot's pinned input, the consumer reads the slot's pinned results
+    def highlight_slot_acquire(self) -> np.ndarray:
+        """-> uint8 view (max_batch, frame_pitch) of the next free slot's pinned input (frame i = row i)"""
+        p, pitch, mx = C.c_void_p(), C.c_size_t(), C.c_longlong()
+        self._check(self._lib.cvvp_highlight_slot_acquire(self._h, C.byref(p), C.byref(pitch), C.byref(mx)))
+        buf = (C.c_uint8 * (int(mx.value) * int(pitch.value))).from_address(p.value)
+        return np.frombuffer(buf, np.uint8).reshape(int(mx.value), int(pitch.value))
+
+    def highlight_slot_commit(self, n: int):
+        self._check(self._lib.cvvp_highlight_slot_commit(self._h, n))
+
+    def highlight_next_view(self):
+        """-> masks (n, H, W) view of the oldest batch's pinned results [, comps (n, max_comps), ncomps (n,)]; valid until
+        highlight_view_release()"""
+        max_batch, max_comps = self._hq
+        h, w = self._hl_shape
+        pm, pitch, n, pc, pn = C.c_void_p(), C.c_size_t(), C.c_longlong(), C.c_void_p(), C.c_void_p()
+        self._check(self._lib.cvvp_highlight_next_view(self._h, C.byref(pm), C.byref(pitch), C.byref(n), C.byref(pc), C.byref(pn)))
+        k, pt = int(n.value), int(pitch.value)
+        buf = (C.c_uint8 * (k * pt)).from_address(pm.value)
+        masks = np.frombuffer(buf, np.uint8).reshape(k, pt)[:, : h * w].reshape(k, h, w)
+        if not max_comps:
+            return masks
+        cbuf = (C.c_uint8 * (k * max_comps * self.COMPONENT_DTYPE.itemsize)).from_address(pc.value)
+        nbuf = (C.c_int32 * k).from_address(pn.value)
+        return masks, np.frombuffer(cbuf, self.COMPONENT_DTYPE).reshape(k, max_comps), np.frombuffer(nbuf, np.int32)
+
+    def highlight_view_release(self):
+        self._check(self._lib.cvvp_highlight_view_release(self._h))
 
     def highlight_queue_end(self):
         self._check(self._lib.cvvp_highlight_queue_end(self._h))

@@ -59,20 +59,42 @@ void release_median(cvvp_ctx *ctx)
     // device buffers are kept for reuse by the next job of the same context
 }
 
+// Device frame stack of the streaming median job.  The job keeps EVERY pushed frame resident (the select needs all of
+// them at once), so a job is limited to  frames x round_up(nelem, 128)  bytes of free HBM -- unlike the reference's
+// histograms, whose size does not depend on the frame count (histogram_median_algo.h:123-126).  To make that limit
+// the real one, the stack is sized EXACTLY to what is asked for (the hint of cvvp_median_begin, rounded up to a
+// granule of 16 frames) and grows by half only when more frames arrive than were announced; while it grows the old
+// and the new stack coexist, which an exact hint avoids altogether.
 int ensure_stack(cvvp_ctx *ctx, long long frames_needed)
 {
     MedianJob &m = ctx->med;
     if (frames_needed <= m.capacity)
         return CVVP_OK;
-    long long new_cap = m.capacity > 0 ? m.capacity : 64;
-    while (new_cap < frames_needed)
-        new_cap *= 2;
-    const size_t bytes = size_t(new_cap) * m.stride;
+    constexpr long long kGranule = 16;
+    long long new_cap = (frames_needed + kGranule - 1) / kGranule * kGranule;
+    if (m.capacity > 0 && m.count > 0) { // growing past what was announced: geometric, so pushes stay amortised O(1)
+        const long long grown = (m.capacity + m.capacity / 2 + kGranule - 1) / kGranule * kGranule;
+        if (grown > new_cap)
+            new_cap = grown;
+    }
+    size_t bytes = size_t(new_cap) * m.stride;
     if (bytes > m.d_stack_bytes) {
         uint8_t *fresh = nullptr;
         if (cudaMalloc(&fresh, bytes) != cudaSuccess) {
             cudaGetLastError();
-            return fail(ctx, CVVP_ERR_NOMEM, "median: cudaMalloc of %zu bytes for the frame stack failed", bytes);
+            // the geometric slack did not fit: retry with exactly what is needed now
+            new_cap = (frames_needed + kGranule - 1) / kGranule * kGranule;
+            bytes = size_t(new_cap) * m.stride;
+            if (bytes <= m.d_stack_bytes || cudaMalloc(&fresh, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                cudaGetLastError();
+                return fail(ctx, CVVP_ERR_NOMEM,
+                            "median: cudaMalloc of %zu bytes for a stack of %lld frames x %zu bytes failed (%zu bytes free); the "
+                            "job keeps every frame resident, so frames x frame bytes must fit the device",
+                            bytes, new_cap, m.stride, free_b);
+            }
         }
         if (m.d_stack && m.count > 0) {
             // frames prepared on the device (cvvp_median_push_source) are written by kernels on the compute stream
@@ -85,7 +107,7 @@ int ensure_stack(cvvp_ctx *ctx, long long frames_needed)
         m.d_stack = fresh;
         m.d_stack_bytes = bytes;
     }
-    m.capacity = new_cap;
+    m.capacity = (long long)(m.d_stack_bytes / m.stride);
     return CVVP_OK;
 }
 
@@ -384,16 +406,37 @@ int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t f
         if (rc != CVVP_OK)
             return rc;
         const long long per_buf = (long long)(kStagingBytes / m.nelem);
-        if (per_buf == 0)
-            return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: frame larger than the staging buffer; pass pinned memory");
-        for (long long done = 0; done < n;) {
-            const long long chunk = (n - done) < per_buf ? (n - done) : per_buf;
+        auto next_buf = [&]() -> StagingBuf * {
             StagingBuf &b = ctx->staging[ctx->staging_next];
             ctx->staging_next = (ctx->staging_next + 1) % ctx->staging.size();
             if (b.in_flight) {
-                CVVP_CUDA_OK(ctx, cudaEventSynchronize(b.done));
+                if (cudaEventSynchronize(b.done) != cudaSuccess)
+                    return nullptr;
                 b.in_flight = false;
             }
+            return &b;
+        };
+        if (per_buf == 0) {
+            // a single frame is larger than a staging buffer (an 8K frame, a 4K colour frame): pieces of the frame
+            for (long long i = 0; i < n; ++i) {
+                for (size_t off = 0; off < m.nelem; off += kStagingBytes) {
+                    const size_t piece = m.nelem - off < kStagingBytes ? m.nelem - off : kStagingBytes;
+                    StagingBuf *b = next_buf();
+                    if (!b)
+                        return fail(ctx, CVVP_ERR_CUDA, "median: waiting for a staging buffer failed");
+                    std::memcpy(b->host, frames + size_t(i) * frame_stride + off, piece);
+                    CVVP_CUDA_OK(ctx, cudaMemcpyAsync(dst + size_t(i) * m.stride + off, b->host, piece, cudaMemcpyHostToDevice, ctx->copy));
+                    CVVP_CUDA_OK(ctx, cudaEventRecord(b->done, ctx->copy));
+                    b->in_flight = true;
+                }
+            }
+        }
+        for (long long done = 0; per_buf > 0 && done < n;) {
+            const long long chunk = (n - done) < per_buf ? (n - done) : per_buf;
+            StagingBuf *bp = next_buf();
+            if (!bp)
+                return fail(ctx, CVVP_ERR_CUDA, "median: waiting for a staging buffer failed");
+            StagingBuf &b = *bp;
             for (long long i = 0; i < chunk; ++i)
                 std::memcpy(b.host + size_t(i) * m.nelem, frames + size_t(done + i) * frame_stride, m.nelem);
             CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst + size_t(done) * m.stride, m.stride, b.host, m.nelem, m.nelem,
@@ -410,6 +453,23 @@ int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t f
 long long cvvp_median_count(const cvvp_ctx *ctx)
 {
     return ctx ? ctx->med.count : 0;
+}
+
+int cvvp_median_stack_device(cvvp_ctx *ctx, const uint8_t **d_frames, size_t *frame_stride, long long *nframes)
+{
+    if (!ctx || !d_frames || !frame_stride || !nframes)
+        return fail(ctx, CVVP_ERR_INVALID, "median: null argument");
+    MedianJob &m = ctx->med;
+    if (!m.active)
+        return fail(ctx, CVVP_ERR_STATE, "median: no job is running");
+    DeviceGuard guard(ctx->device);
+    // everything pushed so far is ordered before whatever the caller queues on the compute stream next
+    CVVP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy));
+    CVVP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->compute, ctx->ev_copy, 0));
+    *d_frames = m.d_stack;
+    *frame_stride = m.stride;
+    *nframes = m.count;
+    return CVVP_OK;
 }
 
 int cvvp_median_finish(cvvp_ctx *ctx, uint8_t *out)
@@ -686,6 +746,37 @@ int cvvp_highlight_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_stride, lo
         return fail(nullptr, CVVP_ERR_INVALID, "null context");
     DeviceGuard guard(ctx->device);
     return highlight_queue_next(ctx, masks_out, out_stride, n_out, comps_out, ncomps_out);
+}
+
+int cvvp_highlight_slot_acquire(cvvp_ctx *ctx, uint8_t **h_frames, size_t *frame_pitch, long long *max_frames)
+{
+    if (!ctx || !h_frames || !frame_pitch)
+        return fail(ctx, CVVP_ERR_INVALID, "null argument");
+    return highlight_slot_acquire(ctx, h_frames, frame_pitch, max_frames);
+}
+
+int cvvp_highlight_slot_commit(cvvp_ctx *ctx, long long n)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    return highlight_slot_commit(ctx, n);
+}
+
+int cvvp_highlight_next_view(cvvp_ctx *ctx, const uint8_t **h_masks, size_t *mask_pitch, long long *n_out,
+                             const cvvp_component **comps, const int **ncomps)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    DeviceGuard guard(ctx->device);
+    return highlight_queue_next_view(ctx, h_masks, mask_pitch, n_out, comps, ncomps);
+}
+
+int cvvp_highlight_view_release(cvvp_ctx *ctx)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    return highlight_queue_view_release(ctx);
 }
 
 int cvvp_highlight_queue_end(cvvp_ctx *ctx)

@@ -175,6 +175,11 @@ int highlight_queue_submit(cvvp_ctx *ctx, const uint8_t *frames, long long n, si
 int highlight_queue_ready(cvvp_ctx *ctx);
 int highlight_queue_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_stride, long long *n_out, cvvp_component *comps_out,
                          int *ncomps_out);
+int highlight_slot_acquire(cvvp_ctx *ctx, uint8_t **h_frames, size_t *frame_pitch, long long *max_frames);
+int highlight_slot_commit(cvvp_ctx *ctx, long long n);
+int highlight_queue_next_view(cvvp_ctx *ctx, const uint8_t **h_masks, size_t *mask_pitch, long long *n_out,
+                              const cvvp_component **comps, const int **ncomps);
+int highlight_queue_view_release(cvvp_ctx *ctx);
 // highlight.cu: geometry of the running job (false: no job)
 bool highlight_geometry(const cvvp_ctx *ctx, int *width, int *height);
 // synth.cu

@@ -189,6 +189,9 @@ int frames_prepare_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_
 /* ------------------------------------------------------------------------------------------------------------------- */
 /* asynchronous ordered highlight queue                                                                                */
 /* ------------------------------------------------------------------------------------------------------------------- */
+// A slot's pinned input holds WHOLE frames as the caller has them (decoded frames when the queue has a frame format,
+// prepared frames otherwise), one every host_pitch bytes, so that a decoder can write straight into it
+// (cvvp_highlight_slot_acquire); only the crop band of every frame crosses the link.
 struct HqSlot {
     uint8_t *h_in{nullptr}, *h_out{nullptr}; // pinned
     cvvp_component *h_comps{nullptr};
@@ -208,8 +211,12 @@ struct HighlightQueue {
     int max_comps{0};
     size_t npix{0}, pitch{0}; // prepared frame bytes / device pitch
     size_t in_bytes{0}, in_pitch{0}, in_offset{0}; // what one frame uploads (crop band or the frame) and where it starts
+    size_t host_pitch{0};                          // bytes between the caller's frames in a slot's pinned input
     std::vector<HqSlot> slots;
     int head{0}, count{0};
+    bool acquired{false}; // the slot after the pending ones is in the caller's hands (slot_acquire .. slot_commit)
+    bool lent{false};     // the oldest pending slot's results are in the caller's hands (next_view .. view_release)
+    bool failed{false};   // a submit died half-way: work of unknown extent is queued on the slot
 };
 
 void highlight_queue_release(cvvp_ctx *ctx)
@@ -277,16 +284,18 @@ int highlight_queue_begin(cvvp_ctx *ctx, int depth, long long max_batch, const c
         q->in_bytes = band.bytes;
         q->in_pitch = band.pitch;
         q->in_offset = band.offset;
+        q->host_pitch = round_up(size_t(fmt->src_width) * size_t(fmt->src_height) * size_t(fmt->src_channels), 64);
     } else {
         q->in_bytes = q->npix;
         q->in_pitch = q->pitch;
         q->in_offset = 0;
+        q->host_pitch = q->pitch;
     }
     q->slots.resize(size_t(depth));
     const size_t nb = size_t(max_batch);
     bool ok = true;
     for (HqSlot &s : q->slots) {
-        ok = ok && cudaMallocHost(&s.h_in, nb * q->in_pitch) == cudaSuccess;
+        ok = ok && cudaMallocHost(&s.h_in, nb * q->host_pitch) == cudaSuccess;
         ok = ok && cudaMallocHost(&s.h_out, nb * q->pitch) == cudaSuccess;
         if (fmt)
             ok = ok && cudaMalloc(&s.d_raw, nb * q->in_pitch) == cudaSuccess;
@@ -317,23 +326,13 @@ int highlight_queue_pending(const cvvp_ctx *ctx)
     return ctx->hq ? ctx->hq->count : 0;
 }
 
-int highlight_queue_submit(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride)
+// queues H2D (crop bands only) -> [frame preparation] -> highlight kernel -> D2H for the n frames in the slot's pinned input
+static int launch_slot(cvvp_ctx *ctx, HighlightQueue *q, HqSlot &s, long long n)
 {
-    HighlightQueue *q = ctx->hq;
-    if (!q)
-        return fail(ctx, CVVP_ERR_STATE, "highlight queue: not begun");
-    if (!frames || n < 1 || n > q->max_batch || frame_stride < q->in_offset + q->in_bytes)
-        return fail(ctx, CVVP_ERR_INVALID, "highlight queue: bad submit arguments (1 <= n <= %lld frames of at least %zu bytes)",
-                    q->max_batch, q->in_offset + q->in_bytes);
-    if (q->count == q->depth)
-        return fail(ctx, CVVP_ERR_STATE, "highlight queue: %d batches pending; call cvvp_highlight_next first", q->depth);
-    HqSlot &s = q->slots[size_t((q->head + q->count) % q->depth)];
-    // a slot is handed out again only after cvvp_highlight_next waited for its `down` event: nothing of it is in flight
-    for (long long i = 0; i < n; ++i)
-        std::memcpy(s.h_in + size_t(i) * q->in_pitch, frames + size_t(i) * frame_stride + q->in_offset, q->in_bytes);
     s.n = n;
     uint8_t *up_to = q->has_fmt ? s.d_raw : s.d_in;
-    CVVP_CUDA_OK(ctx, cudaMemcpyAsync(up_to, s.h_in, size_t(n) * q->in_pitch, cudaMemcpyHostToDevice, ctx->copy));
+    CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(up_to, q->in_pitch, s.h_in + q->in_offset, q->host_pitch, q->in_bytes, size_t(n),
+                                        cudaMemcpyHostToDevice, ctx->copy));
     CVVP_CUDA_OK(ctx, cudaEventRecord(s.up, ctx->copy));
     CVVP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->compute, s.up, 0));
     int rc;
@@ -359,6 +358,88 @@ int highlight_queue_submit(cvvp_ctx *ctx, const uint8_t *frames, long long n, si
         CVVP_CUDA_OK(ctx, cudaMemcpyAsync(s.h_ncomps, s.d_ncomps, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_out));
     }
     CVVP_CUDA_OK(ctx, cudaEventRecord(s.down, ctx->copy_out));
+    return CVVP_OK;
+}
+
+// A launch that failed half-way leaves copies / kernels of unknown extent queued on the slot while the slot is not
+// counted as pending: the next submit would overwrite pinned memory an earlier H2D may still be reading.  Drain the
+// streams and refuse further submits; cvvp_highlight_queue_end (or cvvp_highlight_end) clears the state.
+static int slot_failed(cvvp_ctx *ctx, HighlightQueue *q, int rc)
+{
+    const std::string why = ctx->err;
+    cudaStreamSynchronize(ctx->copy);
+    cudaStreamSynchronize(ctx->compute);
+    cudaStreamSynchronize(ctx->copy_out);
+    cudaGetLastError();
+    q->failed = true;
+    ctx->err = why;
+    return rc;
+}
+
+static int check_can_fill(cvvp_ctx *ctx, HighlightQueue *q)
+{
+    if (!q)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: not begun");
+    if (q->failed)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: an earlier submit failed; end the queue and begin a new one");
+    if (q->count == q->depth)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: %d batches pending; call cvvp_highlight_next first", q->depth);
+    return CVVP_OK;
+}
+
+int highlight_queue_submit(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride)
+{
+    HighlightQueue *q = ctx->hq;
+    int rc = check_can_fill(ctx, q);
+    if (rc != CVVP_OK)
+        return rc;
+    if (q->acquired)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: a slot is acquired; commit it before submitting");
+    if (!frames || n < 1 || n > q->max_batch || frame_stride < q->in_offset + q->in_bytes)
+        return fail(ctx, CVVP_ERR_INVALID, "highlight queue: bad submit arguments (1 <= n <= %lld frames of at least %zu bytes)",
+                    q->max_batch, q->in_offset + q->in_bytes);
+    HqSlot &s = q->slots[size_t((q->head + q->count) % q->depth)];
+    // a slot is handed out again only after cvvp_highlight_next waited for its `down` event: nothing of it is in flight
+    for (long long i = 0; i < n; ++i)
+        std::memcpy(s.h_in + size_t(i) * q->host_pitch + q->in_offset, frames + size_t(i) * frame_stride + q->in_offset, q->in_bytes);
+    rc = launch_slot(ctx, q, s, n);
+    if (rc != CVVP_OK)
+        return slot_failed(ctx, q, rc);
+    q->count++;
+    return CVVP_OK;
+}
+
+int highlight_slot_acquire(cvvp_ctx *ctx, uint8_t **h_frames, size_t *frame_pitch, long long *max_frames)
+{
+    HighlightQueue *q = ctx->hq;
+    int rc = check_can_fill(ctx, q);
+    if (rc != CVVP_OK)
+        return rc;
+    if (q->acquired)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: a slot is already acquired");
+    HqSlot &s = q->slots[size_t((q->head + q->count) % q->depth)];
+    q->acquired = true;
+    *h_frames = s.h_in;
+    *frame_pitch = q->host_pitch;
+    if (max_frames)
+        *max_frames = q->max_batch;
+    return CVVP_OK;
+}
+
+int highlight_slot_commit(cvvp_ctx *ctx, long long n)
+{
+    HighlightQueue *q = ctx->hq;
+    if (!q || !q->acquired)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: no slot is acquired");
+    if (n < 0 || n > q->max_batch)
+        return fail(ctx, CVVP_ERR_INVALID, "highlight queue: a slot takes 0 .. %lld frames", q->max_batch);
+    q->acquired = false;
+    if (n == 0)
+        return CVVP_OK; // handed back unused
+    HqSlot &s = q->slots[size_t((q->head + q->count) % q->depth)];
+    const int rc = launch_slot(ctx, q, s, n);
+    if (rc != CVVP_OK)
+        return slot_failed(ctx, q, rc);
     q->count++;
     return CVVP_OK;
 }
@@ -368,6 +449,8 @@ int highlight_queue_ready(cvvp_ctx *ctx)
     HighlightQueue *q = ctx->hq;
     if (!q || q->count == 0)
         return 0;
+    if (q->lent)
+        return 1;
     const cudaError_t e = cudaEventQuery(q->slots[size_t(q->head)].down);
     if (e == cudaSuccess)
         return 1;
@@ -386,6 +469,8 @@ int highlight_queue_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_stride, l
         return fail(ctx, CVVP_ERR_INVALID, "highlight queue: bad arguments to next");
     if (q->count == 0)
         return fail(ctx, CVVP_ERR_STATE, "highlight queue: nothing pending");
+    if (q->lent)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: the oldest batch is lent out; release the view first");
     HqSlot &s = q->slots[size_t(q->head)];
     const cudaError_t e = cudaEventSynchronize(s.down);
     q->head = (q->head + 1) % q->depth;
@@ -399,6 +484,47 @@ int highlight_queue_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_stride, l
     if (q->max_comps > 0 && ncomps_out)
         std::memcpy(ncomps_out, s.h_ncomps, size_t(s.n) * sizeof(int));
     *n_out = s.n;
+    return CVVP_OK;
+}
+
+int highlight_queue_next_view(cvvp_ctx *ctx, const uint8_t **h_masks, size_t *mask_pitch, long long *n_out,
+                              const cvvp_component **comps, const int **ncomps)
+{
+    HighlightQueue *q = ctx->hq;
+    if (!q)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: not begun");
+    if (!h_masks || !mask_pitch || !n_out)
+        return fail(ctx, CVVP_ERR_INVALID, "highlight queue: bad arguments to next_view");
+    if (q->count == 0)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: nothing pending");
+    if (q->lent)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: the oldest batch is already lent out");
+    HqSlot &s = q->slots[size_t(q->head)];
+    const cudaError_t e = cudaEventSynchronize(s.down);
+    if (e != cudaSuccess) {
+        q->head = (q->head + 1) % q->depth;
+        q->count--;
+        return fail(ctx, CVVP_ERR_CUDA, "highlight queue: batch failed: %s", cudaGetErrorString(e));
+    }
+    q->lent = true;
+    *h_masks = s.h_out;
+    *mask_pitch = q->pitch;
+    *n_out = s.n;
+    if (comps)
+        *comps = q->max_comps > 0 ? s.h_comps : nullptr;
+    if (ncomps)
+        *ncomps = q->max_comps > 0 ? s.h_ncomps : nullptr;
+    return CVVP_OK;
+}
+
+int highlight_queue_view_release(cvvp_ctx *ctx)
+{
+    HighlightQueue *q = ctx->hq;
+    if (!q || !q->lent)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: no view is lent out");
+    q->lent = false;
+    q->head = (q->head + 1) % q->depth;
+    q->count--;
     return CVVP_OK;
 }
 } // namespace cvvp

@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <deque>
 #include <memory>
 #include <sstream>
@@ -180,6 +181,108 @@ private:
     std::unique_ptr<FrameBatch> m_result{};
 };
 
+// The same operator over SEVERAL devices of one process: tokens go to the devices in turn (the reference's analogue: the
+// frame range of the video split over its generator threads, Sources/cv_vid_bg_helpers.cpp:84-120 -- the histogram is
+// order-independent, so it does not matter which worker sees which frame), and the end of the stream runs the
+// frame-sharded job of csrc/median_shard.cu with one rank per device: one pass of window counting with the count
+// records written into the owner device's memory over NVLink, the two-round nibble exchange behind it when an element
+// stayed undecided.  The barrier between phases is a synchronize of every context (all ranks live in this process).
+class GpuShardedMedianAlgo
+{
+public:
+    using token_type = FrameBatch;
+    using result_type = FrameBatch;
+    GpuShardedMedianAlgo(const std::vector<int> &devices, long long frames_hint, SourceFormat source) : m_source{source}
+    {
+        CVVP_ASSERT_MSG(!devices.empty() && devices.size() <= 16, "1..16 devices");
+        CVVP_ASSERT_MSG(source.enabled, "the multi-device median takes decoded frames");
+        for (int d : devices)
+            m_ctx.push_back(std::make_unique<Context>(d));
+        m_hint = frames_hint > 0 ? (frames_hint + (long long)devices.size() - 1) / (long long)devices.size() : -1;
+    }
+    // `turn` tokens in a row go to one device, then the next device takes over
+    void InsertDecoded(const std::uint8_t *frames, long long n, std::size_t stride)
+    {
+        if (!frames || n <= 0)
+            return;
+        if (!m_started) {
+            m_rows = m_source.out_rows();
+            m_cols = m_source.out_cols();
+            m_channels = m_source.out_channels();
+            for (auto &c : m_ctx)
+                c->check(cvvp_median_begin(c->get(), cvvp_frame_format_out_bytes(&m_source.fmt), m_hint));
+            m_started = true;
+        }
+        Context &c = *m_ctx[std::size_t((m_inserted / kTurn) % (long long)m_ctx.size())];
+        c.check(cvvp_median_push_source(c.get(), frames, n, stride, &m_source.fmt));
+        m_inserted += n;
+    }
+    void NotifyNoMoreTokens()
+    {
+        if (!m_started)
+            return;
+        m_started = false;
+        const int world = int(m_ctx.size());
+        const std::size_t nelem = cvvp_frame_format_out_bytes(&m_source.fmt);
+        std::vector<const std::uint8_t *> d_frames(m_ctx.size());
+        std::vector<std::size_t> strides(m_ctx.size());
+        std::vector<long long> counts(m_ctx.size());
+        long long most = 1;
+        for (int r = 0; r < world; ++r) {
+            Context &c = *m_ctx[std::size_t(r)];
+            c.check(cvvp_median_stack_device(c.get(), &d_frames[std::size_t(r)], &strides[std::size_t(r)], &counts[std::size_t(r)]));
+            most = std::max(most, counts[std::size_t(r)]);
+        }
+        for (int r = 0; r < world; ++r)
+            m_ctx[std::size_t(r)]->check(cvvp_median_shard_begin_frames(m_ctx[std::size_t(r)]->get(), nelem, r, world, most));
+        for (int r = 0; r < world; ++r)
+            for (int p = 0; p < world; ++p)
+                if (p != r)
+                    m_ctx[std::size_t(r)]->check(cvvp_median_shard_attach(m_ctx[std::size_t(r)]->get(), p, m_ctx[std::size_t(p)]->get()));
+        auto walk = [&](int first, int last) {
+            for (int phase = first; phase <= last; ++phase) {
+                for (int r = 0; r < world; ++r)
+                    m_ctx[std::size_t(r)]->check(cvvp_median_shard_phase(m_ctx[std::size_t(r)]->get(), phase, d_frames[std::size_t(r)],
+                                                                         counts[std::size_t(r)], strides[std::size_t(r)], nullptr));
+                for (auto &c : m_ctx) // the cross-rank barrier: every rank of this process has finished the phase
+                    c->check(cvvp_ctx_synchronize(c->get()));
+            }
+        };
+        walk(4, 5);
+        long long undecided = 0;
+        m_ctx[0]->check(cvvp_median_shard_unresolved(m_ctx[0]->get(), nullptr, &undecided));
+        if (undecided != 0)
+            walk(0, 3);
+        auto out = std::make_unique<FrameBatch>();
+        out->n = 1;
+        out->rows = m_rows;
+        out->cols = m_cols;
+        out->channels = m_channels;
+        out->data.resize(out->frame_bytes());
+        const std::uint8_t *d_res = nullptr;
+        m_ctx[0]->check(cvvp_median_shard_result(m_ctx[0]->get(), &d_res));
+        m_ctx[0]->check(cvvp_ctx_copy_to_host(m_ctx[0]->get(), out->data.data(), d_res, nelem));
+        for (auto &c : m_ctx) {
+            c->check(cvvp_median_shard_end(c->get()));
+            c->check(cvvp_median_abort(c->get()));
+        }
+        m_result = std::move(out);
+    }
+    std::unique_ptr<FrameBatch> TryGetResult() { return std::move(m_result); }
+    bool HasResults() const { return static_cast<bool>(m_result); }
+    long long FramesInserted() const { return m_inserted; }
+    static constexpr long long kTurn = 32;
+
+private:
+    SourceFormat m_source;
+    std::vector<std::unique_ptr<Context>> m_ctx;
+    long long m_hint{-1};
+    bool m_started{false};
+    long long m_inserted{0};
+    int m_rows{0}, m_cols{0}, m_channels{1};
+    std::unique_ptr<FrameBatch> m_result{};
+};
+
 // ---------------------------------------------------------------------------------------------------------------------
 // highlight: replaces HighlightObjectsAlgo (Sources/ProcessorAlgos/highlight_objects_algo.h:21-107)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -283,6 +386,49 @@ public:
         return nullptr;
     }
     void NotifyNoMoreTokens() { m_no_more = true; } // :82-85 (tokens are independent; nothing is held back)
+
+    // ---- zero-copy token path (queue mode): the token's storage is the queue slot's pinned memory ----
+    // Where the reference's generator fills a fresh cv::Mat that then MOVES through the queues
+    // (Sources/AsyncTokens/token_batch_generator.h:52-67), the decoder here writes its frames straight into the
+    // slot AcquireSlot hands out, and the consumer reads the masks from the view NextView lends.
+    struct Slot {
+        std::uint8_t *frames{nullptr}; // frame i at frames + i * pitch (decoded frames with a SourceFormat, else prepared)
+        std::size_t pitch{0};
+        long long max_frames{0};
+    };
+    struct MaskView {
+        const std::uint8_t *masks{nullptr}; // mask i at masks + i * pitch
+        std::size_t pitch{0};
+        long long n{0};
+        const cvvp_component *comps{nullptr}; // [i * max_comps + k], null without components
+        const int *ncomps{nullptr};
+    };
+    int Pending() const { return cvvp_highlight_queue_pending(m_ctx.get()); }
+    int Depth() const { return m_pack.queue_depth; }
+    bool Ready() const
+    {
+        const int r = cvvp_highlight_queue_ready(m_ctx.get());
+        if (r < 0)
+            m_ctx.check(r);
+        return r == 1;
+    }
+    Slot AcquireSlot()
+    {
+        Slot s;
+        m_ctx.check(cvvp_highlight_slot_acquire(m_ctx.get(), &s.frames, &s.pitch, &s.max_frames));
+        return s;
+    }
+    void CommitSlot(long long n) { m_ctx.check(cvvp_highlight_slot_commit(m_ctx.get(), n)); }
+    MaskView NextView() // blocks until the oldest pending batch is complete
+    {
+        MaskView v;
+        m_ctx.check(cvvp_highlight_next_view(m_ctx.get(), &v.masks, &v.pitch, &v.n, &v.comps, &v.ncomps));
+        return v;
+    }
+    void ReleaseView() { m_ctx.check(cvvp_highlight_view_release(m_ctx.get())); }
+    int rows() const { return m_pack.background.rows; }
+    int cols() const { return m_pack.background.cols; }
+
     bool HasResults() const { return !m_ready.empty() || (m_pack.queue_depth > 0 && cvvp_highlight_queue_pending(m_ctx.get()) > 0); } // :88-91
 
 private:

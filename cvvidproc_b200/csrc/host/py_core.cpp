@@ -12,22 +12,29 @@
 // DEVICE (csrc/frames.cu): the decoded frame is handed over untouched together with a SourceFormat.  CVVP_HOST_PREP=1
 // keeps it on the host through cv2 instead (cross-check; tests hold the two to each other).
 //
-// TrackObjects is a pipeline like the reference's (highlight process || assign process,
-// cv_vid_objecttrack_helpers.cpp:126-133): batches are submitted to the device asynchronously, at most
-// token_storage_limit in flight, while this thread decodes the next batch and runs the tracker callback on the
-// masks that have come back -- strictly in frame order.
+// TrackObjects is a pipeline like the reference's (decode thread || highlight process || assign process,
+// cv_vid_objecttrack_helpers.cpp:71-133): a C++ decode thread (the reference's generator thread, :71-93) takes the GIL
+// only around VideoCapture.read -- which drops it again while it decodes -- and writes every frame straight into the
+// pinned input slot of the device queue; the calling thread submits the filled slots (at most token_storage_limit in
+// flight per device), and runs the tracker callback on the masks that have come back, strictly in frame order, reading
+// them from the queue's pinned output.  CVVP_DEVICES=0,1,... spreads the batches over several GPUs round-robin; the
+// masks are still handed over in frame order (the MatSetIntermediary role, mat_set_intermediary.h:50-68,84-114).
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
+#include <deque>
 #include <iostream>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 
 #include "gpu_algos.hpp"
 
@@ -126,9 +133,32 @@ public:
             return py::none();
         return m_np.attr("ascontiguousarray")(res[1], py::arg("dtype") = m_np.attr("uint8"));
     }
+    // Decode the next frame INTO dst (rows x cols x channels contiguous bytes: a queue slot, a pinned buffer); false at
+    // end of stream.  VideoCapture.read(image) reuses a matching array, so the decoder's copy-out is the only write.
+    bool read_into(std::uint8_t *dst, int rows, int cols, int channels)
+    {
+        std::vector<py::ssize_t> shape{rows, cols};
+        if (channels > 1)
+            shape.push_back(channels);
+        py::array_t<std::uint8_t> view(shape, dst, m_np); // a base object: the array is a view, not a copy
+        py::tuple res = m_vid.attr("read")(view).cast<py::tuple>();
+        if (!res[0].cast<bool>() || res[1].is_none())
+            return false;
+        py::array out = res[1].cast<py::array>();
+        if (out.data() != static_cast<const void *>(dst)) { // the decoder allocated its own array (geometry changed?)
+            py::array c = m_np.attr("ascontiguousarray")(out, py::arg("dtype") = m_np.attr("uint8")).cast<py::array>();
+            CVVP_ASSERT_MSG(std::size_t(c.nbytes()) == std::size_t(rows) * cols * channels,
+                            "all frames must have the geometry of the first one");
+            std::memcpy(dst, c.data(), std::size_t(c.nbytes()));
+        }
+        return true;
+    }
     // what the device has to do with a decoded frame of `channels` channels (:141-156)
     SourceFormat format_for(int rows, int cols, int channels) const
     {
+        // cv::cvtColor(COLOR_RGB2GRAY) throws on anything but 3 or 4 channels (:152-154)
+        CVVP_ASSERT_MSG(!(m_gray && !m_is_gray && channels < 3),
+                        "grayscale conversion needs a 3- or 4-channel frame (cv::cvtColor COLOR_RGB2GRAY)");
         SourceFormat sf;
         sf.enabled = true;
         sf.fmt.src_width = cols;
@@ -160,8 +190,7 @@ public:
             if (ndim == 3)
                 frame = m_cv2.attr("extractChannel")(frame, 0); // :149-151
         } else if (m_gray) {
-            if (ndim == 3)
-                frame = m_cv2.attr("cvtColor")(frame, m_cv2.attr("COLOR_RGB2GRAY")); // :152-154
+            frame = m_cv2.attr("cvtColor")(frame, m_cv2.attr("COLOR_RGB2GRAY")); // :152-154 (throws on < 3 channels)
         }
         return m_np.attr("ascontiguousarray")(frame, py::arg("dtype") = m_np.attr("uint8"));
     }
@@ -221,6 +250,156 @@ std::string timing_report(const IntervalTimer &batches, const IntervalTimer &gen
     return ss.str();
 }
 
+// CVVP_DEVICES=0,1,...: the CUDA devices the two entry points spread their work over (default: the current device)
+std::vector<int> device_list()
+{
+    std::vector<int> out;
+    if (const char *e = std::getenv("CVVP_DEVICES")) {
+        std::stringstream ss{std::string(e)};
+        std::string tok;
+        while (std::getline(ss, tok, ','))
+            if (!tok.empty())
+                out.push_back(std::atoi(tok.c_str()));
+    }
+    if (out.empty())
+        out.push_back(-1);
+    return out;
+}
+
+// page-locked host buffer (cvvp_host_alloc): a decoded frame written here goes to the device without staging
+struct PinnedBuffer {
+    std::uint8_t *p{nullptr};
+    explicit PinnedBuffer(std::size_t bytes)
+    {
+        void *q = nullptr;
+        if (cvvp_host_alloc(bytes, &q) != CVVP_OK)
+            throw std::runtime_error(std::string("cvvidproc(" CVVP_HOST_VERSION "): ") + cvvp_last_error(nullptr));
+        p = static_cast<std::uint8_t *>(q);
+    }
+    ~PinnedBuffer() { cvvp_host_free(p); }
+    PinnedBuffer(const PinnedBuffer &) = delete;
+    PinnedBuffer &operator=(const PinnedBuffer &) = delete;
+};
+
+// The decode thread (the reference's generator thread, cv_vid_objecttrack_helpers.cpp:71-93): it is handed storage for
+// a batch of frames and fills it with VideoCapture.read, taking the GIL frame by frame (cv2 drops it while decoding,
+// so the tracker callback on the calling thread and the decoder run side by side).
+class DecodeWorker
+{
+public:
+    struct Job {
+        std::uint8_t *dst;
+        std::size_t pitch;
+        long long max_frames, prefilled;
+    };
+    struct Done {
+        long long n{0};
+        bool eof{false};
+        std::string error;
+    };
+    DecodeWorker(FrameSource &vid, int rows, int cols, int channels, long long frames_left)
+        : m_vid{vid}, m_rows{rows}, m_cols{cols}, m_channels{channels}, m_left{frames_left}
+    {
+        m_thread = std::thread([this] { run(); });
+    }
+    ~DecodeWorker() // callers hold the GIL or not: the worker never blocks on it while stopping
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_mu);
+            m_stop = true;
+        }
+        m_cv.notify_all();
+        if (m_thread.joinable()) {
+            py::gil_scoped_release nogil; // a read in flight needs the GIL to finish
+            m_thread.join();
+        }
+    }
+    void push(const Job &j)
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_mu);
+            m_jobs.push_back(j);
+        }
+        m_cv.notify_all();
+    }
+    // a finished batch, if any; waits up to `wait_us` for one (call without the GIL when waiting)
+    bool pop(Done &d, long long wait_us)
+    {
+        std::unique_lock<std::mutex> lk(m_mu);
+        if (m_done.empty() && wait_us > 0)
+            m_cv_done.wait_for(lk, std::chrono::microseconds(wait_us), [this] { return !m_done.empty(); });
+        if (m_done.empty())
+            return false;
+        d = std::move(m_done.front());
+        m_done.pop_front();
+        return true;
+    }
+
+    // waits up to `wait_us` for a finished batch without taking it (call without the GIL)
+    void wait_done(long long wait_us)
+    {
+        std::unique_lock<std::mutex> lk(m_mu);
+        if (m_done.empty())
+            m_cv_done.wait_for(lk, std::chrono::microseconds(wait_us), [this] { return !m_done.empty(); });
+    }
+
+private:
+    void run()
+    {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m_mu);
+                m_cv.wait(lk, [this] { return m_stop || !m_jobs.empty(); });
+                if (m_stop)
+                    return;
+                j = m_jobs.front();
+                m_jobs.pop_front();
+            }
+            Done d;
+            d.n = j.prefilled;
+            while (d.n < j.max_frames && m_left > 0 && !d.eof) {
+                {
+                    std::lock_guard<std::mutex> lk(m_mu);
+                    if (m_stop)
+                        return;
+                }
+                py::gil_scoped_acquire gil;
+                try {
+                    if (m_vid.read_into(j.dst + std::size_t(d.n) * j.pitch, m_rows, m_cols, m_channels)) {
+                        ++d.n;
+                        --m_left;
+                    } else {
+                        d.eof = true;
+                    }
+                } catch (py::error_already_set &e) {
+                    d.error = e.what();
+                    d.eof = true;
+                } catch (const std::exception &e) {
+                    d.error = e.what();
+                    d.eof = true;
+                }
+            }
+            if (m_left <= 0)
+                d.eof = true;
+            {
+                std::lock_guard<std::mutex> lk(m_mu);
+                m_done.push_back(std::move(d));
+            }
+            m_cv_done.notify_all();
+        }
+    }
+    FrameSource &m_vid;
+    int m_rows, m_cols, m_channels;
+    long long m_left;
+    std::thread m_thread;
+    std::mutex m_mu;
+    std::condition_variable m_cv, m_cv_done;
+    std::deque<Job> m_jobs;
+    std::deque<Done> m_done;
+    bool m_stop{false};
+};
+
 // ---------------------------------------------------------------------------------------------------------------------
 // GetVideoBackground  (cv_vid_bg_helpers.cpp:197-264)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -261,32 +440,66 @@ py::object GetVideoBackground(const VidBgPack &pack)
     vid.set_crop(crop);
     vid.configure();
 
+    // The reference releases the GIL for this whole call (py_bindings.cpp:63-66).  Here the decoder is Python's cv2, which
+    // needs the GIL to be CALLED but drops it while it decodes; everything else that takes time -- the uploads, the
+    // device frame preparation, the select at the end -- runs with the GIL released, so other Python threads make
+    // progress throughout.
     const bool on_device = !host_prep();
+    const std::vector<int> devices = device_list();
     std::unique_ptr<GpuMedianAlgo> algo_p; // built once the first decoded frame tells the channel count
+    std::unique_ptr<GpuShardedMedianAlgo> sharded_p; // CVVP_DEVICES names several devices
+    std::unique_ptr<PinnedBuffer> pinned;  // the decoder writes every frame here: no fresh array, no staging copy
     long long consumed = 0;
     int rows = 0, cols = 0, channels = 1;
     IntervalTimer t_batch, t_gen, t_unit, t_consume;
     while (consumed < frames_to_analyze) { // generator :128-135
         t_batch.start();
         t_gen.start();
-        py::object f = on_device ? vid.next_decoded() : vid.next();
+        const std::uint8_t *data = nullptr;
+        py::object keep; // keeps the decoded array alive until it has been pushed
+        if (on_device && pinned) {
+            if (!vid.read_into(pinned->p, rows, cols, channels)) {
+                t_gen.stop();
+                break;
+            }
+            data = pinned->p;
+        } else {
+            keep = on_device ? vid.next_decoded() : vid.next();
+            if (keep.is_none()) {
+                t_gen.stop();
+                break;
+            }
+            py::array a = keep.cast<py::array>();
+            array_geometry(a, rows, cols, channels);
+            data = static_cast<const std::uint8_t *>(a.data());
+        }
         t_gen.stop();
-        if (f.is_none())
-            break;
-        py::array a = f.cast<py::array>();
-        array_geometry(a, rows, cols, channels);
-        if (!algo_p) {
-            GpuMedianPack mp{-1, frames_to_analyze, {}};
-            if (on_device)
-                mp.source = vid.format_for(rows, cols, channels);
-            algo_p = std::make_unique<GpuMedianAlgo>(mp);
+        if (!algo_p && !sharded_p) {
+            if (on_device && devices.size() > 1) {
+                sharded_p = std::make_unique<GpuShardedMedianAlgo>(devices, frames_to_analyze, vid.format_for(rows, cols, channels));
+            } else {
+                GpuMedianPack mp{devices[0], frames_to_analyze, {}};
+                if (on_device)
+                    mp.source = vid.format_for(rows, cols, channels);
+                algo_p = std::make_unique<GpuMedianAlgo>(mp);
+            }
         }
         t_unit.start();
         if (on_device) {
             CVVP_ASSERT(rows == int(fh) && cols == int(fw));
-            algo_p->InsertDecoded(static_cast<const std::uint8_t *>(a.data()), 1, std::size_t(rows) * cols * channels);
+            const std::size_t bytes = std::size_t(rows) * cols * channels;
+            {
+                py::gil_scoped_release nogil;
+                if (sharded_p)
+                    sharded_p->InsertDecoded(data, 1, bytes);
+                else
+                    algo_p->InsertDecoded(data, 1, bytes);
+            }
+            if (!pinned)
+                pinned = std::make_unique<PinnedBuffer>(bytes);
         } else {
-            algo_p->InsertRaw(static_cast<const std::uint8_t *>(a.data()), 1, rows, cols, channels, std::size_t(rows) * cols * channels);
+            py::gil_scoped_release nogil;
+            algo_p->InsertRaw(data, 1, rows, cols, channels, std::size_t(rows) * cols * channels);
         }
         t_unit.stop();
         t_batch.stop();
@@ -294,11 +507,19 @@ py::object GetVideoBackground(const VidBgPack &pack)
     }
     t_consume.start();
     std::unique_ptr<FrameBatch> res;
-    if (algo_p) {
-        algo_p->NotifyNoMoreTokens();
-        res = algo_p->TryGetResult();
+    {
+        py::gil_scoped_release nogil;
+        if (sharded_p) {
+            sharded_p->NotifyNoMoreTokens();
+            res = sharded_p->TryGetResult();
+        } else if (algo_p) {
+            algo_p->NotifyNoMoreTokens();
+            res = algo_p->TryGetResult();
+        }
     }
     t_consume.stop();
+    if (pack.print_timing_report) // cv_vid_bg_helpers.cpp:154-155: printed inside VidBackgroundWithAlgo, result or not
+        std::cout << timing_report(t_batch, t_gen, t_consume, t_unit);
     if (!res || res->empty())
         return py::none();
     // shape (H, W) for one channel, (H, W, C) otherwise (ndarray_converter.cpp:141-142)
@@ -307,8 +528,6 @@ py::object GetVideoBackground(const VidBgPack &pack)
         shape.push_back(res->channels);
     py::array_t<std::uint8_t> out(shape);
     std::memcpy(out.mutable_data(), res->data.data(), res->data.size());
-    if (pack.print_timing_report) // cv_vid_bg_helpers.cpp:154-155
-        std::cout << timing_report(t_batch, t_gen, t_consume, t_unit);
     return std::move(out);
 }
 
@@ -402,20 +621,24 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
     bool any = false;
     IntervalTimer h_batch, h_gen, h_unit, h_consume, a_batch, a_gen, a_unit, a_consume;
 
-    // the assign stage: strictly in frame order, one call per frame (assign_objects_algo.h:111-133)
-    auto deliver = [&](const FrameBatch &masks) {
+    // the assign stage: strictly in frame order, one call per frame (assign_objects_algo.h:111-133).  The callback gets a
+    // numpy array that OWNS its bytes (it may keep it), copied from wherever the masks lie (a batch, a pinned view).
+    const int mrows = crop.height, mcols = crop.width;
+    const std::size_t mbytes = std::size_t(mrows) * mcols;
+    auto deliver_raw = [&](const std::uint8_t *masks, std::size_t pitch, long long n, const cvvp_component *comps_all,
+                           const int *ncomps_all, int max_comps, const std::int32_t *labels_all) {
         a_batch.start();
         a_gen.start(); // the intermediary hands the ordered masks over (mat_set_intermediary.h:84-114)
         a_gen.stop();
-        for (int i = 0; i < masks.n; ++i) {
-            py::array_t<std::uint8_t> bw({masks.rows, masks.cols});
-            std::memcpy(bw.mutable_data(), masks.data.data() + std::size_t(i) * masks.frame_bytes(), masks.frame_bytes());
+        for (long long i = 0; i < n; ++i) {
+            py::array_t<std::uint8_t> bw({mrows, mcols});
+            std::memcpy(bw.mutable_data(), masks + std::size_t(i) * pitch, mbytes);
             using namespace pybind11::literals;
             a_unit.start();
             if (want_comps) {
-                const int total = masks.component_count(i);
-                const int cnt = std::min(total, masks.max_comps);
-                const cvvp_component *cs = masks.components(i);
+                const int total = ncomps_all ? ncomps_all[i] : 0;
+                const int cnt = std::min(total, max_comps);
+                const cvvp_component *cs = comps_all + std::size_t(i) * max_comps;
                 py::array_t<std::int32_t> stats({cnt, 5});
                 py::array_t<double> cents({cnt, 2});
                 py::array_t<std::int32_t> first({cnt, 2});
@@ -438,9 +661,9 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
                 comps["stats"] = stats;
                 comps["centroids"] = cents;
                 comps["first"] = first;
-                if (want_labels) {
-                    py::array_t<std::int32_t> lab({masks.rows, masks.cols});
-                    std::memcpy(lab.mutable_data(), masks.label_image(i), masks.frame_bytes() * sizeof(std::int32_t));
+                if (want_labels && labels_all) {
+                    py::array_t<std::int32_t> lab({mrows, mcols});
+                    std::memcpy(lab.mutable_data(), labels_all + std::size_t(i) * mbytes, mbytes * sizeof(std::int32_t));
                     comps["labels"] = lab;
                 }
                 next_id = pack.assign_objects_pack.function("bw_frame"_a = bw, "frames_processed"_a = num_processed,
@@ -462,9 +685,116 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
         }
         a_batch.stop();
     };
+    auto deliver = [&](const FrameBatch &masks) {
+        deliver_raw(masks.data.data(), masks.frame_bytes(), masks.n, masks.comps.empty() ? nullptr : masks.comps.data(),
+                    masks.ncomps.empty() ? nullptr : masks.ncomps.data(), masks.max_comps,
+                    masks.labels.empty() ? nullptr : masks.labels.data());
+    };
 
+    const std::vector<int> devices = device_list();
+    if (on_device) {
+        // ---- pipelined path: decode thread -> pinned queue slots -> device(s) -> ordered callbacks ----
+        // the first frame is decoded here: it tells the channel count the device format needs
+        h_gen.start();
+        py::object f0 = vid.next_decoded();
+        h_gen.stop();
+        if (!f0.is_none()) {
+            py::array a0 = f0.cast<py::array>();
+            int r, c, ch;
+            array_geometry(a0, r, c, ch);
+            CVVP_ASSERT(r == fh && c == fw);
+            hp.queue_depth = depth;
+            hp.max_batch = batch_frames;
+            hp.source = vid.format_for(r, c, ch);
+            CVVP_ASSERT_MSG(hp.source.out_channels() == 1, "TrackObjects needs single-channel frames: set grayscale or "
+                                                           "vid_is_grayscale (cv::findContours requires 8UC1)");
+            std::vector<std::unique_ptr<GpuHighlightAlgo>> lanes; // one operator (context + queue) per device
+            for (int d : devices) {
+                GpuHighlightPack lp = hp;
+                lp.device = d;
+                lanes.push_back(std::make_unique<GpuHighlightAlgo>(std::move(lp)));
+            }
+            const long long D = (long long)lanes.size();
+            const int max_comps = lanes[0]->max_components();
+            const std::size_t frame_bytes = std::size_t(r) * c * ch;
+            DecodeWorker worker{vid, r, c, ch, num_frames - 1};
+            long long submitted = 0, delivered = 0; // batches, in frame order: batch k lives on lane k % D
+            bool decode_done = false, job_out = false, first = true;
+            std::string error;
+            while (error.empty()) {
+                // 1. keep the decoder busy: hand it the next free slot of the lane whose turn it is
+                if (!job_out && !decode_done) {
+                    GpuHighlightAlgo &L = *lanes[std::size_t(submitted % D)];
+                    if (L.Pending() < L.Depth()) {
+                        const GpuHighlightAlgo::Slot slot = L.AcquireSlot();
+                        CVVP_ASSERT(slot.pitch >= frame_bytes);
+                        long long pre = 0;
+                        if (first) { // the frame decoded above is the slot's first one
+                            std::memcpy(slot.frames, a0.data(), frame_bytes);
+                            pre = 1;
+                            first = false;
+                        }
+                        h_batch.start();
+                        h_gen.start();
+                        worker.push(DecodeWorker::Job{slot.frames, slot.pitch, std::min(slot.max_frames, batch_frames), pre});
+                        job_out = true;
+                    }
+                }
+                // 2. a filled slot goes to its device
+                DecodeWorker::Done done;
+                bool progressed = false;
+                if (job_out && worker.pop(done, 0)) {
+                    h_gen.stop();
+                    GpuHighlightAlgo &L = *lanes[std::size_t(submitted % D)];
+                    h_unit.start();
+                    L.CommitSlot(done.n);
+                    h_unit.stop();
+                    h_batch.stop();
+                    job_out = false;
+                    if (done.n > 0)
+                        ++submitted;
+                    if (done.eof)
+                        decode_done = true;
+                    if (!done.error.empty())
+                        error = done.error;
+                    progressed = true;
+                }
+                // 3. the oldest batch goes to the tracker when it is complete -- or when nothing else can move
+                if (delivered < submitted) {
+                    GpuHighlightAlgo &L = *lanes[std::size_t(delivered % D)];
+                    const bool must = decode_done || (!job_out && lanes[std::size_t(submitted % D)]->Pending() >= lanes[0]->Depth());
+                    if (L.Ready() || (must && !job_out)) {
+                        h_consume.start();
+                        GpuHighlightAlgo::MaskView v;
+                        {
+                            py::gil_scoped_release nogil; // other Python threads (and the decoder) run while this waits
+                            v = L.NextView();
+                        }
+                        h_consume.stop();
+                        deliver_raw(v.masks, v.pitch, v.n, v.comps, v.ncomps, max_comps, nullptr);
+                        L.ReleaseView();
+                        ++delivered;
+                        progressed = true;
+                    }
+                } else if (decode_done && !job_out) {
+                    break; // everything decoded, submitted and delivered
+                }
+                // 4. nothing moved: wait for the decoder (briefly, so that a completed batch is noticed soon)
+                if (!progressed) {
+                    py::gil_scoped_release nogil;
+                    if (job_out) {
+                        worker.wait_done(200);
+                    } else {
+                        std::this_thread::sleep_for(std::chrono::microseconds(100));
+                    }
+                }
+            }
+            if (!error.empty())
+                throw std::runtime_error(error);
+        }
+    }
     long long consumed = 0;
-    bool eof = false;
+    bool eof = on_device; // the pipelined path above has consumed the stream
     while (!eof && consumed < num_frames) {
         h_batch.start();
         h_gen.start();

@@ -7,9 +7,11 @@
 // the same order statistic with an on-chip BIT-SLICED RADIX SELECT:
 //
 //   tile      = P consecutive elements (P = 128 >> LOG2S) x all N frames, resident on one SM;
-//   producer  = one thread streaming the tile through a ring of 4 KB TMA boxes
-//               (P bytes x 4096/P frames each, zero-filled out of bounds);
-//   transpose = each consumer warp takes one 4 KB stage, every lane reads 32 words (4 elements x
+//   streaming = a ring of 4 KB TMA boxes (P bytes x 4096/P frames each, zero-filled out of bounds).  There is NO
+//               producer warp: each of the 12 transposer warps owns two private ring slots and re-issues the TMA
+//               load of its own next stage as soon as its lanes have read a slot (median_pipe.cu), so no "empty"
+//               barriers exist and every mbarrier wait is for the direct successor of a fill the warp consumed;
+//   transpose = each transposer warp takes one 4 KB stage, every lane reads 32 words (4 elements x
 //               32 frame slots) and bit-transposes them in registers (32x32 bit matrix:
 //               2 PRMT stages + 3 shift/LOP3 stages) into 4 elements x 8 bit planes, one word =
 //               32 frames of one bit of one element; planes go to shared memory (swizzled so both

@@ -84,8 +84,11 @@ CVVP_API int cvvp_ctx_copy_to_host(cvvp_ctx *ctx, void *host_dst, const void *de
  * (histogram_median_algo.h:160-166).
  * ------------------------------------------------------------------------------------------- */
 
-/* Start a median job on frames of `nelem` bytes.  nframes_hint > 0 pre-sizes the device stack
- * (it grows if more frames are pushed). */
+/* Start a median job on frames of `nelem` bytes.  nframes_hint > 0 sizes the device stack for exactly that many
+ * frames (rounded up to 16; it grows by half if more are pushed, and the old and new stacks coexist while it does).
+ * The job keeps every pushed frame resident in device memory -- frames x round_up(nelem, 128) bytes must fit the
+ * device, unlike the reference's histograms, whose size is independent of the frame count
+ * (histogram_median_algo.h:123-126); a stack that does not fit fails with CVVP_ERR_NOMEM. */
 CVVP_API int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint);
 /* Append n frames from HOST memory; frame i starts at frames + i*frame_stride and holds nelem
  * contiguous bytes.  The copy is asynchronous when `frames` is pinned (cvvp_host_alloc or
@@ -95,6 +98,11 @@ CVVP_API int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hi
 CVVP_API int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride);
 /* Number of frames pushed so far. */
 CVVP_API long long cvvp_median_count(const cvvp_ctx *ctx);
+/* The running job's device stack (frame f at *d_frames + f * *frame_stride), for callers that run a device-resident
+ * form on the pushed frames -- a rank of a frame-sharded job uploads its chunk with cvvp_median_push and hands this
+ * pointer to cvvp_median_shard_phase.  Orders every push made so far before work queued on the compute stream
+ * afterwards; the pointer is valid until the next push (the stack may move when it grows) or the end of the job. */
+CVVP_API int cvvp_median_stack_device(cvvp_ctx *ctx, const uint8_t **d_frames, size_t *frame_stride, long long *nframes);
 /* Run the select over everything pushed and copy the nelem result bytes to HOST memory `out`
  * (synchronous: the result is valid on return).  Ends the job. */
 CVVP_API int cvvp_median_finish(cvvp_ctx *ctx, uint8_t *out);
@@ -298,6 +306,24 @@ CVVP_API int cvvp_highlight_queue_ready(cvvp_ctx *ctx);
  * batch's size is only known on return).  CVVP_ERR_STATE when nothing is pending. */
 CVVP_API int cvvp_highlight_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_stride, long long *n_out,
                                  cvvp_component *comps_out, int *ncomps_out);
+/* Zero-copy forms of submit / next -- the "frames are batched into pinned buffers" of BASELINE.json:north_star.  The
+ * reference's generator fills a token that then moves through the queues without being copied
+ * (Sources/AsyncTokens/token_batch_generator.h:52-67, token_queue.h:60-97); here the token's storage IS the slot:
+ *   cvvp_highlight_slot_acquire  hands out the pinned input of the next free slot: the caller (a video decoder) writes
+ *                                up to *max_frames whole frames into it, frame i at *h_frames + i * *frame_pitch
+ *                                (decoded frames when the queue has a frame format, prepared frames otherwise);
+ *                                CVVP_ERR_STATE when `depth` batches are pending;
+ *   cvvp_highlight_slot_commit   queues the n frames written (n = 0 hands the slot back unused);
+ *   cvvp_highlight_next_view     waits for the oldest pending batch and lends out its pinned results: mask i at
+ *                                *h_masks + i * *mask_pitch, components at (*comps)[i * max_comps + k], counts
+ *                                (*ncomps)[i] (NULL when the queue was begun with max_comps = 0);
+ *   cvvp_highlight_view_release  gives the batch's slot back to the ring.
+ * The pointers are valid until the matching commit / release.  submit / next (copying forms) may be mixed in. */
+CVVP_API int cvvp_highlight_slot_acquire(cvvp_ctx *ctx, uint8_t **h_frames, size_t *frame_pitch, long long *max_frames);
+CVVP_API int cvvp_highlight_slot_commit(cvvp_ctx *ctx, long long n);
+CVVP_API int cvvp_highlight_next_view(cvvp_ctx *ctx, const uint8_t **h_masks, size_t *mask_pitch, long long *n_out,
+                                      const cvvp_component **comps, const int **ncomps);
+CVVP_API int cvvp_highlight_view_release(cvvp_ctx *ctx);
 /* drains and frees the ring (pending results are dropped) */
 CVVP_API int cvvp_highlight_queue_end(cvvp_ctx *ctx);
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_table_covers_header():
     lib = _cabi.load()
-    assert lib.cvvp_abi_version() == 2
+    assert lib.cvvp_abi_version() == 3
     assert set(_cabi.declared_symbols()) <= set(_cabi.BOUND_SYMBOLS)
 
 
@@ -69,4 +69,4 @@ def test_header_is_plain_c_and_links(tmp_path):
     subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(_cabi.HEADER.parent), str(src),
                     "-L", str(lib_dir), "-lcvvp_cuda", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert out == ["2", "3072", "48", "0"]
+    assert out == ["3", "3072", "48", "0"]

@@ -164,3 +164,57 @@ def test_full_hd_queue_matches_synchronous_path(gpu_ctx):
     got = np.concatenate(got)
     assert np.array_equal(got, sync)
     assert np.array_equal(got[7], ho.highlight_objects(frames[7].copy(), p))
+
+
+@pytest.mark.parametrize("depth,batch,decoded", [(1, 3, False), (3, 5, False), (2, 4, True)])
+def test_zero_copy_slots_match_the_copying_forms(gpu_ctx, depth, batch, decoded):
+    """cvvp_highlight_slot_acquire / slot_commit / next_view / view_release: the producer writes whole frames straight
+    into the slot's pinned input (decoded colour frames with a crop when the queue has a format) and the consumer reads
+    the slot's pinned results; same masks, same order as submit / next; the two forms can be mixed"""
+    frames, p = _stream(n=17)
+    H, W = frames.shape[1:]
+    fmt = None
+    src = frames
+    if decoded:
+        pad = np.zeros((len(frames), H + 6, W + 10, 3), np.uint8)
+        pad[:, 4:4 + H, 7:7 + W, 0] = frames
+        pad[..., 1] = 255 - pad[..., 0]
+        src = pad
+        fmt = _cabi.FrameFormat.of(pad.shape[1:], _cabi.FRAMES_CHANNEL0, (7, 4, W, H))
+    want = np.stack([ho.highlight_objects(f.copy(), p) for f in frames])
+    _begin(gpu_ctx, p)
+    try:
+        gpu_ctx.highlight_queue_begin(depth, batch, fmt)
+        fb = int(np.prod(src.shape[1:]))
+        got, i, k = [], 0, 0
+        while i < len(frames) or gpu_ctx.highlight_queue_pending():
+            while i < len(frames) and gpu_ctx.highlight_queue_pending() < depth:
+                n = min(batch, len(frames) - i)
+                if k % 3 == 2:  # every third batch through the copying form
+                    gpu_ctx.highlight_submit(src[i:i + n])
+                else:
+                    slot = gpu_ctx.highlight_slot_acquire()
+                    assert slot.shape[0] == batch and slot.shape[1] >= fb
+                    with pytest.raises(_cabi.CvvpError):  # one slot at a time
+                        gpu_ctx.highlight_slot_acquire()
+                    slot[:n, :fb] = src[i:i + n].reshape(n, fb)
+                    gpu_ctx.highlight_slot_commit(n)
+                i += n
+                k += 1
+            if len(got) % 2:
+                got.append(gpu_ctx.highlight_next().copy())
+            else:
+                view = gpu_ctx.highlight_next_view()
+                with pytest.raises(_cabi.CvvpError):  # the oldest batch is lent out
+                    gpu_ctx.highlight_next()
+                got.append(np.array(view))
+                gpu_ctx.highlight_view_release()
+        slot = gpu_ctx.highlight_slot_acquire()  # handed back unused
+        gpu_ctx.highlight_slot_commit(0)
+        assert gpu_ctx.highlight_queue_pending() == 0
+        with pytest.raises(_cabi.CvvpError):
+            gpu_ctx.highlight_view_release()
+        gpu_ctx.highlight_queue_end()
+    finally:
+        gpu_ctx.highlight_end()
+    assert np.array_equal(np.concatenate(got), want)

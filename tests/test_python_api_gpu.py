@@ -230,3 +230,107 @@ def test_track_objects_on_a_cropped_colour_video(color_video):
     want = _reference_track(gray, p, kwargs)
     assert len(want) > 5
     assert archive == want
+
+
+def _device_lists():
+    import torch
+
+    lists = ["0,0", "0,0,0"]  # several operators on one device: the ordering / exchange logic without a second GPU
+    if torch.cuda.device_count() >= 2:
+        lists.append("0,1")
+    return lists
+
+
+def test_several_devices_one_stream(gray_video, color_video, oracle_median, monkeypatch):
+    """CVVP_DEVICES spreads both entry points over several devices: TrackObjects hands batches to the devices in turn
+    and still delivers the masks strictly in frame order (mat_set_intermediary.h:50-68,84-114); GetVideoBackground
+    gives every device a share of the frames and merges them with the frame-sharded median
+    (cv_vid_bg_helpers.cpp:84-120).  Same archive, same background as with one device."""
+    path, frames = gray_video
+    cpath, cframes = color_video
+    bg1 = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+    assert np.array_equal(bg1, oracle_median(frames))
+    p = ho.canonical_params(bg1)
+    hp = cvp.HighlightObjectsPack(bg1, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                                  p.min_size_threshold, p.width_border)
+    kwargs = {"min_area": 5}
+    want = _reference_track(frames, p, kwargs)
+    monkeypatch.setenv("CVVP_TRACK_BATCH", "4")
+    for devs in _device_lists():
+        monkeypatch.setenv("CVVP_DEVICES", devs)
+        bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+        assert np.array_equal(bg, bg1), devs
+        bgc = cvp.GetVideoBackground(cvp.VidBgPack(cpath, grayscale=True, crop_x=3, crop_y=2, crop_width=41, crop_height=30))
+        gray = np.stack([cv2.cvtColor(np.ascontiguousarray(f[2:32, 3:44]), cv2.COLOR_RGB2GRAY) for f in cframes])
+        assert np.array_equal(bgc, oracle_median(gray)), devs
+        seen = []
+
+        def tracker(bw_frame, frames_processed, objects_prev, objects_archive, next_ID, kwargs):
+            seen.append(frames_processed)
+            return _tracker(bw_frame, frames_processed, objects_prev, objects_archive, next_ID, kwargs)
+
+        for limit in (1, 3):
+            seen.clear()
+            archive = cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(tracker, kwargs),
+                                                              vid_is_grayscale=True, token_storage_limit=limit))
+            assert seen == list(range(len(frames))), (devs, limit)
+            assert archive == want, (devs, limit)
+
+
+def test_other_python_threads_run_during_the_calls(gray_video):
+    """The reference releases the GIL in GetVideoBackground (py_bindings.cpp:63-66); here the uploads, the device work
+    and the waits run without it (and cv2 drops it while decoding), so a second Python thread keeps making progress --
+    also during TrackObjects, whose callbacks are the only part that needs the GIL."""
+    import threading
+    import time
+
+    path, frames = gray_video
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+    ticks, stop = [0], threading.Event()
+
+    def spin():
+        while not stop.is_set():
+            ticks[0] += 1
+            time.sleep(0.0005)
+
+    t = threading.Thread(target=spin)
+    t.start()
+    try:
+        before = ticks[0]
+        t0 = time.perf_counter()
+        for _ in range(3):
+            cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+        dt = time.perf_counter() - t0
+        during_bg = ticks[0] - before
+        p = ho.canonical_params(bg)
+        hp = cvp.HighlightObjectsPack(bg, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                                      p.min_size_threshold, p.width_border)
+        before = ticks[0]
+        cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(_tracker, {"min_area": 5}), vid_is_grayscale=True))
+        during_track = ticks[0] - before
+    finally:
+        stop.set()
+        t.join()
+    # a thread that sleeps 0.5 ms per tick gets at most ~1000-2000 ticks per second; demand a clear share of that
+    assert during_bg >= max(5, int(200 * dt)), (during_bg, dt)
+    assert during_track >= 3
+
+
+def test_a_failing_callback_ends_the_call_cleanly(gray_video):
+    """an exception in the tracker callback propagates (the decode thread is stopped, the queues are drained) and the
+    module stays usable"""
+    path, frames = gray_video
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+    p = ho.canonical_params(bg)
+    hp = cvp.HighlightObjectsPack(bg, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
+                                  p.min_size_threshold, p.width_border)
+
+    def bad(bw_frame, frames_processed, objects_prev, objects_archive, next_ID, kwargs):
+        if frames_processed == 9:
+            raise ValueError("tracker gave up")
+        return next_ID
+
+    with pytest.raises(ValueError, match="tracker gave up"):
+        cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(bad, {}), vid_is_grayscale=True))
+    archive = cvp.TrackObjects(cvp.VidObjectTrackPack(path, hp, cvp.AssignObjectsPack(_tracker, {"min_area": 5}), vid_is_grayscale=True))
+    assert archive == _reference_track(frames, p, {"min_area": 5})
