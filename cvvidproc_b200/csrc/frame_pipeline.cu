@@ -214,7 +214,8 @@ struct HighlightQueue {
     size_t host_pitch{0};                          // bytes between the caller's frames in a slot's pinned input
     std::vector<HqSlot> slots;
     int head{0}, count{0};
-    bool acquired{false}; // the slot after the pending ones is in the caller's hands (slot_acquire .. slot_commit)
+    int acquired{0};      // slots after the pending ones that are in the caller's hands (slot_acquire .. slot_commit)
+    bool gap{false};      // an acquired slot was handed back unused while later ones were still out: those cannot be queued
     bool lent{false};     // the oldest pending slot's results are in the caller's hands (next_view .. view_release)
     bool failed{false};   // a submit died half-way: work of unknown extent is queued on the slot
 };
@@ -382,8 +383,9 @@ static int check_can_fill(cvvp_ctx *ctx, HighlightQueue *q)
         return fail(ctx, CVVP_ERR_STATE, "highlight queue: not begun");
     if (q->failed)
         return fail(ctx, CVVP_ERR_STATE, "highlight queue: an earlier submit failed; end the queue and begin a new one");
-    if (q->count == q->depth)
-        return fail(ctx, CVVP_ERR_STATE, "highlight queue: %d batches pending; call cvvp_highlight_next first", q->depth);
+    if (q->count + q->acquired >= q->depth)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: %d batches pending or being filled; call cvvp_highlight_next first",
+                    q->depth);
     return CVVP_OK;
 }
 
@@ -394,7 +396,7 @@ int highlight_queue_submit(cvvp_ctx *ctx, const uint8_t *frames, long long n, si
     if (rc != CVVP_OK)
         return rc;
     if (q->acquired)
-        return fail(ctx, CVVP_ERR_STATE, "highlight queue: a slot is acquired; commit it before submitting");
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: slots are acquired; commit them before submitting");
     if (!frames || n < 1 || n > q->max_batch || frame_stride < q->in_offset + q->in_bytes)
         return fail(ctx, CVVP_ERR_INVALID, "highlight queue: bad submit arguments (1 <= n <= %lld frames of at least %zu bytes)",
                     q->max_batch, q->in_offset + q->in_bytes);
@@ -415,10 +417,8 @@ int highlight_slot_acquire(cvvp_ctx *ctx, uint8_t **h_frames, size_t *frame_pitc
     int rc = check_can_fill(ctx, q);
     if (rc != CVVP_OK)
         return rc;
-    if (q->acquired)
-        return fail(ctx, CVVP_ERR_STATE, "highlight queue: a slot is already acquired");
-    HqSlot &s = q->slots[size_t((q->head + q->count) % q->depth)];
-    q->acquired = true;
+    HqSlot &s = q->slots[size_t((q->head + q->count + q->acquired) % q->depth)];
+    q->acquired++;
     *h_frames = s.h_in;
     *frame_pitch = q->host_pitch;
     if (max_frames)
@@ -433,9 +433,14 @@ int highlight_slot_commit(cvvp_ctx *ctx, long long n)
         return fail(ctx, CVVP_ERR_STATE, "highlight queue: no slot is acquired");
     if (n < 0 || n > q->max_batch)
         return fail(ctx, CVVP_ERR_INVALID, "highlight queue: a slot takes 0 .. %lld frames", q->max_batch);
-    q->acquired = false;
-    if (n == 0)
-        return CVVP_OK; // handed back unused
+    if (n > 0 && q->gap)
+        return fail(ctx, CVVP_ERR_STATE, "highlight queue: a slot acquired earlier was handed back unused; batches are queued in "
+                                         "the order their slots were acquired");
+    q->acquired--; // the oldest acquired slot
+    if (n == 0) {  // handed back unused (end of the stream)
+        q->gap = q->acquired > 0;
+        return CVVP_OK;
+    }
     HqSlot &s = q->slots[size_t((q->head + q->count) % q->depth)];
     const int rc = launch_slot(ctx, q, s, n);
     if (rc != CVVP_OK)

@@ -23,11 +23,13 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <deque>
+#include <functional>
 #include <iostream>
 #include <limits>
 #include <memory>
@@ -335,6 +337,10 @@ public:
         return true;
     }
 
+    // is the decode thread waiting for the GIL right now?  The calling thread hands it over between tracker callbacks:
+    // CPython switches a thread that holds the GIL out only after its switch interval (5 ms), which would leave the
+    // decoder idle after every frame while a batch of callbacks runs.
+    bool wants_gil() const { return m_wants_gil.load(std::memory_order_acquire); }
     // waits up to `wait_us` for a finished batch without taking it (call without the GIL)
     void wait_done(long long wait_us)
     {
@@ -364,7 +370,9 @@ private:
                     if (m_stop)
                         return;
                 }
+                m_wants_gil.store(true, std::memory_order_release);
                 py::gil_scoped_acquire gil;
+                m_wants_gil.store(false, std::memory_order_release);
                 try {
                     if (m_vid.read_into(j.dst + std::size_t(d.n) * j.pitch, m_rows, m_cols, m_channels)) {
                         ++d.n;
@@ -398,6 +406,7 @@ private:
     std::deque<Job> m_jobs;
     std::deque<Done> m_done;
     bool m_stop{false};
+    std::atomic<bool> m_wants_gil{false};
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -625,12 +634,15 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
     // numpy array that OWNS its bytes (it may keep it), copied from wherever the masks lie (a batch, a pinned view).
     const int mrows = crop.height, mcols = crop.width;
     const std::size_t mbytes = std::size_t(mrows) * mcols;
+    std::function<void()> between_frames; // pipelined path: keeps the decoder and the device fed while a batch is delivered
     auto deliver_raw = [&](const std::uint8_t *masks, std::size_t pitch, long long n, const cvvp_component *comps_all,
                            const int *ncomps_all, int max_comps, const std::int32_t *labels_all) {
         a_batch.start();
         a_gen.start(); // the intermediary hands the ordered masks over (mat_set_intermediary.h:84-114)
         a_gen.stop();
         for (long long i = 0; i < n; ++i) {
+            if (between_frames)
+                between_frames();
             py::array_t<std::uint8_t> bw({mrows, mcols});
             std::memcpy(bw.mutable_data(), masks + std::size_t(i) * pitch, mbytes);
             using namespace pybind11::literals;
@@ -718,52 +730,65 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
             const int max_comps = lanes[0]->max_components();
             const std::size_t frame_bytes = std::size_t(r) * c * ch;
             DecodeWorker worker{vid, r, c, ch, num_frames - 1};
-            long long submitted = 0, delivered = 0; // batches, in frame order: batch k lives on lane k % D
-            bool decode_done = false, job_out = false, first = true;
+            // batches in frame order: batch k lives on lane k % D.  handed >= committed >= delivered.
+            long long handed = 0, popped = 0, committed = 0, delivered = 0; // popped: slots the decoder gave back
+            std::vector<int> out_on_lane(lanes.size(), 0); // slots of the lane the decoder holds
+            bool decode_done = false, first = true;
             std::string error;
-            while (error.empty()) {
-                // 1. keep the decoder busy: hand it the next free slot of the lane whose turn it is
-                if (!job_out && !decode_done) {
-                    GpuHighlightAlgo &L = *lanes[std::size_t(submitted % D)];
-                    if (L.Pending() < L.Depth()) {
-                        const GpuHighlightAlgo::Slot slot = L.AcquireSlot();
-                        CVVP_ASSERT(slot.pitch >= frame_bytes);
-                        long long pre = 0;
-                        if (first) { // the frame decoded above is the slot's first one
-                            std::memcpy(slot.frames, a0.data(), frame_bytes);
-                            pre = 1;
-                            first = false;
-                        }
-                        h_batch.start();
-                        h_gen.start();
-                        worker.push(DecodeWorker::Job{slot.frames, slot.pitch, std::min(slot.max_frames, batch_frames), pre});
-                        job_out = true;
-                    }
-                }
-                // 2. a filled slot goes to its device
+            // non-blocking: queue the slots the decoder has filled (in order), hand it every free slot to work ahead
+            auto service = [&]() {
                 DecodeWorker::Done done;
-                bool progressed = false;
-                if (job_out && worker.pop(done, 0)) {
+                while (handed > popped && worker.pop(done, 0)) {
                     h_gen.stop();
-                    GpuHighlightAlgo &L = *lanes[std::size_t(submitted % D)];
+                    const std::size_t lane = std::size_t(popped % D);
                     h_unit.start();
-                    L.CommitSlot(done.n);
+                    lanes[lane]->CommitSlot(done.n);
                     h_unit.stop();
                     h_batch.stop();
-                    job_out = false;
-                    if (done.n > 0)
-                        ++submitted;
+                    out_on_lane[lane]--;
+                    ++popped;
+                    if (done.n > 0) // (a slot that comes back empty at the end of the stream is not a batch)
+                        ++committed;
                     if (done.eof)
                         decode_done = true;
-                    if (!done.error.empty())
+                    if (!done.error.empty() && error.empty())
                         error = done.error;
-                    progressed = true;
                 }
-                // 3. the oldest batch goes to the tracker when it is complete -- or when nothing else can move
-                if (delivered < submitted) {
+                while (!decode_done && error.empty()) {
+                    const std::size_t lane = std::size_t(handed % D);
+                    GpuHighlightAlgo &L = *lanes[lane];
+                    if (L.Pending() + out_on_lane[lane] >= L.Depth())
+                        break;
+                    const GpuHighlightAlgo::Slot slot = L.AcquireSlot();
+                    CVVP_ASSERT(slot.pitch >= frame_bytes);
+                    long long pre = 0;
+                    if (first) { // the frame decoded above is the first slot's first one
+                        std::memcpy(slot.frames, a0.data(), frame_bytes);
+                        pre = 1;
+                        first = false;
+                    }
+                    h_batch.start();
+                    h_gen.start();
+                    worker.push(DecodeWorker::Job{slot.frames, slot.pitch, std::min(slot.max_frames, batch_frames), pre});
+                    out_on_lane[lane]++;
+                    ++handed;
+                }
+            };
+            between_frames = [&]() {
+                service();
+                if (worker.wants_gil()) { // hand the GIL to the decode thread: it needs it for a moment per frame
+                    py::gil_scoped_release nogil;
+                    for (int spin = 0; spin < 2000 && worker.wants_gil(); ++spin)
+                        std::this_thread::yield();
+                }
+            };
+            while (error.empty()) {
+                service();
+                if (delivered < committed) {
+                    // the oldest batch goes to the tracker: now if it is complete, else once nothing else can move
                     GpuHighlightAlgo &L = *lanes[std::size_t(delivered % D)];
-                    const bool must = decode_done || (!job_out && lanes[std::size_t(submitted % D)]->Pending() >= lanes[0]->Depth());
-                    if (L.Ready() || (must && !job_out)) {
+                    const bool idle = decode_done || handed == popped; // the decoder holds no slot: a lane is full
+                    if (L.Ready() || idle) {
                         h_consume.start();
                         GpuHighlightAlgo::MaskView v;
                         {
@@ -774,21 +799,19 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
                         deliver_raw(v.masks, v.pitch, v.n, v.comps, v.ncomps, max_comps, nullptr);
                         L.ReleaseView();
                         ++delivered;
-                        progressed = true;
+                        continue;
                     }
-                } else if (decode_done && !job_out) {
-                    break; // everything decoded, submitted and delivered
+                } else if (decode_done && handed == popped) {
+                    break; // everything decoded, queued and delivered
                 }
-                // 4. nothing moved: wait for the decoder (briefly, so that a completed batch is noticed soon)
-                if (!progressed) {
-                    py::gil_scoped_release nogil;
-                    if (job_out) {
-                        worker.wait_done(200);
-                    } else {
-                        std::this_thread::sleep_for(std::chrono::microseconds(100));
-                    }
-                }
+                // nothing to deliver yet: wait for the decoder (briefly, so that a completed batch is noticed soon)
+                py::gil_scoped_release nogil;
+                if (handed > popped)
+                    worker.wait_done(200);
+                else
+                    std::this_thread::sleep_for(std::chrono::microseconds(100));
             }
+            between_frames = nullptr;
             if (!error.empty())
                 throw std::runtime_error(error);
         }

@@ -311,9 +311,12 @@ CVVP_API int cvvp_highlight_next(cvvp_ctx *ctx, uint8_t *masks_out, size_t out_s
  * (Sources/AsyncTokens/token_batch_generator.h:52-67, token_queue.h:60-97); here the token's storage IS the slot:
  *   cvvp_highlight_slot_acquire  hands out the pinned input of the next free slot: the caller (a video decoder) writes
  *                                up to *max_frames whole frames into it, frame i at *h_frames + i * *frame_pitch
- *                                (decoded frames when the queue has a frame format, prepared frames otherwise);
- *                                CVVP_ERR_STATE when `depth` batches are pending;
- *   cvvp_highlight_slot_commit   queues the n frames written (n = 0 hands the slot back unused);
+ *                                (decoded frames when the queue has a frame format, prepared frames otherwise).
+ *                                Several slots may be out at once (a decoder working ahead); CVVP_ERR_STATE when
+ *                                `depth` batches are pending or being filled;
+ *   cvvp_highlight_slot_commit   queues the n frames written to the OLDEST acquired slot (slots are committed in the
+ *                                order they were acquired).  n = 0 hands it back unused -- the end of the stream: slots
+ *                                acquired after it can then only be handed back as well;
  *   cvvp_highlight_next_view     waits for the oldest pending batch and lends out its pinned results: mask i at
  *                                *h_masks + i * *mask_pitch, components at (*comps)[i * max_comps + k], counts
  *                                (*ncomps)[i] (NULL when the queue was begun with max_comps = 0);

@@ -195,8 +195,6 @@ def test_zero_copy_slots_match_the_copying_forms(gpu_ctx, depth, batch, decoded)
                 else:
                     slot = gpu_ctx.highlight_slot_acquire()
                     assert slot.shape[0] == batch and slot.shape[1] >= fb
-                    with pytest.raises(_cabi.CvvpError):  # one slot at a time
-                        gpu_ctx.highlight_slot_acquire()
                     slot[:n, :fb] = src[i:i + n].reshape(n, fb)
                     gpu_ctx.highlight_slot_commit(n)
                 i += n
@@ -209,8 +207,25 @@ def test_zero_copy_slots_match_the_copying_forms(gpu_ctx, depth, batch, decoded)
                     gpu_ctx.highlight_next()
                 got.append(np.array(view))
                 gpu_ctx.highlight_view_release()
-        slot = gpu_ctx.highlight_slot_acquire()  # handed back unused
-        gpu_ctx.highlight_slot_commit(0)
+        # a decoder working ahead: every free slot may be out at once, they are committed in acquisition order, and the
+        # end of the stream hands the rest back unused
+        slots = [gpu_ctx.highlight_slot_acquire() for _ in range(depth)]
+        with pytest.raises(_cabi.CvvpError):  # the ring is full
+            gpu_ctx.highlight_slot_acquire()
+        m = min(batch, 3)
+        for j, sl in enumerate(slots):
+            sl[:m, :fb] = src[j:j + m].reshape(m, fb)
+        gpu_ctx.highlight_slot_commit(m)
+        for _ in slots[1:]:
+            gpu_ctx.highlight_slot_commit(0)
+        assert gpu_ctx.highlight_queue_pending() == 1
+        assert np.array_equal(gpu_ctx.highlight_next(), want[:m])
+        if depth >= 2:
+            a, b = gpu_ctx.highlight_slot_acquire(), gpu_ctx.highlight_slot_acquire()
+            gpu_ctx.highlight_slot_commit(0)
+            with pytest.raises(_cabi.CvvpError):  # the slot after a returned one cannot be queued any more
+                gpu_ctx.highlight_slot_commit(1)
+            gpu_ctx.highlight_slot_commit(0)
         assert gpu_ctx.highlight_queue_pending() == 0
         with pytest.raises(_cabi.CvvpError):
             gpu_ctx.highlight_view_release()

@@ -86,6 +86,28 @@ def _worker(rank, world, port, nframes, nelem, seed, out_dir):
             dist.all_gather(parts, t)
             return np.concatenate([p.numpy() for p in parts])[:nelem].astype(dtype)
 
+        # ---- the one-pass form first (phases 4, 5): window records to the owners, the owners decide what they can
+        def push_records(rec):
+            padded = np.zeros((world * slice_len, 11), np.int64)
+            padded[:nelem] = rec
+            send = [torch.from_numpy(padded[r * slice_len : (r + 1) * slice_len].copy()) for r in range(world)]
+            recv = [torch.empty_like(send[0]) for _ in range(world)]
+            for owner in range(world):
+                dist.gather(send[owner], recv if rank == owner else None, dst=owner)
+            return np.stack([t.numpy() for t in recv])
+
+        recs = push_records(sm.window_records(mine))                  # phase 4
+        dist.barrier()
+        res_own, ok_own = sm.owner_window_final(recs)                 # phase 5
+        res_w = broadcast(res_own, np.uint8)
+        undecided = torch.tensor([int((~ok_own[: max(0, min(slice_len, nelem - rank * slice_len))]).sum())])
+        dist.all_reduce(undecided)                                    # every rank learns the same number
+        dist.barrier()
+        want = np.sort(stack, axis=0)[nframes // 2]
+        ok_all = broadcast(ok_own.astype(np.uint8), np.uint8).astype(bool)
+        window_ok = bool(np.array_equal(res_w[ok_all], want[ok_all])) and int(undecided[0]) == int((~ok_all).sum())
+        np.save(os.path.join(out_dir, f"win_{rank}.npy"), np.array([window_ok, int(undecided[0])]))
+        # ---- the two-round exchange (what runs when `undecided` is not zero; exact for any input)
         c1 = push(sm.nibble_counts(mine, "hi"))                       # phase 0
         dist.barrier()
         sel_own = sm.owner_pick_hi(c1)                                # phase 1 (pad elements pick garbage, cut below)
@@ -95,7 +117,6 @@ def _worker(rank, world, port, nframes, nelem, seed, out_dir):
         dist.barrier()
         res = broadcast(sm.owner_pick_lo(c2, sel_own), np.uint8)      # phase 3
         dist.barrier()
-        want = np.sort(stack, axis=0)[nframes // 2]
         np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([np.array_equal(res, want)]))
     finally:
         dist.destroy_process_group()
@@ -107,6 +128,31 @@ def test_exchange_protocol_over_gloo(tmp_path, world, nframes, nelem):
     mp.spawn(_worker, args=(world, port, nframes, nelem, 11, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert np.load(tmp_path / f"ok_{r}.npy")[0], f"rank {r}"
+        win = np.load(tmp_path / f"win_{r}.npy")
+        assert win[0], f"rank {r}: the one-pass form decided an element wrongly or the ranks disagree on what is left"
+    assert len({int(np.load(tmp_path / f"win_{r}.npy")[1]) for r in range(world)}) == 1
+
+
+def test_window_model_decides_a_noisy_background_and_never_lies(oracle_median):
+    """the numpy model of phases 4 + 5: a background with sensor-like noise is decided everywhere; unrelated chunks are
+    reported as undecided instead of being answered wrongly"""
+    import shard_model as sm
+
+    rng = np.random.default_rng(8)
+    n, nelem = 600, 400
+    stack = (120 + rng.integers(-3, 5, (n, nelem))).astype(np.uint8)
+    want = oracle_median(stack.reshape(n, 1, nelem)).reshape(-1)
+    for world in (1, 2, 5):
+        recs = np.stack([sm.window_records(stack[sharded.frame_chunk(n, r, world)[0]:][: sharded.frame_chunk(n, r, world)[1]])
+                         for r in range(world)])
+        res, ok = sm.owner_window_final(recs)
+        assert ok.all() and np.array_equal(res, want)
+    stack[:300, :100] = rng.integers(0, 256, (300, 100), dtype=np.uint8)
+    want = oracle_median(stack.reshape(n, 1, nelem)).reshape(-1)
+    recs = np.stack([sm.window_records(stack[:300]), sm.window_records(stack[300:])])
+    res, ok = sm.owner_window_final(recs)
+    assert ok[100:].all() and not ok[:100].all()
+    assert np.array_equal(res[ok], want[ok])
 
 
 def test_shard_model_matches_oracle(oracle_median):
