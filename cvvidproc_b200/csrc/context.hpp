@@ -48,7 +48,10 @@ struct ShardPush {
     const uint32_t *accum; // counts of this rank's earlier frame chunks (8 words per element), or nullptr
     uint32_t slice;
     uint32_t stage; // 1: round 1 stages a tile's count vectors in shared memory and stores them 512 B per warp (peer owners)
-    const uint32_t *gate; // not NULL: the kernel returns at once when *gate == 0 (fallback rounds of a window job)
+    // not NULL: the launch only takes the *tile_count tiles listed in tile_list (128 elements each) instead of all of
+    // them -- the two counting rounds behind a window pass recount only the tiles that hold an undecided element
+    const uint32_t *tile_list;
+    const uint32_t *tile_count;
 };
 struct MedianShard; // median_shard.cu
 

@@ -252,7 +252,7 @@ public:
         long long undecided = 0;
         m_ctx[0]->check(cvvp_median_shard_unresolved(m_ctx[0]->get(), nullptr, &undecided));
         if (undecided != 0)
-            walk(0, 3);
+            walk(10, 13); // the two-round exchange over the tiles that hold an undecided element
         auto out = std::make_unique<FrameBatch>();
         out->n = 1;
         out->rows = m_rows;

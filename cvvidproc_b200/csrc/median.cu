@@ -39,9 +39,9 @@ int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, siz
     // faster there, and reach 16 x 65535 frames (median_shard.cu).  CVVP_MEDIAN_TWO_PASS=0/1 forces either path (tests).
     // Long stacks first try ONE pass of window counting (median_pipe_kernel MODE 3: every 1024-frame launch counts
     // its frames in an 8-value window around its own pilot median; the owner kernel names the median wherever it
-    // lies inside every launch's window) and run the two counting passes only for frames whose elements were not all
-    // resolved -- on the device, gated by a flag, so the call stays asynchronous.  CVVP_MEDIAN_WINDOW=0 skips the
-    // window pass (tests hold both to the oracle).
+    // lies inside every launch's window) and run the two counting passes only over the 128-element tiles that hold an
+    // undecided element -- the tile list is built on the device, so the call stays asynchronous.
+    // CVVP_MEDIAN_WINDOW=0 skips the window pass (tests hold both to the oracle).
     const char *force = getenv("CVVP_MEDIAN_TWO_PASS");
     const bool two_pass = force ? force[0] == '1' : nframes > 2048;
     if (two_pass || nframes > median_max_frames()) {

@@ -163,9 +163,6 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     const uint32_t warp = tid >> 5;
     const uint32_t lane = tid & 31;
 
-    if (MODE != 0 && push.gate && __ldcg(push.gate) == 0u)
-        return; // fallback rounds of a window job in which every element was resolved
-
     if (tid == 0) {
         prefetch_tmap(&tmap);
         for (int i = 0; i < kRing; ++i)
@@ -181,8 +178,14 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     }
     __syncthreads();
 
-    // tiles of this CTA, in the order every role walks them
-    const uint32_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // tiles of this CTA, in the order every role walks them: every gridDim.x-th of all tiles, or of the listed ones
+    const uint32_t *tile_list = MODE != 0 ? push.tile_list : nullptr;
+    const uint32_t ntl = tile_list ? min(__ldcg(push.tile_count), ntiles) : ntiles;
+    const uint32_t my_tiles = blockIdx.x < ntl ? (ntl - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto tile_at = [&](uint32_t t) {
+        const uint32_t idx = blockIdx.x + t * gridDim.x;
+        return tile_list ? __ldcg(tile_list + idx) : idx;
+    };
 
     if (warp >= NSELW) {
         // ===================== transposers (self-service TMA) =====================
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
         // issue the TMA load of the stage at (tile iteration t, stage s) into this warp's slot for its k-th stage
         auto issue = [&](uint32_t k, uint32_t t, uint32_t s) {
             const uint32_t slot = w + kTrWarps * (k & 1u);
-            const uint32_t tile = blockIdx.x + t * gridDim.x;
+            const uint32_t tile = tile_at(t);
             mbar_arrive_expect_tx(&ring_full[slot], kStageBytes);
             tma_load_2d(ring + size_t(slot) * kStageWords, &tmap, &ring_full[slot], int32_t(tile * P),
                         int32_t(s * kSlotsPerStage), l2_policy);
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     const uint32_t k0 = nframes / 2u + (nst * kSlotsPerStage - nframes); // wanted rank incl. zero pad slots
 
     for (uint32_t it = 0; it < my_tiles; ++it) {
-        const uint32_t tile = blockIdx.x + it * gridDim.x;
+        const uint32_t tile = tile_at(it);
         const uint32_t buf = (NBUF == 2) ? (it & 1u) : 0u;
         const uint32_t q = (NBUF == 2) ? (it >> 1) : it;
         mbar_wait(&planes_full[buf], q & 1u);

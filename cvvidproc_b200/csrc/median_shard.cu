@@ -28,8 +28,11 @@
 // intersection [lo - 1, hi] of their windows, so whenever G(lo - 1) <= N/2 < G(hi) the median is the first value
 // there with G(v) > N/2 -- the reference's rule (:160-166) -- and it is stored into every rank's result image.
 // Elements whose median lies outside some source's window (sources with very different content) are counted into
-// every rank's `unresolved` word, and the job then runs phases 0..3 (exact for any input).  A video background
-// resolves everywhere; the result is bit-identical either way.
+// every rank's `unresolved` word and their 128-element tile is flagged on every rank; the job then runs phases
+// 10..13 = phases 0..3 restricted to the flagged tiles (the counting kernels walk a compacted tile list, the owner
+// kernels skip elements of other tiles), so a handful of flickering pixels costs a few tiles, not a second and third
+// pass over the stack.  Phases 0..3 on the whole image stay available (exact for any input on their own).  A video
+// background resolves everywhere; the result is bit-identical either way.
 //
 // Between phases the caller places a cross-rank barrier on the stream (a kernel's peer stores are complete when the
 // kernel is; the barrier orders them before the peer's next kernel).  No kernel ever waits for another rank, so ranks
@@ -60,7 +63,10 @@ struct MedianShard {
                 // the owners sum world * spr vectors in 32 bits (world * spr <= kMaxShardRanks)
     int wsubs{1}; // window records per rank (one per launch of <= 1024 frames) the first receive area has room for
     int cslots{1}; // record slots per rank of the first receive area = max(spr, wsubs)
-    size_t off_flag{0}; // one word: elements the window pass left unresolved (summed over all owners)
+    size_t off_flag{0}; // word 0: elements the window pass left unresolved (summed over all owners); word 1: flagged tiles
+    size_t off_tflag{0}; // [ntiles] words: tile holds an undecided element (written by the owners of its elements)
+    size_t off_tlist{0}; // [ntiles] words: the flagged tiles, compacted (phase 10)
+    uint32_t ntiles{0};
 };
 
 // frames one launch of the counting kernel takes at full tile width (128-byte TMA boxes): 32 stages x 32 frames
@@ -78,7 +84,8 @@ struct OwnerArgs {
     uint32_t *sel[kMaxShardRanks];    // every rank's sel array
     uint8_t *result[kMaxShardRanks];  // every rank's result image
     uint32_t *flag[kMaxShardRanks];   // window pass: every rank's `unresolved` word
-    const uint32_t *gate;             // not NULL: return at once when *gate == 0 (fallback rounds, nothing unresolved)
+    uint32_t *tflag[kMaxShardRanks];  // window pass: every rank's tile flags
+    const uint32_t *only_flagged;     // not NULL (this rank's tile flags): skip elements whose tile is not flagged
 };
 
 // the s-th vector / record of the round lives in slot (s % used) of rank (s / used)
@@ -102,10 +109,8 @@ __device__ __forceinline__ void add_counts(uint32_t (&cnt)[16], const uint32_t *
 // phase 1: one thread per owned element
 __global__ void __launch_bounds__(256) shard_pick_kernel(const __grid_constant__ OwnerArgs A)
 {
-    if (A.gate && __ldcg(A.gate) == 0u)
-        return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < A.owned) {
+    if (i < A.owned && (!A.only_flagged || __ldcg(A.only_flagged + ((size_t(A.rank) * A.slice + i) >> 7)) != 0u)) {
         uint32_t cnt[16];
 #pragma unroll
         for (int b = 0; b < 16; ++b)
@@ -141,10 +146,8 @@ __global__ void __launch_bounds__(256) shard_pick_kernel(const __grid_constant__
 // phase 3: one thread per 4 owned elements (one 32-bit store of result bytes per rank)
 __global__ void __launch_bounds__(256) shard_final_kernel(const __grid_constant__ OwnerArgs A)
 {
-    if (A.gate && __ldcg(A.gate) == 0u)
-        return;
-    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    if (i4 < A.owned) {
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; // four elements of one tile
+    if (i4 < A.owned && (!A.only_flagged || __ldcg(A.only_flagged + ((size_t(A.rank) * A.slice + i4) >> 7)) != 0u)) {
         const size_t e0 = size_t(A.rank) * A.slice + i4;
         uint32_t packed = 0;
         const uint32_t n = min(4u, A.owned - i4);
@@ -182,9 +185,10 @@ __global__ void __launch_bounds__(256) shard_final_kernel(const __grid_constant_
     __threadfence_system();
 }
 
-// phase 5: window records of every source -> result bytes.  One thread per 4 owned elements.  Record of source s for
-// owned element i: counts[(s * slice + i) * 8 ..]: words 0..3 = bins 0..7 (16 bits each), 4 = frames below the
-// window, 5 = window base, 6 = frames of the source (0: the source is empty and is skipped).
+// phase 5: window records of every source -> result bytes.  One thread per owned element (a warp reads 1 KB of
+// consecutive records per source); four neighbouring lanes pool their bytes into one 32-bit store per rank.  Record of
+// source s for owned element i: counts[(s * slice + i) * 8 ..]: words 0..3 = bins 0..7 (16 bits each), 4 = frames below
+// the window, 5 = window base, 6 = frames of the source (0: the source is empty and is skipped).
 __global__ void __launch_bounds__(256) shard_window_final_kernel(const __grid_constant__ OwnerArgs A)
 {
     __shared__ uint32_t delta[9][256]; // per thread: frames whose value first counts at window position i
@@ -192,64 +196,65 @@ __global__ void __launch_bounds__(256) shard_window_final_kernel(const __grid_co
     if (threadIdx.x == 0)
         unresolved = 0;
     __syncthreads();
-    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    uint32_t bad = 0;
-    if (i4 < A.owned) {
-        const size_t e0 = size_t(A.rank) * A.slice + i4;
-        uint32_t packed = 0;
-        const uint32_t n = min(4u, A.owned - i4);
-        for (uint32_t q = 0; q < n; ++q) {
-            // pass 1: N, and the intersection [lo, hi] of the sources' windows
-            uint32_t total = 0, lo = 0, hi = 255;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = i < A.owned;
+    uint32_t med = 0;
+    bool ok = true;
+    if (mine) {
+        ok = false;
+        // pass 1: N, and the intersection [lo, hi] of the sources' windows
+        uint32_t total = 0, lo = 0, hi = 255;
+        for (uint32_t src = 0; src < A.world; ++src) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4 *>(A.counts + (src_slot(A, src) * A.slice + i) * 8u) + 1);
+            if (t.z == 0u)
+                continue;
+            total += t.z;
+            lo = max(lo, t.y);
+            hi = min(hi, t.y + 7u);
+        }
+        const uint32_t k = total / 2u; // halfway rank: first value with cumulative count > N / 2  (:160-166)
+        if (total != 0u && lo <= hi) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+                delta[c][threadIdx.x] = 0;
+            uint32_t cum = 0; // G(lo - 1), then G(lo - 1 + c)
             for (uint32_t src = 0; src < A.world; ++src) {
-                const uint4 t = __ldcg(reinterpret_cast<const uint4 *>(A.counts + (src_slot(A, src) * A.slice + i4 + q) * 8u) + 1);
+                const uint4 *rec = reinterpret_cast<const uint4 *>(A.counts + (src_slot(A, src) * A.slice + i) * 8u);
+                const uint4 t = __ldg(rec + 1);
                 if (t.z == 0u)
                     continue;
-                total += t.z;
-                lo = max(lo, t.y);
-                hi = min(hi, t.y + 7u);
-            }
-            const uint32_t k = total / 2u; // halfway rank: first value with cumulative count > N / 2  (:160-166)
-            uint32_t med = 0;
-            bool ok = false;
-            if (total != 0u && lo <= hi) {
+                const uint4 b = __ldg(rec);
+                const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+                const int o = int(lo - t.y); // window position of lo in this source (0..7)
+                cum += t.x;
 #pragma unroll
-                for (int i = 0; i < 9; ++i)
-                    delta[i][threadIdx.x] = 0;
-                uint32_t cum = 0; // G(lo - 1), then G(lo - 1 + i)
-                for (uint32_t src = 0; src < A.world; ++src) {
-                    const uint4 *rec = reinterpret_cast<const uint4 *>(A.counts + (src_slot(A, src) * A.slice + i4 + q) * 8u);
-                    const uint4 t = __ldcg(rec + 1);
-                    if (t.z == 0u)
-                        continue;
-                    const uint4 b = __ldcg(rec);
-                    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
-                    const int o = int(lo - t.y); // window position of lo in this source (0..7)
-                    cum += t.x;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint32_t cnt = (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xFFFFu);
-                        const int pos = c - o + 1; // value base + c is counted by G(lo - 1 + i) for every i >= pos
-                        delta[pos > 0 ? pos : 0][threadIdx.x] += cnt;
-                    }
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t cnt = (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xFFFFu);
+                    const int pos = c - o + 1; // value base + c is counted by G(lo - 1 + j) for every j >= pos
+                    delta[pos > 0 ? pos : 0][threadIdx.x] += cnt;
                 }
-                cum += delta[0][threadIdx.x];
-                const uint32_t span = hi - lo + 1u; // G is exact for i = 0 .. span
-                if (cum <= k) {
-                    for (uint32_t i = 1; i <= span; ++i) {
-                        cum += delta[i][threadIdx.x];
-                        if (cum > k) {
-                            med = lo - 1u + i;
-                            ok = true;
-                            break;
-                        }
+            }
+            cum += delta[0][threadIdx.x];
+            const uint32_t span = hi - lo + 1u; // G is exact for positions 0 .. span
+            if (cum <= k) {
+                for (uint32_t c = 1; c <= span; ++c) {
+                    cum += delta[c][threadIdx.x];
+                    if (cum > k) {
+                        med = lo - 1u + c;
+                        ok = true;
+                        break;
                     }
                 }
             }
-            if (!ok)
-                ++bad;
-            packed |= med << (8u * q);
         }
+    }
+    // four lanes -> one word (owned slices start at multiples of 128 elements, so element i & ~3 is word aligned)
+    uint32_t packed = med << (8u * (threadIdx.x & 3u));
+    packed |= __shfl_xor_sync(0xFFFFFFFFu, packed, 1);
+    packed |= __shfl_xor_sync(0xFFFFFFFFu, packed, 2);
+    if (mine && (threadIdx.x & 3u) == 0u) {
+        const size_t e0 = size_t(A.rank) * A.slice + i;
+        const uint32_t n = min(4u, A.owned - i);
         for (uint32_t r = 0; r < A.nranks; ++r) {
             uint8_t *dst = A.result[r] + e0;
             if (n == 4u) {
@@ -260,13 +265,26 @@ __global__ void __launch_bounds__(256) shard_window_final_kernel(const __grid_co
             }
         }
     }
-    if (bad)
-        atomicAdd(&unresolved, bad);
+    if (!ok) {
+        atomicAdd(&unresolved, 1u);
+        const size_t tile = (size_t(A.rank) * A.slice + i) >> 7; // the 128-element tile of the counting kernels
+        for (uint32_t r = 0; r < A.nranks; ++r)
+            A.tflag[r][tile] = 1u;
+    }
     __syncthreads();
     if (threadIdx.x == 0 && unresolved != 0u)
         for (uint32_t r = 0; r < A.nranks; ++r)
             atomicAdd_system(A.flag[r], unresolved);
     __threadfence_system();
+}
+
+// phase 10, before the restricted counting: flagged tiles -> compact list (one block; *count is zero on entry)
+__global__ void __launch_bounds__(1024) shard_tile_list_kernel(const uint32_t *__restrict__ flags, uint32_t ntiles,
+                                                               uint32_t *__restrict__ list, uint32_t *__restrict__ count)
+{
+    for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x)
+        if (__ldcg(flags + t) != 0u)
+            list[atomicAdd(count, 1u)] = t;
 }
 
 // a rank without frames still owes every owner a (zero) count vector
@@ -338,8 +356,11 @@ static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, int sp
     sh->off_c2 = counts1_bytes;
     sh->off_sel = counts1_bytes + counts2_bytes;
     sh->off_res = sh->off_sel + round_up(nelem * 4u, 256);
+    sh->ntiles = uint32_t((nelem + 127) / 128);
     sh->off_flag = sh->off_res + round_up(nelem, 256);
-    sh->bytes = sh->off_flag + 256;
+    sh->off_tflag = sh->off_flag + 256;
+    sh->off_tlist = sh->off_tflag + round_up(size_t(sh->ntiles) * 4u, 256);
+    sh->bytes = sh->off_tlist + round_up(size_t(sh->ntiles) * 4u, 256);
     if (cudaMalloc(reinterpret_cast<void **>(&sh->buf), sh->bytes) != cudaSuccess) {
         cudaGetLastError();
         const size_t wanted = sh->bytes;
@@ -413,7 +434,8 @@ static int shard_window_count(cvvp_ctx *ctx, MedianShard *sh, const uint8_t *d_f
     per = (per + 31) / 32 * 32; // whole plane words
     if (per > kChunkFrames)
         per = kChunkFrames;
-    CVVP_CUDA_OK(ctx, cudaMemsetAsync(sh->buf + sh->off_flag, 0, sizeof(uint32_t), s));
+    // the undecided count, the list length and the tile flags of this job (one contiguous region)
+    CVVP_CUDA_OK(ctx, cudaMemsetAsync(sh->buf + sh->off_flag, 0, (sh->off_tflag - sh->off_flag) + size_t(sh->ntiles) * 4u, s));
     for (int j = 0; j < sh->wsubs; ++j) {
         ShardPush push{};
         const size_t off = sh->off_c1 + (size_t(sh->rank) * sh->cslots + size_t(j)) * sh->slice * 32u;
@@ -440,8 +462,12 @@ static int shard_window_count(cvvp_ctx *ctx, MedianShard *sh, const uint8_t *d_f
 // One phase of a sharded job (see the file header).  d_result: where phase 3 stores this rank's copy of the result
 // bytes instead of its own exchange buffer (the one-rank two-pass path writes straight into the caller's image).
 static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t *d_frames, long long nframes,
-                       size_t frame_stride, uint8_t *d_result, cudaStream_t s, bool gated = false)
+                       size_t frame_stride, uint8_t *d_result, cudaStream_t s)
 {
+    // phases 10..13: phases 0..3 restricted to the tiles the window pass flagged
+    const bool restricted = phase >= 10 && phase <= 13;
+    if (restricted)
+        phase -= 10;
     if (!all_peers_known(sh))
         return fail(ctx, CVVP_ERR_STATE, "median shard: not every peer buffer is mapped (import / attach all ranks first)");
     if (nframes < 0)
@@ -449,9 +475,17 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
     if (nframes > kSlotFrames * sh->spr)
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "median shard: %lld frames on one rank exceed the %d x 16-bit counts (%lld)",
                     nframes, sh->spr, kSlotFrames * sh->spr);
-    const uint32_t *gate = gated ? reinterpret_cast<const uint32_t *>(sh->buf + sh->off_flag) : nullptr;
+    const uint32_t *tflags = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_tflag);
+    uint32_t *tlist = reinterpret_cast<uint32_t *>(sh->buf + sh->off_tlist);
+    uint32_t *tcount = reinterpret_cast<uint32_t *>(sh->buf + sh->off_flag) + 1;
     if (phase == 4)
         return shard_window_count(ctx, sh, d_frames, nframes, frame_stride, s);
+    if (restricted && phase == 0) {
+        CVVP_CUDA_OK(ctx, cudaMemsetAsync(tcount, 0, sizeof(uint32_t), s));
+        shard_tile_list_kernel<<<1, 1024, 0, s>>>(tflags, sh->ntiles, tlist, tcount);
+        CVVP_CUDA_OK(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     if (phase == 0 || phase == 2) {
         // slot j of this rank takes frames [j * 65535, (j + 1) * 65535) (possibly none)
         for (int j = 0; j < sh->spr; ++j) {
@@ -464,7 +498,10 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
                 push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
             push.sel = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_sel);
             push.slice = sh->slice;
-            push.gate = gate;
+            if (restricted) {
+                push.tile_list = tlist;
+                push.tile_count = tcount;
+            }
             {
                 const char *e = getenv("CVVP_SHARD_STAGE"); // development switch; default: stage when owners are peers
                 push.stage = e ? (e[0] == '1') : (sh->world > 1);
@@ -483,9 +520,11 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
         A.used = uint32_t(phase == 5 ? sh->wsubs : sh->spr);
         A.slots = uint32_t(phase == 3 ? sh->spr : sh->cslots);
         A.world = uint32_t(sh->world) * A.used;
-        A.gate = gate;
-        for (int r = 0; r < sh->world; ++r)
+        A.only_flagged = restricted ? tflags : nullptr;
+        for (int r = 0; r < sh->world; ++r) {
             A.flag[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_flag);
+            A.tflag[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_tflag);
+        }
         A.rank = uint32_t(sh->rank);
         A.nranks = uint32_t(sh->world);
         const size_t first = size_t(sh->rank) * sh->slice;
@@ -503,12 +542,12 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
         else if (phase == 3)
             shard_final_kernel<<<((A.owned + 3) / 4 + 255) / 256, 256, 0, s>>>(A);
         else
-            shard_window_final_kernel<<<((A.owned + 3) / 4 + 255) / 256, 256, 0, s>>>(A);
+            shard_window_final_kernel<<<(A.owned + 255) / 256, 256, 0, s>>>(A);
         CVVP_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches++;
         return CVVP_OK;
     }
-    return fail(ctx, CVVP_ERR_INVALID, "median shard: phase must be 0..5");
+    return fail(ctx, CVVP_ERR_INVALID, "median shard: phase must be 0..5 or 10..13");
 }
 
 long long median_two_pass_max_frames()
@@ -517,9 +556,10 @@ long long median_two_pass_max_frames()
 }
 
 // Single-GPU median of a stack too long for the on-chip select at full tile width: the sharded job with ONE rank.
-// window != 0: one pass of window counting first (phases 4, 5); the two counting passes (phases 0..3) follow on the
-// stream GATED by the device-side `unresolved` word, i.e. they return at once when every element was resolved -- no
-// host round trip, the call stays asynchronous.  window == 0: the two counting passes only.  Either way two passes
+// window != 0: one pass of window counting first (phases 4, 5); the two counting rounds follow on the stream
+// restricted to the tiles that hold an undecided element (phases 10..13; the tile list is built on the device, so
+// with nothing undecided they return at once) -- no host round trip, the call stays asynchronous.  window == 0: the
+// two counting passes over the whole image only.  Either way two passes
 // over the frames in chunks of <= 1024 at 128-byte tiles beat one pass at the 32- or 16-byte tiles the on-chip
 // select would need beyond 2048 frames.
 int median_long_stack(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,
@@ -544,7 +584,7 @@ int median_long_stack(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes,
         }
     }
     for (int phase = 0; phase < 4; ++phase) {
-        const int rc = shard_phase(ctx, ctx->big, phase, d_frames, nframes, frame_stride, d_out, stream, window != 0);
+        const int rc = shard_phase(ctx, ctx->big, phase + (window ? 10 : 0), d_frames, nframes, frame_stride, d_out, stream);
         if (rc != CVVP_OK)
             return rc;
     }

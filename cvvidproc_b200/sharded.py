@@ -136,20 +136,22 @@ class ShardedMedian:
         self.last_unresolved = self.ctx.median_shard_unresolved()
         return self.last_unresolved
 
-    def run_two_round(self, d_frames: int, nframes: int, frame_stride: int):
-        """The four phases of the two-round nibble exchange with the barriers in between (exact for any input)."""
+    def run_two_round(self, d_frames: int, nframes: int, frame_stride: int, restricted: bool = False):
+        """The four phases of the two-round nibble exchange with the barriers in between (exact for any input).
+        restricted: only over the 128-element tiles the one-pass form flagged (phases 10..13; after run_window)."""
         for p in range(4):
-            self.phase(p, d_frames, nframes, frame_stride)
+            self.phase(p + (10 if restricted else 0), d_frames, nframes, frame_stride)
             self._barrier()
 
     def run(self, d_frames: int, nframes: int, frame_stride: int, window: bool = True) -> int:
         """One job (every rank of the group must call it with the same `window`): the one-pass form when every rank's
         frames fit its record slots, then -- only if it left elements undecided, which every rank learns as the same
-        number -- the two-round exchange.  Returns the device pointer of the full result image (nelem bytes), complete
+        number -- the two-round exchange over the tiles that hold such an element.  Returns the device pointer of the full result image (nelem bytes), complete
         once the stream reaches the last barrier."""
-        if window and self.run_window(d_frames, nframes, frame_stride) == 0:
-            return self.ctx.median_shard_result()
-        self.run_two_round(d_frames, nframes, frame_stride)
+        if not window:
+            self.run_two_round(d_frames, nframes, frame_stride)
+        elif self.run_window(d_frames, nframes, frame_stride) != 0:
+            self.run_two_round(d_frames, nframes, frame_stride, restricted=True)
         return self.ctx.median_shard_result()
 
     def result_ptr(self) -> int:

@@ -148,8 +148,10 @@ CVVP_API int cvvp_median_device(cvvp_ctx *ctx, const uint8_t *d_frames, long lon
  *   on chip from 256 of its own frames (per launch of <= 1024 frames), phase 5 lets the owner name
  *   the median of ALL frames wherever it lies inside every window.  The result is exact where it
  *   is given; cvvp_median_shard_unresolved returns how many elements could NOT be decided (the
- *   same number on every rank; 0 for an ordinary video).  When it is not 0 run phases 0..3, which
- *   are exact for any input and rewrite the whole image.
+ *   same number on every rank; 0 for an ordinary video).  When it is not 0 run
+ *     phase 10, BARRIER, phase 11, BARRIER, phase 12, BARRIER, phase 13, BARRIER
+ *   = phases 0..3 restricted to the 128-element tiles that hold an undecided element (phase 5
+ *   flagged them on every rank), or phases 0..3 themselves, which rewrite the whole image.
  * ------------------------------------------------------------------------------------------- */
 #define CVVP_IPC_HANDLE_BYTES 64
 /* rank in [0, world), world <= 16; allocates this rank's exchange buffers (64 B per element and
@@ -164,9 +166,9 @@ CVVP_API int cvvp_median_shard_export(cvvp_ctx *ctx, void *handle_out);
 CVVP_API int cvvp_median_shard_import(cvvp_ctx *ctx, int peer_rank, const void *handle);
 /* same-process peer (several contexts in one process, on one or several devices) */
 CVVP_API int cvvp_median_shard_attach(cvvp_ctx *ctx, int peer_rank, cvvp_ctx *peer_ctx);
-/* phases 0, 2 and 4 read this rank's frames (device pointer, same layout rules as cvvp_median_device;
- * nframes may be 0, may differ between ranks, at most what the job was begun for); phases 1, 3 and 5 ignore the
- * frame arguments.
+/* phases 0, 2, 4, 10 and 12 read this rank's frames (device pointer, same layout rules as cvvp_median_device;
+ * nframes may be 0, may differ between ranks, at most what the job was begun for); phases 1, 3, 5, 11 and 13 ignore
+ * the frame arguments.
  * Runs on `stream` (NULL = the context's compute stream) and does not synchronize. */
 CVVP_API int cvvp_median_shard_phase(cvvp_ctx *ctx, int phase, const uint8_t *d_frames, long long nframes,
                                      size_t frame_stride, void *stream);

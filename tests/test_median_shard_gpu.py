@@ -14,14 +14,15 @@ from cvvidproc_b200 import _cabi, sharded
 pytestmark = pytest.mark.gpu
 
 
-FORMS = ["two_round", "window"]
+FORMS = ["two_round", "window", "window_then_full"]
 LAST = {}  # what the last _sharded_median call observed (unresolved elements of the one-pass form)
 
 
 def _sharded_median(frames_per_rank, nelem, form="two_round"):
     """frames_per_rank: list of uint8 arrays (n_r, nelem); returns every rank's result image.
     form: "two_round" = phases 0..3; "window" = the one-pass form (phases 4, 5) and, exactly as ShardedMedian.run does,
-    the two-round exchange only when it left elements undecided; "window_only" = phases 4, 5 alone."""
+    the two-round exchange over the flagged tiles (phases 10..13) only when it left elements undecided;
+    "window_then_full" = the same with the whole-image phases 0..3 behind it; "window_only" = phases 4, 5 alone."""
     world = len(frames_per_rank)
     ctxs = [_cabi.Context(0) for _ in range(world)]
     jobs, stacks = [], []
@@ -50,8 +51,10 @@ def _sharded_median(frames_per_rank, nelem, form="two_round"):
             left = [job.ctx.median_shard_unresolved() for job in jobs]
             assert len(set(left)) == 1, f"ranks disagree on the undecided elements: {left}"
             LAST["unresolved"] = left[0]
-        if form == "two_round" or (form == "window" and LAST["unresolved"] != 0):
+        if form == "two_round" or (form == "window_then_full" and LAST["unresolved"] != 0):
             walk(range(4))
+        elif form == "window" and LAST["unresolved"] != 0:
+            walk(range(10, 14))
         return [job.ctx.copy_to_host(job.result_ptr(), nelem) for job in jobs]
     finally:
         for job in jobs:
@@ -166,21 +169,21 @@ def test_two_valued_split_pins_upper_median(form):
     near_hi = np.full((n // 2, 256), 0x54, np.uint8)
     for got in _sharded_median([near_lo, near_hi], 256, form):
         assert (got == 0x54).all()
-    if form == "window":
+    if form.startswith("window"):
         assert LAST["unresolved"] == 0
     for got in _sharded_median([near_lo, near_hi[:-1]], 256, form):
         assert (got == 0x51).all()
     zeros = np.zeros((33, 256), np.uint8)  # value 0 coincides with the zero-filled pad slots
     for got in _sharded_median([zeros, zeros[:5]], 256, form):
         assert (got == 0).all()
-    if form == "window":
+    if form.startswith("window"):
         assert LAST["unresolved"] == 0
     ff = np.full((33, 256), 255, np.uint8)
     for got in _sharded_median([ff, zeros[:30]], 256, form):
         assert (got == 255).all()
     for got in _sharded_median([ff, ff[:7]], 256, form):  # window clamped at the top of the range
         assert (got == 255).all()
-    if form == "window":
+    if form.startswith("window"):
         assert LAST["unresolved"] == 0
 
 
