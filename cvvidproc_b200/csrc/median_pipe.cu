@@ -163,6 +163,12 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     const uint32_t warp = tid >> 5;
     const uint32_t lane = tid & 31;
 
+    // tiles of this launch: all of them, or the listed ones (nothing listed: nothing to do, not even barrier set-up)
+    const uint32_t *tile_list = MODE != 0 ? push.tile_list : nullptr;
+    const uint32_t ntl = tile_list ? min(__ldcg(push.tile_count), ntiles) : ntiles;
+    if (ntl == 0u)
+        return;
+
     if (tid == 0) {
         prefetch_tmap(&tmap);
         for (int i = 0; i < kRing; ++i)
@@ -179,8 +185,6 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     __syncthreads();
 
     // tiles of this CTA, in the order every role walks them: every gridDim.x-th of all tiles, or of the listed ones
-    const uint32_t *tile_list = MODE != 0 ? push.tile_list : nullptr;
-    const uint32_t ntl = tile_list ? min(__ldcg(push.tile_count), ntiles) : ntiles;
     const uint32_t my_tiles = blockIdx.x < ntl ? (ntl - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto tile_at = [&](uint32_t t) {
         const uint32_t idx = blockIdx.x + t * gridDim.x;

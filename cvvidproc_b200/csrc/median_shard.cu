@@ -85,7 +85,8 @@ struct OwnerArgs {
     uint8_t *result[kMaxShardRanks];  // every rank's result image
     uint32_t *flag[kMaxShardRanks];   // window pass: every rank's `unresolved` word
     uint32_t *tflag[kMaxShardRanks];  // window pass: every rank's tile flags
-    const uint32_t *only_flagged;     // not NULL (this rank's tile flags): skip elements whose tile is not flagged
+    const uint32_t *tile_list;        // restricted rounds: the flagged tiles and how many there are
+    const uint32_t *tile_count;
 };
 
 // the s-th vector / record of the round lives in slot (s % used) of rank (s / used)
@@ -106,81 +107,116 @@ __device__ __forceinline__ void add_counts(uint32_t (&cnt)[16], const uint32_t *
     }
 }
 
-// phase 1: one thread per owned element
-__global__ void __launch_bounds__(256) shard_pick_kernel(const __grid_constant__ OwnerArgs A)
+// phase 1 for owned element i
+__device__ __forceinline__ void pick_element(const OwnerArgs &A, uint32_t i)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < A.owned && (!A.only_flagged || __ldcg(A.only_flagged + ((size_t(A.rank) * A.slice + i) >> 7)) != 0u)) {
+    uint32_t cnt[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b)
+        cnt[b] = 0;
+    for (uint32_t src = 0; src < A.world; ++src)
+        add_counts(cnt, A.counts + (src_slot(A, src) * A.slice + i) * 8u);
+    uint32_t total = 0;
+#pragma unroll
+    for (int b = 0; b < 16; ++b)
+        total += cnt[b];
+    const uint32_t k = total / 2u; // halfway rank: first bin with cumulative count > N / 2  (:160-166)
+    uint32_t h = 15u, below = 0u, cum = 0u;
+    bool found = false;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        if (!found && cum + cnt[b] > k) {
+            h = uint32_t(b);
+            below = cum;
+            found = true;
+        }
+        cum += cnt[b];
+    }
+    if (!found)
+        below = total - cnt[15]; // unreachable with exact counts; mirrors the reference's default bin
+    const uint32_t v = h | ((k - below) << 8);
+    const size_t e = size_t(A.rank) * A.slice + i;
+    for (uint32_t r = 0; r < A.nranks; ++r)
+        A.sel[r][e] = v;
+}
+
+// phase 3 for the owned elements i4 .. i4 + 3 (one 32-bit store of result bytes per rank)
+__device__ __forceinline__ void final_group(const OwnerArgs &A, uint32_t i4)
+{
+    const size_t e0 = size_t(A.rank) * A.slice + i4;
+    uint32_t packed = 0;
+    const uint32_t n = min(4u, A.owned - i4);
+    for (uint32_t q = 0; q < n; ++q) {
         uint32_t cnt[16];
 #pragma unroll
         for (int b = 0; b < 16; ++b)
             cnt[b] = 0;
         for (uint32_t src = 0; src < A.world; ++src)
-            add_counts(cnt, A.counts + (src_slot(A, src) * A.slice + i) * 8u);
-        uint32_t total = 0;
-#pragma unroll
-        for (int b = 0; b < 16; ++b)
-            total += cnt[b];
-        const uint32_t k = total / 2u; // halfway rank: first bin with cumulative count > N / 2  (:160-166)
-        uint32_t h = 15u, below = 0u, cum = 0u;
+            add_counts(cnt, A.counts + (src_slot(A, src) * A.slice + i4 + q) * 8u);
+        const uint32_t s = __ldcg(A.sel[A.rank] + e0 + q);
+        const uint32_t h = s & 15u, k = s >> 8;
+        uint32_t l = 15u, cum = 0u;
         bool found = false;
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
             if (!found && cum + cnt[b] > k) {
-                h = uint32_t(b);
-                below = cum;
+                l = uint32_t(b);
                 found = true;
             }
             cum += cnt[b];
         }
-        if (!found)
-            below = total - cnt[15]; // unreachable with exact counts; mirrors the reference's default bin
-        const uint32_t v = h | ((k - below) << 8);
-        const size_t e = size_t(A.rank) * A.slice + i;
-        for (uint32_t r = 0; r < A.nranks; ++r)
-            A.sel[r][e] = v;
+        packed |= ((h << 4) | l) << (8u * q);
+    }
+    for (uint32_t r = 0; r < A.nranks; ++r) {
+        uint8_t *dst = A.result[r] + e0;
+        if (n == 4u) {
+            *reinterpret_cast<uint32_t *>(dst) = packed; // e0 is a multiple of 4 (slice % 128 == 0)
+        } else {
+            for (uint32_t q = 0; q < n; ++q)
+                dst[q] = uint8_t(packed >> (8u * q));
+        }
+    }
+}
+
+// phases 1 and 3 over ALL owned elements: one thread per element / per 4 elements
+__global__ void __launch_bounds__(256) shard_pick_kernel(const __grid_constant__ OwnerArgs A)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < A.owned)
+        pick_element(A, i);
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) shard_final_kernel(const __grid_constant__ OwnerArgs A)
+{
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i4 < A.owned)
+        final_group(A, i4);
+    __threadfence_system();
+}
+
+// phases 11 and 13: the same over the LISTED tiles only (128 elements each; a tile lies inside one owner's slice).  A
+// fixed grid walks the list, so an empty list costs a launch and nothing else.
+__global__ void __launch_bounds__(128) shard_pick_listed_kernel(const __grid_constant__ OwnerArgs A)
+{
+    const uint32_t n = __ldcg(A.tile_count);
+    const uint32_t first = A.rank * A.slice;
+    for (uint32_t idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        const uint32_t e = __ldcg(A.tile_list + idx) * 128u + threadIdx.x;
+        if (e >= first && e - first < A.owned)
+            pick_element(A, e - first);
     }
     __threadfence_system();
 }
 
-// phase 3: one thread per 4 owned elements (one 32-bit store of result bytes per rank)
-__global__ void __launch_bounds__(256) shard_final_kernel(const __grid_constant__ OwnerArgs A)
+__global__ void __launch_bounds__(32) shard_final_listed_kernel(const __grid_constant__ OwnerArgs A)
 {
-    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u; // four elements of one tile
-    if (i4 < A.owned && (!A.only_flagged || __ldcg(A.only_flagged + ((size_t(A.rank) * A.slice + i4) >> 7)) != 0u)) {
-        const size_t e0 = size_t(A.rank) * A.slice + i4;
-        uint32_t packed = 0;
-        const uint32_t n = min(4u, A.owned - i4);
-        for (uint32_t q = 0; q < n; ++q) {
-            uint32_t cnt[16];
-#pragma unroll
-            for (int b = 0; b < 16; ++b)
-                cnt[b] = 0;
-            for (uint32_t src = 0; src < A.world; ++src)
-                add_counts(cnt, A.counts + (src_slot(A, src) * A.slice + i4 + q) * 8u);
-            const uint32_t s = __ldcg(A.sel[A.rank] + e0 + q);
-            const uint32_t h = s & 15u, k = s >> 8;
-            uint32_t l = 15u, cum = 0u;
-            bool found = false;
-#pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                if (!found && cum + cnt[b] > k) {
-                    l = uint32_t(b);
-                    found = true;
-                }
-                cum += cnt[b];
-            }
-            packed |= ((h << 4) | l) << (8u * q);
-        }
-        for (uint32_t r = 0; r < A.nranks; ++r) {
-            uint8_t *dst = A.result[r] + e0;
-            if (n == 4u) {
-                *reinterpret_cast<uint32_t *>(dst) = packed; // e0 is a multiple of 4 (slice % 128 == 0)
-            } else {
-                for (uint32_t q = 0; q < n; ++q)
-                    dst[q] = uint8_t(packed >> (8u * q));
-            }
-        }
+    const uint32_t n = __ldcg(A.tile_count);
+    const uint32_t first = A.rank * A.slice;
+    for (uint32_t idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        const uint32_t e = __ldcg(A.tile_list + idx) * 128u + 4u * threadIdx.x;
+        if (e >= first && e - first < A.owned)
+            final_group(A, e - first);
     }
     __threadfence_system();
 }
@@ -520,7 +556,8 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
         A.used = uint32_t(phase == 5 ? sh->wsubs : sh->spr);
         A.slots = uint32_t(phase == 3 ? sh->spr : sh->cslots);
         A.world = uint32_t(sh->world) * A.used;
-        A.only_flagged = restricted ? tflags : nullptr;
+        A.tile_list = tlist;
+        A.tile_count = tcount;
         for (int r = 0; r < sh->world; ++r) {
             A.flag[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_flag);
             A.tflag[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_tflag);
@@ -537,7 +574,12 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
             A.result[sh->rank] = d_result;
         if (A.owned == 0)
             return CVVP_OK;
-        if (phase == 1)
+        const unsigned listed_grid = unsigned(std::min<uint32_t>(sh->ntiles, 8u * uint32_t(ctx->sm_count)));
+        if (phase == 1 && restricted)
+            shard_pick_listed_kernel<<<listed_grid, 128, 0, s>>>(A);
+        else if (phase == 3 && restricted)
+            shard_final_listed_kernel<<<listed_grid, 32, 0, s>>>(A);
+        else if (phase == 1)
             shard_pick_kernel<<<(A.owned + 255) / 256, 256, 0, s>>>(A);
         else if (phase == 3)
             shard_final_kernel<<<((A.owned + 3) / 4 + 255) / 256, 256, 0, s>>>(A);

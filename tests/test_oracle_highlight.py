@@ -90,13 +90,28 @@ def test_workload_parameters_match_the_oracle():
         assert c[k] == getattr(p, k)
 
 
+def test_bench_workload_tables_match_the_package():
+    """bench.py repeats the workload tables (its reference arm must not import the package): they are the package's"""
+    import importlib.util
+    from pathlib import Path
+
+    from cvvidproc_b200 import synth
+
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name, p in synth.CONFIG_PARAMS.items():
+        assert {k: bench.CONFIGS[name][k] for k in p} == p, name
+    assert bench.CANONICAL_HIGHLIGHT == synth.CANONICAL_HIGHLIGHT
+
+
 def test_bench_gpu_arm_does_not_touch_the_oracle():
     """only the cpu_baseline / reference legs of bench.py may use oracle/ (it is the checker, never the product)"""
     import ast
     from pathlib import Path
 
     tree = ast.parse((Path(__file__).resolve().parent.parent / "bench.py").read_text())
-    allowed = {"cpu_median_fn", "cpu_highlight_rate", "run_reference_arm"}
+    allowed = {"cpu_median_fn", "cpu_highlight_rate", "run_reference_arm", "host_synth", "cpu_track_pipeline"}
     for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
         uses = [n for n in ast.walk(fn) if (isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n))
                 or (isinstance(n, ast.Constant) and isinstance(n.value, str) and n.value == "oracle")]
