@@ -758,7 +758,7 @@ def highlight_bench(E: Env, cfg, frames_rank, first_frame, total_frames, steps, 
     (ms,) = E.max_over_ranks([e0.elapsed_time(e1) / steps])
     # end to end from pinned host memory through cvvp_highlight_frames (bounded pinned buffers: a prefix of the frames,
     # processed ceil(n / n0) times per step when the rank's share is larger)
-    n0 = int(max(1, min(nfr, PINNED_CAP_BYTES // 2 // npix)))
+    n0 = int(max(1, min(nfr, PINNED_CAP_BYTES // npix)))  # one pinned buffer in, one out
     pin_in = E.cabi.PinnedBuffer(n0 * npix)
     pin_out = E.cabi.PinnedBuffer(n0 * npix)
     pin_in.array[:] = frames[:n0].cpu().numpy().reshape(-1)
