@@ -640,9 +640,9 @@ def median_sharded(E: Env, cfg, n_rank, first_frame, total_frames, steps, warmup
     job_mpxf = W * H * total_frames / 1e6
     res = {"ms_per_step": ms, "value": job_mpxf / (ms * 1e-3), "gpu_launches": int(launches), "kernel_ms": p4,
            "undecided_elements": int(undecided)}
-    res["roofline"] = roofline(float(most) * nelem + 32.0 * nelem * -(-most // 1024), p4,
+    res["roofline"] = roofline(float(most) * nelem + 20.0 * nelem * -(-most // 1024), p4,
                                "median_pipe_kernel<MODE 3> (window counting, one pass over the rank's frames)",
-                               note="algorithmic bytes = every input byte once + one 32-byte record per element and launch")
+                               note="algorithmic bytes = every input byte once + one 20-byte record per element and launch")
     res["roofline"]["phase_ms"] = {"window_count": p4, "window_final": p5,
                                    "barriers_and_host_check": max(0.0, ms - p4 - p5)}
     result_dev = ctx.copy_to_host(job.result_ptr(), nelem)

@@ -52,6 +52,9 @@ struct ShardPush {
     // them -- the two counting rounds behind a window pass recount only the tiles that hold an undecided element
     const uint32_t *tile_list;
     const uint32_t *tile_count;
+    // window counting (MODE 3): a source's frame count goes to one header word per owner, not into every record
+    uint32_t *hdr[kMaxShardRanks];
+    uint32_t nranks;
 };
 struct MedianShard; // median_shard.cu
 

@@ -130,7 +130,8 @@ __device__ __forceinline__ void window_row(uint32_t (&acc)[4], uint32_t &below, 
 //         3 = frame-sharded job / long stack in ONE pass over the frames: every element's select threads first pick a
 //             PILOT median of two of their plane rows (256 of the launch's <= 1024 frames) on chip, then count all
 //             frames in the 8-value window [pilot - 4, pilot + 3] (8 bins) and below it, and push
-//             {bins, below, window base, frame count} (32 B) to the element's owner.  The owner can name the median of
+//             {8 x u16 bins, below | window base << 16} (20 B) to the element's owner (the launch's frame count goes to
+//             a header word per owner).  The owner can name the median of
 //             ALL sources exactly whenever it lies inside every source's window (shard_window_final_kernel); elements
 //             where it does not are flagged and the job falls back to rounds 1 + 2.  (NSELW = 16 only.)
 template <int LOG2S, int JT, int NSELW, int MODE>
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     uint64_t *planes_empty = bars + kRing + 2; // [2]
     volatile uint32_t *sel_done = reinterpret_cast<volatile uint32_t *>(bars + kRing + 4); // [2] selects completed
     uint32_t *rows_free = reinterpret_cast<uint32_t *>(bars + kRing + 4) + 4; // [8] MODE 3: select warps done with row j
+    uint32_t *rec_stage = rows_free + 12; // MODE 3, staged push: a tile's 128 records of 5 words (16-byte aligned)
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5;
@@ -168,6 +170,9 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     const uint32_t ntl = tile_list ? min(__ldcg(push.tile_count), ntiles) : ntiles;
     if (ntl == 0u)
         return;
+    if (MODE == 3 && blockIdx.x == 0 && tid == 0)
+        for (uint32_t r = 0; r < push.nranks; ++r)
+            *push.hdr[r] = nframes; // how many frames this source's records count
 
     if (tid == 0) {
         prefetch_tmap(&tmap);
@@ -422,14 +427,50 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
                 acc[0] -= pad;
             else
                 below -= pad;
-            if ((lane >> kColBits) == 0u && e < nelem) {
+            // record of the element: words 0..3 = bins, word 4 = below | window base << 16 (below <= 1024 frames)
+            const uint32_t tail = below | (wbase << 16);
+            if (push.stage) {
+                // Staged push: the tile's 128 records (2560 contiguous bytes in ONE owner's buffer: tiles do not
+                // straddle owners) are assembled in shared memory and written 16 bytes per thread.  Storing them
+                // straight from the select threads makes every store instruction write scattered 8-byte pieces --
+                // poor packets for NVLink once most owners are peers (7 of 8 ranks: 0.65 instead of 0.55 ms).
+                if ((lane >> kColBits) == 0u) {
+                    if (s_g == 0) {
+                        rec_stage[s_elem * 5u + 0u] = acc[0];
+                        rec_stage[s_elem * 5u + 1u] = acc[1];
+                    } else if (s_g == 1) {
+                        rec_stage[s_elem * 5u + 2u] = acc[2];
+                        rec_stage[s_elem * 5u + 3u] = acc[3];
+                    } else if (s_g == 2) {
+                        rec_stage[s_elem * 5u + 4u] = tail;
+                    }
+                }
+                named_bar_sync(1, NSELW * 32);
+                const size_t e0 = size_t(tile) * P;
+                const uint32_t owner = uint32_t(e0) / push.slice;
+                uint32_t *dst = push.dst[owner] + (e0 - size_t(owner) * push.slice) * 5u;
+                const uint32_t words = uint32_t(min(size_t(P), size_t(nelem) - e0)) * 5u;
+                if (tid < (P * 5u + 3u) / 4u) {
+                    if (4u * tid + 4u <= words) {
+                        reinterpret_cast<uint4 *>(dst)[tid] = reinterpret_cast<const uint4 *>(rec_stage)[tid];
+                    } else {
+                        for (uint32_t w = 4u * tid; w < words; ++w)
+                            dst[w] = rec_stage[w];
+                    }
+                }
+                named_bar_sync(1, NSELW * 32); // the staging area is rewritten for the next tile
+            } else if ((lane >> kColBits) == 0u && e < nelem) {
                 const uint32_t owner = uint32_t(e) / push.slice;
-                uint32_t *dst = push.dst[owner] + (size_t(e) - size_t(owner) * push.slice) * 8u;
-                const uint2 v = s_g == 0 ? make_uint2(acc[0], acc[1])
-                              : s_g == 1 ? make_uint2(acc[2], acc[3])
-                              : s_g == 2 ? make_uint2(below, wbase)
-                                         : make_uint2(nframes, 0u);
-                *reinterpret_cast<uint2 *>(dst + 2u * s_g) = v;
+                uint32_t *dst = push.dst[owner] + (size_t(e) - size_t(owner) * push.slice) * 5u;
+                if (s_g == 0) {
+                    dst[0] = acc[0];
+                    dst[1] = acc[1];
+                } else if (s_g == 1) {
+                    dst[2] = acc[2];
+                    dst[3] = acc[3];
+                } else if (s_g == 2) {
+                    dst[4] = tail;
+                }
             }
         } else if constexpr (MODE != 0) {
             // ---- frame-sharded job: nibble counts of this rank's frames, pushed to the owner of the element ----
@@ -620,7 +661,7 @@ int launch_pipe_variant(cvvp_ctx *ctx, const CUtensorMap &tmap, uint8_t *d_out, 
     constexpr uint32_t G = NSELW / 4;
     constexpr uint32_t NBUF = (NSELW == 8) ? 2 : 1;
     const uint32_t ntiles = (nelem + P - 1) / P;
-    const size_t smem_bytes = size_t(kRing) * kStageBytes + size_t(NBUF) * (G * JT * 4096u) + size_t(kRing + 4) * 8 + 16 + 32;
+    const size_t smem_bytes = size_t(kRing) * kStageBytes + size_t(NBUF) * (G * JT * 4096u) + size_t(kRing + 4) * 8 + 16 + 48 + (MODE == 3 ? 2560 : 0);
     if (smem_bytes > ctx->smem_optin)
         return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: tile does not fit shared memory");
     auto kern = median_pipe_kernel<LOG2S, JT, NSELW, MODE>;

@@ -23,8 +23,8 @@
 // ONE-PASS FORM (phases 4 and 5, tried first).  The two rounds above read every frame twice.  Phase 4
 // (median_pipe_kernel MODE 3) reads them once: each launch (<= 1024 frames of a rank) picks, per element, a pilot
 // median of 256 of its own frames on chip and counts ALL its frames in the 8-value window [pilot - 4, pilot + 3]
-// and below it; the 32-byte record {8 bins, below, window base, frame count} goes to the element's owner like the
-// nibble counts do.  Phase 5 (shard_window_final_kernel, owner): the cumulative count of all sources is exact on the
+// and below it; the 20-byte record {8 x u16 bins, below | window base << 16} goes to the element's owner like the
+// nibble counts do (the launch's frame count goes to one header word per owner).  Phase 5 (shard_window_final_kernel, owner): the cumulative count of all sources is exact on the
 // intersection [lo - 1, hi] of their windows, so whenever G(lo - 1) <= N/2 < G(hi) the median is the first value
 // there with G(v) > N/2 -- the reference's rule (:160-166) -- and it is stored into every rank's result image.
 // Elements whose median lies outside some source's window (sources with very different content) are counted into
@@ -66,6 +66,7 @@ struct MedianShard {
     size_t off_flag{0}; // word 0: elements the window pass left unresolved (summed over all owners); word 1: flagged tiles
     size_t off_tflag{0}; // [ntiles] words: tile holds an undecided element (written by the owners of its elements)
     size_t off_tlist{0}; // [ntiles] words: the flagged tiles, compacted (phase 10)
+    size_t off_hdr{0};   // [world * cslots] words: frames counted by the window records of every source slot
     uint32_t ntiles{0};
 };
 
@@ -87,6 +88,7 @@ struct OwnerArgs {
     uint32_t *tflag[kMaxShardRanks];  // window pass: every rank's tile flags
     const uint32_t *tile_list;        // restricted rounds: the flagged tiles and how many there are
     const uint32_t *tile_count;
+    const uint32_t *src_frames;       // window pass: frames behind every source slot's records (0: skip the slot)
 };
 
 // the s-th vector / record of the round lives in slot (s % used) of rank (s / used)
@@ -221,10 +223,11 @@ __global__ void __launch_bounds__(32) shard_final_listed_kernel(const __grid_con
     __threadfence_system();
 }
 
-// phase 5: window records of every source -> result bytes.  One thread per owned element (a warp reads 1 KB of
-// consecutive records per source); four neighbouring lanes pool their bytes into one 32-bit store per rank.  Record of
-// source s for owned element i: counts[(s * slice + i) * 8 ..]: words 0..3 = bins 0..7 (16 bits each), 4 = frames below
-// the window, 5 = window base, 6 = frames of the source (0: the source is empty and is skipped).
+// phase 5: window records of every source -> result bytes.  One thread per owned element (a warp reads 640
+// consecutive bytes of records per source); four neighbouring lanes pool their bytes into one 32-bit store per rank.
+// Record of source slot s for owned element i: 5 words at counts[(s * slice * 8) + i * 5]: words 0..3 = bins 0..7
+// (16 bits each), word 4 = frames below the window | window base << 16; src_frames[s] = frames of the source (0: the
+// slot is empty and is skipped).
 __global__ void __launch_bounds__(256) shard_window_final_kernel(const __grid_constant__ OwnerArgs A)
 {
     __shared__ uint32_t delta[9][256]; // per thread: frames whose value first counts at window position i
@@ -241,12 +244,14 @@ __global__ void __launch_bounds__(256) shard_window_final_kernel(const __grid_co
         // pass 1: N, and the intersection [lo, hi] of the sources' windows
         uint32_t total = 0, lo = 0, hi = 255;
         for (uint32_t src = 0; src < A.world; ++src) {
-            const uint4 t = __ldg(reinterpret_cast<const uint4 *>(A.counts + (src_slot(A, src) * A.slice + i) * 8u) + 1);
-            if (t.z == 0u)
+            const size_t slot = src_slot(A, src);
+            const uint32_t nfr = __ldg(A.src_frames + slot);
+            if (nfr == 0u)
                 continue;
-            total += t.z;
-            lo = max(lo, t.y);
-            hi = min(hi, t.y + 7u);
+            const uint32_t base = __ldg(A.counts + slot * A.slice * 8u + size_t(i) * 5u + 4u) >> 16;
+            total += nfr;
+            lo = max(lo, base);
+            hi = min(hi, base + 7u);
         }
         const uint32_t k = total / 2u; // halfway rank: first value with cumulative count > N / 2  (:160-166)
         if (total != 0u && lo <= hi) {
@@ -255,14 +260,14 @@ __global__ void __launch_bounds__(256) shard_window_final_kernel(const __grid_co
                 delta[c][threadIdx.x] = 0;
             uint32_t cum = 0; // G(lo - 1), then G(lo - 1 + c)
             for (uint32_t src = 0; src < A.world; ++src) {
-                const uint4 *rec = reinterpret_cast<const uint4 *>(A.counts + (src_slot(A, src) * A.slice + i) * 8u);
-                const uint4 t = __ldg(rec + 1);
-                if (t.z == 0u)
+                const size_t slot = src_slot(A, src);
+                if (__ldg(A.src_frames + slot) == 0u)
                     continue;
-                const uint4 b = __ldg(rec);
-                const uint32_t w[4] = {b.x, b.y, b.z, b.w};
-                const int o = int(lo - t.y); // window position of lo in this source (0..7)
-                cum += t.x;
+                const uint32_t *rec = A.counts + slot * A.slice * 8u + size_t(i) * 5u;
+                const uint32_t w[4] = {__ldg(rec), __ldg(rec + 1), __ldg(rec + 2), __ldg(rec + 3)};
+                const uint32_t t = __ldg(rec + 4);
+                const int o = int(lo - (t >> 16)); // window position of lo in this source (0..7)
+                cum += t & 0xFFFFu;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint32_t cnt = (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xFFFFu);
@@ -321,6 +326,14 @@ __global__ void __launch_bounds__(1024) shard_tile_list_kernel(const uint32_t *_
     for (uint32_t t = threadIdx.x; t < ntiles; t += blockDim.x)
         if (__ldcg(flags + t) != 0u)
             list[atomicAdd(count, 1u)] = t;
+}
+
+// window counting: a source slot without frames only tells every owner so
+__global__ void shard_empty_slot_kernel(const __grid_constant__ ShardPush push)
+{
+    if (threadIdx.x < push.nranks)
+        *push.hdr[threadIdx.x] = 0u;
+    __threadfence_system();
 }
 
 // a rank without frames still owes every owner a (zero) count vector
@@ -396,7 +409,8 @@ static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, int sp
     sh->off_flag = sh->off_res + round_up(nelem, 256);
     sh->off_tflag = sh->off_flag + 256;
     sh->off_tlist = sh->off_tflag + round_up(size_t(sh->ntiles) * 4u, 256);
-    sh->bytes = sh->off_tlist + round_up(size_t(sh->ntiles) * 4u, 256);
+    sh->off_hdr = sh->off_tlist + round_up(size_t(sh->ntiles) * 4u, 256);
+    sh->bytes = sh->off_hdr + round_up(size_t(world) * size_t(sh->cslots) * 4u, 256);
     if (cudaMalloc(reinterpret_cast<void **>(&sh->buf), sh->bytes) != cudaSuccess) {
         cudaGetLastError();
         const size_t wanted = sh->bytes;
@@ -474,15 +488,24 @@ static int shard_window_count(cvvp_ctx *ctx, MedianShard *sh, const uint8_t *d_f
     CVVP_CUDA_OK(ctx, cudaMemsetAsync(sh->buf + sh->off_flag, 0, (sh->off_tflag - sh->off_flag) + size_t(sh->ntiles) * 4u, s));
     for (int j = 0; j < sh->wsubs; ++j) {
         ShardPush push{};
-        const size_t off = sh->off_c1 + (size_t(sh->rank) * sh->cslots + size_t(j)) * sh->slice * 32u;
-        for (int r = 0; r < sh->world; ++r)
+        const size_t slot = size_t(sh->rank) * sh->cslots + size_t(j);
+        const size_t off = sh->off_c1 + slot * sh->slice * 32u; // (records take 20 of a slot's 32 bytes per element)
+        for (int r = 0; r < sh->world; ++r) {
             push.dst[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + off);
+            push.hdr[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_hdr) + slot;
+        }
+        push.nranks = uint32_t(sh->world);
         push.slice = sh->slice;
+        {
+            // staged push (a tile's records assembled in shared memory, written 16 bytes per thread): pays for its two
+            // named barriers per tile once most owners are peers.  CVVP_SHARD_STAGE=0/1 forces it off / on.
+            const char *e = getenv("CVVP_SHARD_STAGE");
+            push.stage = e ? (e[0] == '1') : (sh->world > 1);
+        }
         const long long first = std::min<long long>(nframes, per * j);
         const long long n = std::min<long long>(nframes - first, per);
         if (n <= 0) {
-            const size_t cnt = sh->nelem * 2;
-            shard_zero_push_kernel<<<unsigned((cnt + 255) / 256), 256, 0, s>>>(push, uint32_t(sh->nelem));
+            shard_empty_slot_kernel<<<1, 32, 0, s>>>(push);
             CVVP_CUDA_OK(ctx, cudaGetLastError());
             ctx->launches++;
             continue;
@@ -558,6 +581,7 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
         A.world = uint32_t(sh->world) * A.used;
         A.tile_list = tlist;
         A.tile_count = tcount;
+        A.src_frames = reinterpret_cast<const uint32_t *>(sh->buf + sh->off_hdr);
         for (int r = 0; r < sh->world; ++r) {
             A.flag[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_flag);
             A.tflag[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_tflag);

@@ -146,9 +146,14 @@ def test_both_push_paths(oracle_median, monkeypatch, stage, world):
     for n, nelem in ((40, 1000), (700, 257), (2300, 130)):  # one stage pair / double buffer / several launches
         frames = rng.integers(0, 256, (n, nelem), dtype=np.uint8)
         frames[:, 0] = 0
+        frames[:, nelem // 2:] = rng.integers(30, 36, (n, nelem - nelem // 2), dtype=np.uint8)  # decided by the one pass
         want = oracle_median(frames.reshape(n, 1, nelem)).reshape(-1)
-        for got in _sharded_median(_split(frames, world), nelem):
-            assert np.array_equal(got, want), (stage, world, n)
+        for form in ("two_round", "window", "window_only"):  # the window records have the same two push paths
+            for got in _sharded_median(_split(frames, world), nelem, form):
+                if form == "window_only":
+                    assert np.array_equal(got[nelem // 2:], want[nelem // 2:]), (stage, world, n, form)
+                else:
+                    assert np.array_equal(got, want), (stage, world, n, form)
 
 
 @pytest.mark.parametrize("form", FORMS)
