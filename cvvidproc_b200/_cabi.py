@@ -54,6 +54,7 @@ def load():
         "cvvp_ctx_device": (i32, [vp]),
         "cvvp_ctx_sm_count": (i32, [vp]),
         "cvvp_ctx_launch_count": (i64, [vp]),
+        "cvvp_pool_trim": (sz, []),
         "cvvp_host_alloc": (i32, [sz, C.POINTER(vp)]),
         "cvvp_host_free": (i32, [vp]),
         "cvvp_ctx_copy_to_host": (i32, [vp, vp, vp, sz]),

@@ -2,6 +2,7 @@
 // (host-buffer) median job with pinned staging and stream/event pipelining, and the
 // device-resident forms used by the benchmark.  No C++ exception leaves this file.
 #include "context.hpp"
+#include "pool.hpp"
 
 #include <cstring>
 #include <new>
@@ -318,6 +319,11 @@ int cvvp_host_free(void *ptr)
         return fail(nullptr, CVVP_ERR_CUDA, "cudaFreeHost failed: %s", cudaGetErrorString(e));
     }
     return CVVP_OK;
+}
+
+size_t cvvp_pool_trim(void)
+{
+    return pool_trim();
 }
 
 int cvvp_ctx_copy_to_host(cvvp_ctx *ctx, void *host_dst, const void *device_src, size_t bytes)

@@ -9,6 +9,7 @@
 //     MatSetIntermediary (ProcessorTokenHandlers/mat_set_intermediary.h:50-68) -- now a ring of batch slots whose
 //     H2D, kernels and D2H are ordered by CUDA events on three streams; batches complete in submission order.
 #include "context.hpp"
+#include "pool.hpp"
 
 #include <cstring>
 #include <new>
@@ -193,6 +194,7 @@ int frames_prepare_host(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_
 // prepared frames otherwise), one every host_pitch bytes, so that a decoder can write straight into it
 // (cvvp_highlight_slot_acquire); only the crop band of every frame crosses the link.
 struct HqSlot {
+    size_t b_h_in{0}, b_h_out{0}, b_raw{0}, b_in{0}, b_out{0}; // bytes of the pooled buffers below (pool.hpp)
     uint8_t *h_in{nullptr}, *h_out{nullptr}; // pinned
     cvvp_component *h_comps{nullptr};
     int *h_ncomps{nullptr};
@@ -229,13 +231,14 @@ void highlight_queue_release(cvvp_ctx *ctx)
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy_out);
     for (HqSlot &s : q->slots) {
-        free_host(s.h_in);
-        free_host(s.h_out);
+        pool_host_free(s.h_in, s.b_h_in);
+        pool_host_free(s.h_out, s.b_h_out);
         free_host(s.h_comps);
         free_host(s.h_ncomps);
-        free_dev(s.d_raw);
-        free_dev(s.d_in);
-        free_dev(s.d_out);
+        pool_dev_free(s.d_raw, s.b_raw);
+        pool_dev_free(s.d_in, s.b_in);
+        pool_dev_free(s.d_out, s.b_out);
+        s.h_in = s.h_out = s.d_raw = s.d_in = s.d_out = nullptr;
         free_dev(s.d_comps);
         free_dev(s.d_ncomps);
         if (s.up)
@@ -296,12 +299,29 @@ int highlight_queue_begin(cvvp_ctx *ctx, int depth, long long max_batch, const c
     const size_t nb = size_t(max_batch);
     bool ok = true;
     for (HqSlot &s : q->slots) {
-        ok = ok && cudaMallocHost(&s.h_in, nb * q->host_pitch) == cudaSuccess;
-        ok = ok && cudaMallocHost(&s.h_out, nb * q->pitch) == cudaSuccess;
+        // the big buffers come from the process-wide pool: a job on the next video of the same geometry reuses them
+        auto host = [&](uint8_t *&p, size_t &b, size_t bytes) {
+            void *v = nullptr;
+            if (pool_host_alloc(&v, bytes) != cudaSuccess)
+                return false;
+            p = static_cast<uint8_t *>(v);
+            b = bytes;
+            return true;
+        };
+        auto dev = [&](uint8_t *&p, size_t &b, size_t bytes) {
+            void *v = nullptr;
+            if (pool_dev_alloc(&v, bytes) != cudaSuccess)
+                return false;
+            p = static_cast<uint8_t *>(v);
+            b = bytes;
+            return true;
+        };
+        ok = ok && host(s.h_in, s.b_h_in, nb * q->host_pitch);
+        ok = ok && host(s.h_out, s.b_h_out, nb * q->pitch);
         if (fmt)
-            ok = ok && cudaMalloc(&s.d_raw, nb * q->in_pitch) == cudaSuccess;
-        ok = ok && cudaMalloc(&s.d_in, nb * q->pitch) == cudaSuccess;
-        ok = ok && cudaMalloc(&s.d_out, nb * q->pitch) == cudaSuccess;
+            ok = ok && dev(s.d_raw, s.b_raw, nb * q->in_pitch);
+        ok = ok && dev(s.d_in, s.b_in, nb * q->pitch);
+        ok = ok && dev(s.d_out, s.b_out, nb * q->pitch);
         if (max_comps > 0) {
             ok = ok && cudaMallocHost(&s.h_comps, nb * size_t(max_comps) * sizeof(cvvp_component)) == cudaSuccess;
             ok = ok && cudaMallocHost(&s.h_ncomps, nb * sizeof(int)) == cudaSuccess;

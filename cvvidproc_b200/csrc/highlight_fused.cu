@@ -24,6 +24,7 @@
 //
 // run record: xinfo[id] = x_start | row << 16 | value << 31   (W <= 65535, H <= 32767; larger frames use highlight.cu)
 #include "highlight_state.hpp"
+#include "pool.hpp"
 
 #include <climits>
 #include <cstdlib>
@@ -1918,10 +1919,11 @@ bool fused_supports(const HighlightState *st)
 void fused_release(HighlightState *st)
 {
     FusedScratch &fs = st->fs;
-    void *ptrs[] = {fs.bits, fs.runs, fs.rowoff, fs.queue};
-    for (void *p : ptrs)
-        if (p)
-            cudaFree(p);
+    pool_dev_free(fs.bits, fs.bits_bytes); // parked for the next job of this geometry (pool.hpp)
+    pool_dev_free(fs.runs, fs.runs_bytes);
+    pool_dev_free(fs.rowoff, fs.rowoff_bytes);
+    if (fs.queue)
+        cudaFree(fs.queue);
     fs = FusedScratch();
 }
 
@@ -1999,9 +2001,12 @@ static int ensure_fused(cvvp_ctx *ctx, HighlightState *st)
     const size_t nb = sizeof(uint32_t) * size_t(slots) * kImages * fg.nwords;
     const size_t nr = sizeof(uint32_t) * size_t(slots) * run_words(fg);
     const size_t no = sizeof(uint32_t) * size_t(slots) * 2 * fg.rstride;
-    if (cudaMalloc(reinterpret_cast<void **>(&fs.bits), nb) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void **>(&fs.runs), nr) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void **>(&fs.rowoff), no) != cudaSuccess ||
+    fs.bits_bytes = nb;
+    fs.runs_bytes = nr;
+    fs.rowoff_bytes = no;
+    if (pool_dev_alloc(reinterpret_cast<void **>(&fs.bits), nb) != cudaSuccess ||
+        pool_dev_alloc(reinterpret_cast<void **>(&fs.runs), nr) != cudaSuccess ||
+        pool_dev_alloc(reinterpret_cast<void **>(&fs.rowoff), no) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void **>(&fs.queue), 2 * sizeof(unsigned)) != cudaSuccess) {
         cudaGetLastError();
         fused_release(st);

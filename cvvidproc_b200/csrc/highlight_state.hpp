@@ -26,6 +26,7 @@ struct FusedScratch {
     uint32_t *rowoff{nullptr}; // [slots][2][rstride]
     unsigned *queue{nullptr};  // frame queue counters (one per launch in flight, ring of kQueueRing)
     unsigned queue_next{0};
+    size_t bits_bytes{0}, runs_bytes{0}, rowoff_bytes{0}; // sizes of the pooled allocations above (pool.hpp)
 };
 
 // optional component output of the call in progress (cvvp_highlight_device_cc); comps == nullptr: off

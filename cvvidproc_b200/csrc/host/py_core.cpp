@@ -337,6 +337,9 @@ public:
         return true;
     }
 
+    // where the decode thread's time went (developer aid, CVVP_TRACK_DEBUG): inside VideoCapture.read, waiting for the
+    // GIL, waiting for a slot to fill
+    std::chrono::steady_clock::duration t_read{}, t_gil_wait{}, t_job_wait{};
     // is the decode thread waiting for the GIL right now?  The calling thread hands it over between tracker callbacks:
     // CPython switches a thread that holds the GIL out only after its switch interval (5 ms), which would leave the
     // decoder idle after every frame while a batch of callbacks runs.
@@ -355,12 +358,14 @@ private:
         for (;;) {
             Job j;
             {
+                const auto tj = std::chrono::steady_clock::now();
                 std::unique_lock<std::mutex> lk(m_mu);
                 m_cv.wait(lk, [this] { return m_stop || !m_jobs.empty(); });
                 if (m_stop)
                     return;
                 j = m_jobs.front();
                 m_jobs.pop_front();
+                t_job_wait += std::chrono::steady_clock::now() - tj;
             }
             Done d;
             d.n = j.prefilled;
@@ -370,9 +375,17 @@ private:
                     if (m_stop)
                         return;
                 }
+                const auto tw = std::chrono::steady_clock::now();
                 m_wants_gil.store(true, std::memory_order_release);
                 py::gil_scoped_acquire gil;
                 m_wants_gil.store(false, std::memory_order_release);
+                const auto tr = std::chrono::steady_clock::now();
+                t_gil_wait += tr - tw;
+                struct Stop {
+                    std::chrono::steady_clock::duration &acc;
+                    std::chrono::steady_clock::time_point t0;
+                    ~Stop() { acc += std::chrono::steady_clock::now() - t0; }
+                } stop{t_read, tr};
                 try {
                     if (m_vid.read_into(j.dst + std::size_t(d.n) * j.pitch, m_rows, m_cols, m_channels)) {
                         ++d.n;
@@ -812,6 +825,13 @@ py::dict TrackObjects(const VidObjectTrackPack &pack)
                     std::this_thread::sleep_for(std::chrono::microseconds(100));
             }
             between_frames = nullptr;
+            if (std::getenv("CVVP_TRACK_DEBUG")) {
+                auto ms = [](std::chrono::steady_clock::duration d) { return std::chrono::duration<double, std::milli>(d).count(); };
+                std::cerr << "[cvvp track] decode thread: read " << ms(worker.t_read) << " ms, GIL wait " << ms(worker.t_gil_wait)
+                          << " ms, slot wait " << ms(worker.t_job_wait) << " ms; calling thread: callbacks " << a_unit.ms()
+                          << " ms, result wait " << h_consume.ms() << " ms, commits " << h_unit.ms() << " ms; batches " << committed
+                          << " of " << batch_frames << " frames\n";
+            }
             if (!error.empty())
                 throw std::runtime_error(error);
         }

@@ -65,6 +65,11 @@ CVVP_API int cvvp_ctx_sm_count(const cvvp_ctx *ctx);
  * batched into pinned buffers" part of BASELINE.json:north_star. */
 CVVP_API int cvvp_host_alloc(size_t bytes, void **out_ptr);
 CVVP_API int cvvp_host_free(void *ptr);
+/* The library parks the large buffers of a finished job -- the highlight queue's pinned slots and device buffers, the
+ * fused highlight kernel's scratch -- for the next job of the same geometry in this process (page-locking a few
+ * hundred MB costs more than highlighting a short clip): at most 3 GB of pinned and 24 GB of device memory.
+ * cvvp_pool_trim releases everything that is parked and returns the bytes released.  Thread-safe. */
+CVVP_API size_t cvvp_pool_trim(void);
 /* synchronous device -> host copy on the context's compute stream (after everything queued there): lets callers
  * of the device-resident entry points fetch a result without a CUDA binding of their own */
 CVVP_API int cvvp_ctx_copy_to_host(cvvp_ctx *ctx, void *host_dst, const void *device_src, size_t bytes);

@@ -233,3 +233,25 @@ def test_zero_copy_slots_match_the_copying_forms(gpu_ctx, depth, batch, decoded)
     finally:
         gpu_ctx.highlight_end()
     assert np.array_equal(np.concatenate(got), want)
+
+
+def test_buffers_of_a_finished_job_are_reused_and_trimmed(gpu_ctx):
+    """the queue's pinned slots / device buffers and the fused kernel's scratch are parked when a job ends and handed to
+    the next job of the same geometry (csrc/pool.hpp); results are unaffected and cvvp_pool_trim releases what is parked"""
+    lib = _cabi.load()
+    frames, p = _stream(n=10)
+    want = np.stack([ho.highlight_objects(f.copy(), p) for f in frames])
+    lib.cvvp_pool_trim()
+    for _ in range(3):  # the second and third job run on recycled (dirty) buffers
+        _begin(gpu_ctx, p)
+        try:
+            gpu_ctx.highlight_queue_begin(2, 64)  # 64 frames x 61 KB: above the pool's 1 MB threshold
+            gpu_ctx.highlight_submit(frames[:7])
+            gpu_ctx.highlight_submit(frames[7:])
+            got = np.concatenate([gpu_ctx.highlight_next().copy(), gpu_ctx.highlight_next().copy()])
+            gpu_ctx.highlight_queue_end()
+        finally:
+            gpu_ctx.highlight_end()
+        assert np.array_equal(got, want)
+    assert lib.cvvp_pool_trim() > 0
+    assert lib.cvvp_pool_trim() == 0

@@ -5,6 +5,8 @@ the one a real multi-GPU job runs, peer stores simply land in local memory, and 
 synchronize of every context.  (Real peer memory over NVLink is exercised by `bench.py --gpus N`.)  Bit-exact is the
 bar: the result must be sorted[N/2] over ALL ranks' frames (histogram_median_algo.h:160-166).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -302,3 +304,25 @@ def test_call_order_errors():
             ctx.median_shard_begin(1000, 0, 17)  # too many ranks
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("nelem", [128, 129, 148 * 128 - 1, 148 * 128 + 1, 3 * 148 * 128 + 77])
+def test_window_pipeline_stress(oracle_median, nelem):
+    """The row-by-row hand-over of the plane buffer (monotonic rows_free counters) and the staged record push under the
+    geometries that stress a hand-rolled pipeline: one tile, one tile more / less than there are SMs, every stage count
+    that changes the select threads' row count (nst = 1..32 -> 1..8 rows per thread), each repeated -- a race would show
+    up as a wrong byte or as the 2 s watchdog trap."""
+    rng = np.random.default_rng(nelem)
+    for n in (1, 31, 32, 33, 97, 128, 129, 160, 255, 256, 257, 480, 512, 513, 767, 992, 1023, 1024):
+        frames = (100 + rng.integers(-3, 5, (n, nelem))).astype(np.uint8)
+        want = oracle_median(frames.reshape(n, 1, nelem)).reshape(-1)
+        for rep in range(2):
+            for world, stage in ((1, "0"), (1, "1"), (2, "1")):
+                os.environ["CVVP_SHARD_STAGE"] = stage
+                try:
+                    outs = _sharded_median(_split(np.concatenate([frames, frames]) if world == 2 else frames, world), nelem, "window_only")
+                finally:
+                    os.environ.pop("CVVP_SHARD_STAGE", None)
+                assert LAST["unresolved"] == 0, (n, world, stage)
+                for got in outs:
+                    assert np.array_equal(got, want), (n, world, stage, rep)

@@ -116,3 +116,21 @@ def test_bench_gpu_arm_does_not_touch_the_oracle():
         uses = [n for n in ast.walk(fn) if (isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n))
                 or (isinstance(n, ast.Constant) and isinstance(n.value, str) and n.value == "oracle")]
         assert not uses or fn.name in allowed, fn.name
+
+
+def test_label_model_matches_cv2_restatement_at_full_hd():
+    """the independent label model against the cv2 restatement on full 1080p frames of the C3 stream (the geometry the
+    benchmark runs): the second opinion on the oracle at the size that matters"""
+    from cvvidproc_b200 import synth
+
+    p_ = synth.CONFIG_PARAMS["C3"]
+    w, h = p_["width"], p_["height"]
+    stack = synth.synth_frames(0, 15, w, h, p_["seed"], p_["ndisks"])
+    bg = np.sort(stack, axis=0)[7]
+    p = ho.canonical_params(bg)
+    frames = [synth.synth_frame(f, w, h, p_["seed"], p_["ndisks"]) for f in (1000, 1097, 1194, 4321, 9999)]
+    for i, fr in enumerate(frames):
+        want = ho.highlight_objects(fr.copy(), p)
+        got = hm.highlight_objects(fr, p.background, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi,
+                                   p.min_size_hyst, p.min_size_threshold)
+        assert np.array_equal(got, want), f"frame {i}: {(got != want).sum()} pixels differ"
