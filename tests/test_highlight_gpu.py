@@ -245,3 +245,33 @@ def test_argument_errors(gpu_ctx):
         rc = lib.cvvp_highlight_frames(gpu_ctx.handle, bg.ctypes.data, 1, 64, bg.ctypes.data, 64)
         if rc != 0:
             raise _cabi.CvvpError(rc, lib.cvvp_last_error(gpu_ctx.handle).decode())
+
+
+# Openings over structuring elements of many shapes (the separable plan with one, two and three column patterns, the
+# generic tap loop, empty rows, taps without the pixel itself, asymmetric anchors), both kernel builds.
+@pytest.mark.parametrize("variant", ["large", "small"])
+@pytest.mark.parametrize("selem", [
+    [[1]], [[1, 1, 1, 1]], [[1], [1], [1], [1]], [[0, 1, 0], [1, 1, 1], [0, 1, 0]], [[1, 1], [1, 1]],
+    [[0, 0, 1, 0], [1, 1, 1, 1], [1, 1, 1, 1], [1, 1, 1, 1]], [[1, 0, 0, 0, 0, 0, 0, 1]], [[0, 0, 0, 1], [0, 0, 0, 1]],
+    [[1, 1, 1], [0, 0, 0], [1, 1, 1]], [[0, 0, 0], [0, 0, 0], [1, 0, 1]], [[1, 0, 1, 1, 0, 1, 1, 1, 1]],
+    [[0, 1, 0], [0, 0, 0], [0, 0, 0], [1, 1, 1]], [[1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1]],
+], ids=lambda s: "x".join(str(len(r)) for r in s[:1]) + f"_{len(s)}rows_" + "".join(str(v) for r in s for v in r)[:12])
+def test_openings_of_many_elements_match_oracle(gpu_ctx, selem, variant, monkeypatch):
+    """structuring elements of 1-4 rows, taps with and without the pixel itself, empty rows, asymmetric anchors, on frames
+    with objects at every border, odd widths included; both kernel builds"""
+    monkeypatch.setenv("CVVP_HL_VARIANT", variant)
+    rng = np.random.default_rng(len(selem) * 131 + len(selem[0]))
+    for (h, w) in ((37, 70), (64, 128), (33, 257), (96, 1000)):
+        bg = np.full((h, w), 150, np.uint8)
+        frame = bg.copy()
+        blobs = rng.integers(0, 2, (h // 4 + 1, w // 4 + 1), dtype=np.uint8).repeat(4, 0).repeat(4, 1)[:h, :w]
+        frame[blobs > 0] = 100
+        frame[rng.integers(0, h, 40), rng.integers(0, w, 40)] = 90  # specks the opening removes
+        frame[:3, :] = 100  # objects on every border
+        frame[-2:, :] = 100
+        frame[:, :2] = 100
+        frame[:, -5:] = 100
+        p = ho.HighlightParams(bg, np.array(selem, np.uint8), 14, 7, 16, 3, 3, 0)
+        got = _gpu(gpu_ctx, frame[None], p)[0]
+        want = ho.highlight_objects(frame.copy(), p)
+        assert np.array_equal(got, want), f"{(got != want).sum()} pixels differ at {h}x{w}"
