@@ -107,6 +107,7 @@ struct FusedArgs {
     uint32_t smem_words; // dynamic shared memory of the CTA, in 32-bit words
     // opening in shared-memory row bands (0 rows = structuring element too large: global-memory taps instead)
     int band_rows, dy_min, dy_max, pad_words;
+    int ct_elem; // 0 = run-time plan; 1.. = the structuring element has a compile-time instantiation (open_bands_ct)
     MorphPlan plan;
     // optional component output of the final masks (cvvp_highlight_device_cc): nullptr = off
     cvvp_component *comps; // [frame][max_comps]
@@ -695,6 +696,145 @@ __device__ void open_bands_sep(const FusedArgs &P, const uint32_t *src, uint32_t
                 const int pat = P.plan.row_pat[k];
                 const uint32_t *t = P.plan.pat_ident[pat] ? E : smem + size_t(pat + 1) * tile_words;
                 const uint4 v = *reinterpret_cast<const uint4 *>(t + (ty + P.plan.row_dy[k] - P.dy_min) * pitch + off);
+                acc.x |= v.x;
+                acc.y |= v.y;
+                acc.z |= v.z;
+                acc.w |= v.w;
+            }
+            acc.x &= vq.x;
+            acc.y &= vq.y;
+            acc.z &= vq.z;
+            acc.w &= vq.w;
+            *reinterpret_cast<uint4 *>(dst + size_t(y0 + ty) * P.WWp + 4 * qc) = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- opening with the structuring element known at COMPILE time ---------------------------------------------------------
+// With taps that are only known at run time a horizontal step costs ~6 instructions per tap and word (decode the offset,
+// pick the word pair, funnel shift, combine) and a vertical step re-derives every tile address from the plan tables:
+// the two openings are a fifth of the kernel's instructions.  The structuring elements people actually use are few --
+// the reference's only documented one is cv::getStructuringElement(MORPH_ELLIPSE, (4, 4)) (Sources/rand_tests.cpp:42-51,
+// :333-342) -- so the common ones are instantiated with their rows as template constants: every row of such an element
+// is either the single tap {0} or ONE contiguous range of taps [LO, HI].  The shifts are immediates, three AND / OR
+// fold into one LOP3, the row offsets are loop invariants.  Same band structure, same border rule, same result as
+// open_bands_sep; elements without an instantiation take that path.
+template <int DYMIN_, int NROWS_, int LO_, int HI_, unsigned IDENT_>
+struct CtElem {
+    static constexpr int dy_min = DYMIN_, nrows = NROWS_, lo = LO_, hi = HI_;
+    static constexpr unsigned ident = IDENT_; // bit j: tap row dy_min + j is the single tap {0}; else the range [lo, hi]
+};
+using CtEllipse4 = CtElem<-2, 4, -2, 1, 0x1u>;  // [[0,0,1,0],[1,1,1,1],[1,1,1,1],[1,1,1,1]]  (cv2 MORPH_ELLIPSE 4x4)
+using CtCross3 = CtElem<-1, 3, -1, 1, 0x5u>;    // [[0,1,0],[1,1,1],[0,1,0]]                  (MORPH_ELLIPSE / CROSS 3x3)
+using CtRect3 = CtElem<-1, 3, -1, 1, 0x0u>;     // 3x3 of ones
+using CtEllipse5 = CtElem<-2, 5, -2, 2, 0x11u>; // [[0,0,1,0,0],[1,1,1,1,1] x 3,[0,0,1,0,0]]  (MORPH_ELLIPSE 5x5)
+
+// horizontal step over the range [E::lo, E::hi]: w[0] = the word left of the quad, w[1..4] = the quad, w[5] = the word right
+template <bool ERODE, class E>
+__device__ __forceinline__ uint4 ct_hstep(const uint32_t (&w)[6])
+{
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t acc = ERODE ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+        for (int dx = E::lo; dx <= E::hi; ++dx) {
+            const uint32_t v = dx == 0 ? w[j + 1] : dx < 0 ? __funnelshift_r(w[j], w[j + 1], 32 + dx) : __funnelshift_r(w[j + 1], w[j + 2], dx);
+            acc = ERODE ? (acc & v) : (acc | v);
+        }
+        o[j] = acc;
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// tiles: S = staged source rows, Ht = horizontal results (of S, later of E), Et = eroded rows; geometry as open_bands_sep
+template <class E>
+__device__ void open_bands_ct(const FusedArgs &P, const uint32_t *src, uint32_t *dst, uint32_t *smem)
+{
+    const int tid = threadIdx.x;
+    const int pitch = P.WWp + 2 * kPadWords;
+    constexpr int span = E::nrows - 1, dy_max = E::dy_min + span;
+    const int BH = P.band_rows;
+    const int rows_max = BH + 2 * span;
+    const size_t tile_words = size_t(rows_max) * pitch;
+    uint32_t *S = smem, *Ht = smem + tile_words, *Et = smem + 2 * tile_words;
+    const int qpr = P.WWp >> 2;
+    const int rstep = NT / qpr;
+    const int qc = tid % qpr, r0 = tid / qpr >= rstep ? INT_MAX / 2 : tid / qpr;
+    const int off = kPadWords + 4 * qc;
+    const uint4 vq = valid_quad(P, qc);
+    for (int i = tid; i < rows_max * 2 * kPadWords; i += NT) {
+        const int row = i / (2 * kPadWords), c = i - row * (2 * kPadWords);
+        const int col = c < kPadWords ? c : P.WWp + c;
+        S[row * pitch + col] = 0xFFFFFFFFu;
+        Et[row * pitch + col] = 0u;
+    }
+    for (int y0 = 0; y0 < P.H; y0 += BH) {
+        const int y1 = min(y0 + BH, P.H);
+        const int e0 = y0 + E::dy_min, e1 = y1 + dy_max;
+        const int s0 = e0 + E::dy_min, s1 = e1 + dy_max;
+        const int srows = s1 - s0, erows = e1 - e0;
+        for (int tr = r0; tr < srows; tr += rstep) {
+            const int r = s0 + tr;
+            uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (r >= 0 && r < P.H) {
+                v = __ldcg(reinterpret_cast<const uint4 *>(src + size_t(r) * P.WWp) + qc);
+                v.x |= ~vq.x;
+                v.y |= ~vq.y;
+                v.z |= ~vq.z;
+                v.w |= ~vq.w;
+            }
+            *reinterpret_cast<uint4 *>(S + tr * pitch + off) = v;
+        }
+        __syncthreads();
+        // erosion, horizontal step (an all-clear neighbourhood stays clear: the range contains the tap 0)
+        for (int tr = r0; tr < srows; tr += rstep) {
+            const uint32_t *row = S + tr * pitch + off;
+            const uint4 c = *reinterpret_cast<const uint4 *>(row);
+            const uint32_t w[6] = {row[-1], c.x, c.y, c.z, c.w, row[4]};
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5]) != 0)
+                o = ct_hstep<true, E>(w);
+            *reinterpret_cast<uint4 *>(Ht + tr * pitch + off) = o;
+        }
+        __syncthreads();
+        // erosion, vertical step: eroded tile row te <-> image row e0 + te; tap row j reads tile row te + j
+        for (int te = r0; te < erows; te += rstep) {
+            const int e = e0 + te;
+            uint4 acc = make_uint4(0, 0, 0, 0);
+            if (e >= 0 && e < P.H) {
+                acc = vq;
+#pragma unroll
+                for (int j = 0; j < E::nrows; ++j) {
+                    const uint32_t *t = ((E::ident >> j) & 1u) ? S : Ht;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(t + (te + j) * pitch + off);
+                    acc.x &= v.x;
+                    acc.y &= v.y;
+                    acc.z &= v.z;
+                    acc.w &= v.w;
+                }
+            }
+            *reinterpret_cast<uint4 *>(Et + te * pitch + off) = acc;
+        }
+        __syncthreads();
+        // dilation, horizontal step of the eroded rows
+        for (int tr = r0; tr < erows; tr += rstep) {
+            const uint32_t *row = Et + tr * pitch + off;
+            const uint4 c = *reinterpret_cast<const uint4 *>(row);
+            const uint32_t w[6] = {row[-1], c.x, c.y, c.z, c.w, row[4]};
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if ((w[0] | w[1] | w[2] | w[3] | w[4] | w[5]) != 0)
+                o = ct_hstep<false, E>(w);
+            *reinterpret_cast<uint4 *>(Ht + tr * pitch + off) = o;
+        }
+        __syncthreads();
+        for (int ty = r0; ty < y1 - y0; ty += rstep) {
+            uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < E::nrows; ++j) {
+                const uint32_t *t = ((E::ident >> j) & 1u) ? Et : Ht;
+                const uint4 v = *reinterpret_cast<const uint4 *>(t + (ty + j) * pitch + off);
                 acc.x |= v.x;
                 acc.y |= v.y;
                 acc.z |= v.z;
@@ -1696,7 +1836,15 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) highlight_fused_kernel(const F
         CVVP_DEBUG_STAGE(3, L, false)
         // ---- branch A: threshold -> open -> remove small -> fill holes                                  (:35-47)
         if (P.band_rows > 0) {
-            if (P.plan.sep)
+            if (P.ct_elem == 1)
+                open_bands_ct<CtEllipse4>(P, A, Tm, dyn);
+            else if (P.ct_elem == 2)
+                open_bands_ct<CtCross3>(P, A, Tm, dyn);
+            else if (P.ct_elem == 3)
+                open_bands_ct<CtRect3>(P, A, Tm, dyn);
+            else if (P.ct_elem == 4)
+                open_bands_ct<CtEllipse5>(P, A, Tm, dyn);
+            else if (P.plan.sep)
                 open_bands_sep(P, A, Tm, dyn);
             else
                 open_bands(P, offs, A, Tm, dyn);
@@ -1740,7 +1888,15 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) highlight_fused_kernel(const F
         prof_tick(P.prof, P.prof, sh, kPHyst);
         CVVP_DEBUG_STAGE(7, U, false)
         if (P.band_rows > 0) {
-            if (P.plan.sep)
+            if (P.ct_elem == 1)
+                open_bands_ct<CtEllipse4>(P, U, Tm, dyn);
+            else if (P.ct_elem == 2)
+                open_bands_ct<CtCross3>(P, U, Tm, dyn);
+            else if (P.ct_elem == 3)
+                open_bands_ct<CtRect3>(P, U, Tm, dyn);
+            else if (P.ct_elem == 4)
+                open_bands_ct<CtEllipse5>(P, U, Tm, dyn);
+            else if (P.plan.sep)
                 open_bands_sep(P, U, Tm, dyn);
             else
                 open_bands(P, offs, U, Tm, dyn);
@@ -1867,6 +2023,40 @@ MorphPlan make_plan(const std::vector<short2> &offs)
     pl.npat = int(pats.size());
     pl.sep = 1;
     return pl;
+}
+
+// which compile-time instantiation of the opening (open_bands_ct) an element has: 0 = none
+template <class E>
+bool matches_ct(const std::vector<short2> &offs)
+{
+    std::vector<short2> want;
+    for (int j = 0; j < E::nrows; ++j) {
+        if ((E::ident >> j) & 1u) {
+            want.push_back(make_short2(0, short(E::dy_min + j)));
+        } else {
+            for (int dx = E::lo; dx <= E::hi; ++dx)
+                want.push_back(make_short2(short(dx), short(E::dy_min + j)));
+        }
+    }
+    if (want.size() != offs.size())
+        return false;
+    for (size_t i = 0; i < want.size(); ++i)
+        if (want[i].x != offs[i].x || want[i].y != offs[i].y)
+            return false;
+    return true;
+}
+
+int match_ct_elem(const std::vector<short2> &offs)
+{
+    if (matches_ct<CtEllipse4>(offs))
+        return 1;
+    if (matches_ct<CtCross3>(offs))
+        return 2;
+    if (matches_ct<CtRect3>(offs))
+        return 3;
+    if (matches_ct<CtEllipse5>(offs))
+        return 4;
+    return 0;
 }
 
 FusedGeom fused_geom(const HlGeom &g)
@@ -2065,6 +2255,8 @@ int HLF(highlight_fused_batch)(cvvp_ctx *ctx, HighlightState *st, const uint8_t 
     if (getenv("CVVP_HL_NO_SEP"))
         P.plan.sep = 0; // developer aid: force the generic tap loop
     P.band_rows = pick_band_rows(fg, st->dy_min, st->dy_max, P.plan);
+    // the common structuring elements have compile-time instantiations of the opening (CVVP_HL_NO_CT=1: run-time plan)
+    P.ct_elem = (P.plan.sep && P.band_rows > 0 && !getenv("CVVP_HL_NO_CT")) ? match_ct_elem(st->h_offs) : 0;
     auto aligned16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     P.fast_io = (P.W % 32 == 0) && aligned16(in) && aligned16(d_out) && aligned16(st->d_bg) && frame_stride % 16 == 0 &&
                 out_stride % 16 == 0;

@@ -247,14 +247,25 @@ def test_argument_errors(gpu_ctx):
             raise _cabi.CvvpError(rc, lib.cvvp_last_error(gpu_ctx.handle).decode())
 
 
-# Openings over structuring elements of many shapes (the separable plan with one, two and three column patterns, the
-# generic tap loop, empty rows, taps without the pixel itself, asymmetric anchors), both kernel builds.
+# Openings over structuring elements of many shapes: the compile-time instantiations (4x4 / 5x5 ellipse, 3x3 cross and
+# rectangle: csrc/highlight_fused.cu open_bands_ct), the separable run-time plan with one, two and three column patterns,
+# the generic tap loop, empty rows, taps without the pixel itself, asymmetric anchors; both kernel builds.
+@pytest.mark.parametrize("case", [c for c in hl_cases.adversarial_cases()], ids=lambda c: c[0])
+def test_run_time_plan_adversarial_frames_match_oracle(gpu_ctx, case, monkeypatch):
+    """CVVP_HL_NO_CT=1: elements that have a compile-time instantiation go through the run-time plan instead"""
+    monkeypatch.setenv("CVVP_HL_NO_CT", "1")
+    _, frame, p = case
+    got = _gpu(gpu_ctx, frame[None], p)[0]
+    assert np.array_equal(got, ho.highlight_objects(frame.copy(), p))
+
+
 @pytest.mark.parametrize("variant", ["large", "small"])
 @pytest.mark.parametrize("selem", [
     [[1]], [[1, 1, 1, 1]], [[1], [1], [1], [1]], [[0, 1, 0], [1, 1, 1], [0, 1, 0]], [[1, 1], [1, 1]],
     [[0, 0, 1, 0], [1, 1, 1, 1], [1, 1, 1, 1], [1, 1, 1, 1]], [[1, 0, 0, 0, 0, 0, 0, 1]], [[0, 0, 0, 1], [0, 0, 0, 1]],
     [[1, 1, 1], [0, 0, 0], [1, 1, 1]], [[0, 0, 0], [0, 0, 0], [1, 0, 1]], [[1, 0, 1, 1, 0, 1, 1, 1, 1]],
     [[0, 1, 0], [0, 0, 0], [0, 0, 0], [1, 1, 1]], [[1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1]],
+    [[1, 1, 1], [1, 1, 1], [1, 1, 1]], [[0, 0, 1, 0, 0], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [0, 0, 1, 0, 0]],
 ], ids=lambda s: "x".join(str(len(r)) for r in s[:1]) + f"_{len(s)}rows_" + "".join(str(v) for r in s for v in r)[:12])
 def test_openings_of_many_elements_match_oracle(gpu_ctx, selem, variant, monkeypatch):
     """structuring elements of 1-4 rows, taps with and without the pixel itself, empty rows, asymmetric anchors, on frames
