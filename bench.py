@@ -25,7 +25,7 @@ The default (C2) line also carries the other halves of BASELINE's metric as obje
 beside it).
 
 N > 1 (one process per GPU under torchrun): the median shards over FRAME chunks (BASELINE north_star); the merge is
-the count exchange of csrc/median_shard.cu -- one pass of window counting whose 32-byte records are stored into the
+the count exchange of csrc/median_shard.cu -- one pass of window counting whose 20-byte records are stored into the
 owner rank's memory over NVLink by the counting kernel, and the two-round nibble exchange behind it for elements the
 one pass cannot decide (none on a video background).  `--median-sharding rows` instead splits the single C2 stack into
 row bands (no data-path collective; strong scaling).  The highlight stage shards by frame with no collective.
