@@ -645,6 +645,7 @@ def median_sharded(E: Env, cfg, n_rank, first_frame, total_frames, steps, warmup
                                note="algorithmic bytes = every input byte once + one 20-byte record per element and launch")
     res["roofline"]["phase_ms"] = {"window_count": p4, "window_final": p5,
                                    "barriers_and_host_check": max(0.0, ms - p4 - p5)}
+    res["barrier"] = job.barrier_kind
     result_dev = ctx.copy_to_host(job.result_ptr(), nelem)
     # ---- end to end through the host-buffer C ABI: cvvp_median_push of this rank's pinned frames, the exchange on the
     # pushed stack (cvvp_median_stack_device), the full result image back in host memory
@@ -1088,7 +1089,7 @@ def run_gpu_arm(args, rank, local_rank, world):
             "data": "synthetic", "config": conf, "clocks": clocks, "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
             "roofline": main["roofline"], "cpu_baseline": main.get("cpu_baseline"), "parity_spot_check": main["parity_spot_check"],
         }
-        for k in ("undecided_elements", "steps_timed", "frames_per_step"):
+        for k in ("undecided_elements", "barrier", "steps_timed", "frames_per_step"):
             if k in main:
                 line[k] = main[k]
         line.update(extras)

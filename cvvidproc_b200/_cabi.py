@@ -78,6 +78,7 @@ def load():
         "cvvp_median_shard_begin": (i32, [vp, sz, i32, i32]),
         "cvvp_median_shard_begin_frames": (i32, [vp, sz, i32, i32, i64]),
         "cvvp_median_shard_unresolved": (i32, [vp, vp, C.POINTER(i64)]),
+        "cvvp_median_shard_barrier": (i32, [vp, vp]),
         "cvvp_median_shard_export": (i32, [vp, vp]),
         "cvvp_median_shard_import": (i32, [vp, i32, vp]),
         "cvvp_median_shard_attach": (i32, [vp, i32, vp]),
@@ -325,6 +326,10 @@ class Context:
             self._check(self._lib.cvvp_median_shard_begin(self._h, nelem, rank, world))
         else:
             self._check(self._lib.cvvp_median_shard_begin_frames(self._h, nelem, rank, world, max_rank_frames))
+
+    def median_shard_barrier(self, stream: int = 0):
+        """the library's own cross-rank barrier on the stream (ranks = processes with one GPU each)"""
+        self._check(self._lib.cvvp_median_shard_barrier(self._h, stream or None))
 
     def median_shard_unresolved(self, stream: int = 0) -> int:
         """elements the one-pass form (phases 4, 5) left undecided; waits for the stream"""

@@ -67,7 +67,9 @@ struct MedianShard {
     size_t off_tflag{0}; // [ntiles] words: tile holds an undecided element (written by the owners of its elements)
     size_t off_tlist{0}; // [ntiles] words: the flagged tiles, compacted (phase 10)
     size_t off_hdr{0};   // [world * cslots] words: frames counted by the window records of every source slot
+    size_t off_bar{0};   // [kMaxShardRanks] words: bar[r] = the last barrier epoch rank r has arrived at (cvvp_median_shard_barrier)
     uint32_t ntiles{0};
+    uint32_t epoch{0};   // barriers this rank has issued
 };
 
 // frames one launch of the counting kernel takes at full tile width (128-byte TMA boxes): 32 stages x 32 frames
@@ -336,6 +338,48 @@ __global__ void shard_empty_slot_kernel(const __grid_constant__ ShardPush push)
     __threadfence_system();
 }
 
+// Cross-rank barrier on the stream, for ranks that each have a GPU of their own: lane r tells rank r "I have arrived
+// at barrier `epoch`" (a system-scope release store into r's exchange buffer over NVLink) and waits until rank r has
+// told this rank the same.  Everything a rank queued before its barrier -- its counting kernel's peer stores, each
+// fenced system-wide -- is complete before it signals, so what follows the barrier on any rank sees it.  One warp, a
+// few microseconds, where a one-element NCCL all-reduce costs 15-25.  The peers' kernels run on OTHER devices; ranks
+// that share a device must not use this (the waiting kernel would keep the other rank's kernel from ever running):
+// they take a host-side barrier instead.  A wait of more than 2 s traps.
+struct BarrierArgs {
+    uint32_t *bar[kMaxShardRanks]; // every rank's flag array
+    uint32_t rank, world, epoch;
+};
+
+__global__ void __launch_bounds__(32) shard_barrier_kernel(const __grid_constant__ BarrierArgs B)
+{
+    const uint32_t r = threadIdx.x;
+    if (r < B.world) {
+        __threadfence_system();
+        uint32_t *theirs = B.bar[r] + B.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(B.epoch) : "memory");
+        const uint32_t *mine = B.bar[B.rank] + r;
+        uint32_t v;
+        unsigned long long t0 = 0;
+        uint32_t spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if (int32_t(v - B.epoch) >= 0)
+                break;
+            __nanosleep(100);
+            if ((++spins & 0xFFu) == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0)
+                    t0 = t;
+                else if (t - t0 > 2000000000ull)
+                    __trap();
+            }
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+}
+
 // a rank without frames still owes every owner a (zero) count vector
 __global__ void __launch_bounds__(256) shard_zero_push_kernel(const __grid_constant__ ShardPush push, uint32_t nelem)
 {
@@ -410,7 +454,8 @@ static int shard_create(cvvp_ctx *ctx, size_t nelem, int rank, int world, int sp
     sh->off_tflag = sh->off_flag + 256;
     sh->off_tlist = sh->off_tflag + round_up(size_t(sh->ntiles) * 4u, 256);
     sh->off_hdr = sh->off_tlist + round_up(size_t(sh->ntiles) * 4u, 256);
-    sh->bytes = sh->off_hdr + round_up(size_t(world) * size_t(sh->cslots) * 4u, 256);
+    sh->off_bar = sh->off_hdr + round_up(size_t(world) * size_t(sh->cslots) * 4u, 256);
+    sh->bytes = sh->off_bar + 256;
     if (cudaMalloc(reinterpret_cast<void **>(&sh->buf), sh->bytes) != cudaSuccess) {
         cudaGetLastError();
         const size_t wanted = sh->bytes;
@@ -696,6 +741,34 @@ int cvvp_median_shard_begin_frames(cvvp_ctx *ctx, size_t nelem, int rank, int wo
                     max_rank_frames, world, kMaxShardRanks);
     DeviceGuard guard(ctx->device);
     return shard_create(ctx, nelem, rank, world, int(spr), int((max_rank_frames + kChunkFrames - 1) / kChunkFrames), &ctx->shard);
+}
+
+int cvvp_median_shard_barrier(cvvp_ctx *ctx, void *stream)
+{
+    if (!ctx)
+        return fail(nullptr, CVVP_ERR_INVALID, "null context");
+    MedianShard *sh = ctx->shard;
+    if (!sh)
+        return fail(ctx, CVVP_ERR_STATE, "median shard: no sharded job is open");
+    if (!all_peers_known(sh))
+        return fail(ctx, CVVP_ERR_STATE, "median shard: not every peer buffer is mapped (import / attach all ranks first)");
+    for (int r = 0; r < sh->world; ++r)
+        if (sh->attached[r])
+            return fail(ctx, CVVP_ERR_UNSUPPORTED,
+                        "median shard: the device barrier is for ranks in processes of their own, one GPU each; ranks attached "
+                        "inside one process synchronize their contexts instead");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->compute;
+    BarrierArgs B{};
+    for (int r = 0; r < sh->world; ++r)
+        B.bar[r] = reinterpret_cast<uint32_t *>(sh->peer[r] + sh->off_bar);
+    B.rank = uint32_t(sh->rank);
+    B.world = uint32_t(sh->world);
+    B.epoch = ++sh->epoch;
+    shard_barrier_kernel<<<1, 32, 0, s>>>(B);
+    CVVP_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches++;
+    return CVVP_OK;
 }
 
 int cvvp_median_shard_unresolved(cvvp_ctx *ctx, void *stream, long long *out_elements)

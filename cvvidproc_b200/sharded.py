@@ -73,6 +73,7 @@ class ShardedMedian:
         self._stream = None
         self.max_rank_frames = max_rank_frames
         self.last_unresolved = None  # elements the one-pass form left undecided in the last run()
+        self.barrier_kind = "caller-supplied"
         ctx.median_shard_begin(nelem, rank, world, max_rank_frames)
         self._open = True
 
@@ -89,15 +90,30 @@ class ShardedMedian:
             if peer != self.rank:
                 self.ctx.median_shard_import(peer, h)
         if self._barrier is None:
+            # Every rank on a GPU of its own (what torchrun launches): the library's one-warp flag barrier over the mapped
+            # exchange buffers.  Ranks that share a device must not spin on each other on it: a one-element NCCL
+            # all-reduce on the context's stream instead.  CVVP_SHARD_BARRIER=nccl|device forces either.
+            import os
+
             dev = torch.device("cuda", self.ctx.device)
-            self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
-            self._stream = torch.cuda.ExternalStream(self.ctx.stream, device=dev)
+            mine_id = (os.uname().nodename, str(torch.cuda.get_device_properties(self.ctx.device).uuid))
+            ids = [None] * self.world
+            dist.all_gather_object(ids, mine_id, group=self._group)
+            own_gpu = len(set(ids)) == self.world
+            choice = os.environ.get("CVVP_SHARD_BARRIER", "device" if own_gpu else "nccl")
+            if choice == "device" and own_gpu:
+                self.barrier_kind = "device flags over peer memory"
+                self._barrier = self.ctx.median_shard_barrier
+            else:
+                self.barrier_kind = "one-element NCCL all-reduce"
+                self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                self._stream = torch.cuda.ExternalStream(self.ctx.stream, device=dev)
 
-            def barrier():
-                with torch.cuda.stream(self._stream):
-                    dist.all_reduce(self._flag, group=self._group)
+                def barrier():
+                    with torch.cuda.stream(self._stream):
+                        dist.all_reduce(self._flag, group=self._group)
 
-            self._barrier = barrier
+                self._barrier = barrier
         dist.barrier(group=self._group)  # every rank has mapped every buffer before the first store
 
     @staticmethod

@@ -177,6 +177,13 @@ CVVP_API int cvvp_median_shard_attach(cvvp_ctx *ctx, int peer_rank, cvvp_ctx *pe
  * Runs on `stream` (NULL = the context's compute stream) and does not synchronize. */
 CVVP_API int cvvp_median_shard_phase(cvvp_ctx *ctx, int phase, const uint8_t *d_frames, long long nframes,
                                      size_t frame_stride, void *stream);
+/* A BARRIER of the library's own, for ranks that are processes with ONE GPU EACH (what torchrun launches): a one-warp
+ * kernel on `stream` that signals every peer through its mapped exchange buffer and waits for every peer's signal
+ * (a few microseconds; a one-element NCCL all-reduce costs 15-25).  Every rank must call it the same number of
+ * times.  Not for ranks that share a device (CVVP_ERR_UNSUPPORTED for attached ranks; processes that share a GPU must
+ * not call it: the waiting kernel would keep the peer's kernel from running) -- those use a host-side barrier.  A
+ * wait of more than 2 s traps (the stream reports a CUDA error) instead of hanging. */
+CVVP_API int cvvp_median_shard_barrier(cvvp_ctx *ctx, void *stream);
 /* after the barrier that follows phase 5: waits for `stream` (NULL = the context's compute stream) and returns the
  * number of elements the one-pass form left undecided, summed over all owners (identical on every rank) */
 CVVP_API int cvvp_median_shard_unresolved(cvvp_ctx *ctx, void *stream, long long *out_elements);
