@@ -90,7 +90,9 @@ int median_launch_mode(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes
     const cuuint32_t box[2] = {cuuint32_t(128 >> log2s), cuuint32_t(32 << log2s)};
     const cuuint32_t estride[2] = {1, 1};
     const CUresult cr = ctx->encode_tiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(d_frames), gdim,
-                                          gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          // 128-byte rows are swizzled for the kernel's transposing matrix loads
+                                          log2s == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS)
         return fail(ctx, CVVP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(cr));

@@ -12,24 +12,11 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m)
     return d;
 }
 
-// In-register transpose of a 32x32 bit matrix: afterwards r[j] bit i == (old r[i]) bit j.
-__device__ __forceinline__ void transpose32(uint32_t (&r)[32])
+// The three bit stages of the 32x32 bit transpose: every block of eight words r[8p .. 8p+7] holds one element's 32
+// frame slots as bytes (word j, byte k = one frame slot each); afterwards r[8p + b] is bit plane b of that element,
+// bit 8k + j = the slot that was byte k of word j.
+__device__ __forceinline__ void transpose_bits(uint32_t (&r)[32])
 {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const uint32_t a = r[i], b = r[i + 16];
-        r[i] = __byte_perm(a, b, 0x5410);
-        r[i + 16] = __byte_perm(a, b, 0x7632);
-    }
-#pragma unroll
-    for (int h = 0; h < 32; h += 16) {
-#pragma unroll
-        for (int i = h; i < h + 8; ++i) {
-            const uint32_t a = r[i], b = r[i + 8];
-            r[i] = __byte_perm(a, b, 0x6240);
-            r[i + 8] = __byte_perm(a, b, 0x7351);
-        }
-    }
 #pragma unroll
     for (int h = 0; h < 32; h += 8) {
 #pragma unroll
@@ -56,11 +43,8 @@ __device__ __forceinline__ void transpose32(uint32_t (&r)[32])
     }
 }
 
-// High nibbles only: afterwards r[8p + 4 .. 8p + 7] hold bit planes 4..7 of element p (the other entries are
-// scratch).  The byte stages are the same as in transpose32; from the 4-bit stage on only the half of every pair that
-// carries the high nibbles is computed (160 instead of 256 instructions).  Used by the counting round that needs the
-// high nibble alone (median_pipe_kernel MODE 1).
-__device__ __forceinline__ void transpose32_hi(uint32_t (&r)[32])
+// The two byte stages: r[i] = the word of frame slot i (4 elements) -> r[8p + j] = element p, slots j, j+8, j+16, j+24.
+__device__ __forceinline__ void transpose_bytes(uint32_t (&r)[32])
 {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -77,6 +61,21 @@ __device__ __forceinline__ void transpose32_hi(uint32_t (&r)[32])
             r[i + 8] = __byte_perm(a, b, 0x7351);
         }
     }
+}
+
+// In-register transpose of a 32x32 bit matrix: afterwards r[j] bit i == (old r[i]) bit j.
+__device__ __forceinline__ void transpose32(uint32_t (&r)[32])
+{
+    transpose_bytes(r);
+    transpose_bits(r);
+}
+
+// High nibbles only: afterwards r[8p + 4 .. 8p + 7] hold bit planes 4..7 of element p (the other entries are
+// scratch).  The byte stages are the same as in transpose32; from the 4-bit stage on only the half of every pair that
+// carries the high nibbles is computed (160 instead of 256 instructions).  Used by the counting round that needs the
+// high nibble alone (median_pipe_kernel MODE 1).
+__device__ __forceinline__ void transpose_bits_hi(uint32_t (&r)[32])
+{
 #pragma unroll
     for (int h = 0; h < 32; h += 8) {
 #pragma unroll
@@ -98,5 +97,11 @@ __device__ __forceinline__ void transpose32_hi(uint32_t (&r)[32])
             r[i + 1] = bitsel(a >> 1, b, 0x55555555u);
         }
     }
+}
+
+__device__ __forceinline__ void transpose32_hi(uint32_t (&r)[32])
+{
+    transpose_bytes(r);
+    transpose_bits_hi(r);
 }
 } // namespace cvvp

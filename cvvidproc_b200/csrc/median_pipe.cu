@@ -93,6 +93,17 @@ __device__ __forceinline__ void red_release_shared_inc(uint32_t *p)
     asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
 }
 
+// One transposing matrix load: two 16 x 16 BYTE tiles (lanes 0..15 / 16..31 name the 16-byte rows of the first / second
+// tile) arrive transposed -- lane T holds, of each tile, column T / 4 and column T / 4 + 8, rows 4 (T % 4) .. + 3 packed
+// into one register each (layout measured with tools/scratch/ldsm_probe.cu).  SASS: LDSM.8.MT1616.
+__device__ __forceinline__ void ldsm_t_b8_x2(uint32_t &a0, uint32_t &a1, uint32_t &b0, uint32_t &b1, uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a0), "=r"(a1), "=r"(b0), "=r"(b1)
+                 : "r"(addr)
+                 : "memory");
+}
+
 // Window counting (MODE 3) of one plane row: lo / hi = bit planes 0..3 / 4..7 of one element over 32 frame slots,
 // fb[b] = bit b of the window base replicated over the word.  d = v - base is formed bit-sliced (one LOP3 for the
 // difference bit, one for the borrow); the final borrow marks the slots below the window (v < base), the OR of
@@ -147,6 +158,9 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     constexpr uint32_t G = NSELW / 4;              // stage classes (st % G) = select threads per (element, sub-block)
     constexpr uint32_t NBUF = (NSELW == 8) ? 2 : 1;
     constexpr uint32_t kBufWords = G * JT * 1024u; // one plane buffer: G*JT stages x 4 KB
+    // P == 128: the stage lies in shared memory with TMA's 128-byte swizzle and is read with transposing matrix loads
+    // (the byte stages of the transpose happen in the load path instead of 64 PRMTs per lane and stage)
+    constexpr bool kLdsm = (LOG2S == 0);
     static_assert(G == 2 || G == 4, "8 or 16 select warps");
     static_assert((1 << kColBits) >= int(G), "stage classes are encoded in the low column bits");
 
@@ -229,26 +243,54 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
             issue(1, ti2, st2);
         advance(ti2, st2);
 
+        // byte offsets of this lane's tile row in a swizzled stage, for even and odd loads (see below)
+        uint32_t ldsm_off[2];
+        {
+            const uint32_t m = (lane >> 2) & 3u, i = lane & 3u, pass = lane >> 4;
+            for (uint32_t odd = 0; odd < 2; ++odd) {
+                const uint32_t f = 4u * ((odd + m) & 1u) + i; // frame slot within the group of eight
+                ldsm_off[odd] = f * 128u + (((4u * pass + m) ^ f) << 4);
+            }
+        }
         uint32_t k = 0;
         for (uint32_t gs = w; gs < total_stages; gs += kTrWarps, ++k) {
             const uint32_t buf = (NBUF == 2) ? (ti & 1u) : 0u;
             const uint32_t q = (NBUF == 2) ? (ti >> 1) : ti; // fill number of this buffer
             const uint32_t slot = w + kTrWarps * (k & 1u);
             mbar_wait(&ring_full[slot], (k >> 1) & 1u);
-            const uint32_t *src = ring + size_t(slot) * kStageWords + lane;
             uint32_t r[32];
+            if constexpr (kLdsm) {
+                // load k: tile A = 16-byte chunks 0..3 of the 128-byte frame rows, tile B = chunks 4..7; tile row
+                // 4m + i = chunk m of frame slot 8 (k / 2) + 4 ((k + m) & 1) + i.  Lane T (m = T % 4) receives 4 slots
+                // of elements 16 (4 pass + m) + T / 4 (+ 8) per load and all 32 slots after the eight loads.  The
+                // slot permutation makes rows 0..7 of a tile hit eight different swizzled chunks: no bank conflicts
+                // (plain rows: 4-way, measured 3.5x slower).
+                const uint32_t sb = smem_u32(ring + size_t(slot) * kStageWords);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                r[i] = src[i * 32];
+                for (int kk = 0; kk < 8; ++kk)
+                    ldsm_t_b8_x2(r[kk], r[8 + kk], r[16 + kk], r[24 + kk], sb + ldsm_off[kk & 1] + (kk >> 1) * 1024);
+            } else {
+                const uint32_t *src = ring + size_t(slot) * kStageWords + lane;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    r[i] = src[i * 32];
+            }
             __syncwarp(); // every lane has read the slot: refill it with this warp's stage k+2 (same slot)
             if (lane == 0 && gs + 2 * kTrWarps < total_stages)
                 issue(k, ti2, st2);
             advance(ti2, st2);
-            if (MODE == 1)
-                transpose32_hi(r); // the high-nibble round needs planes 4..7 only
-            else
-                transpose32(r);
-            // r[8*p + b] = bit plane b of element 4*c+p over this lane's 32 frame slots.
+            if constexpr (kLdsm) {
+                if (MODE == 1)
+                    transpose_bits_hi(r); // the high-nibble round needs planes 4..7 only
+                else
+                    transpose_bits(r);
+            } else {
+                if (MODE == 1)
+                    transpose32_hi(r);
+                else
+                    transpose32(r);
+            }
+            // r[8*p + b] = bit plane b of this lane's p-th element (elem_of(lane, p)) over its 32 frame slots.
             // Selectors must be done with the previous fill of this buffer.  Pre-check (almost always already
             // true): the fill before that one is finished, which makes the parity wait at most one phase away.
             if constexpr (MODE == 3) {
@@ -301,7 +343,8 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     const uint32_t s_col = lane ^ s_cx;
     const uint32_t s_L = (lane & ~(G - 1u)) | s_cx;
     const uint32_t s_c = s_L & ((32u >> LOG2S) - 1u);
-    const uint32_t s_elem = 4u * s_c + s_p;
+    // element of (transposer lane c, register block p): byte p of word c, or what the matrix loads deliver
+    const uint32_t s_elem = kLdsm ? 64u * (s_p >> 1) + 16u * (s_c & 3u) + 8u * (s_p & 1u) + (s_c >> 2) : 4u * s_c + s_p;
     const bool s_writer = (s_g == 0u) && ((lane >> kColBits) == 0u);
     const uint32_t k0 = nframes / 2u + (nst * kSlotsPerStage - nframes); // wanted rank incl. zero pad slots
 
