@@ -49,12 +49,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 
+// try_wait that may stay suspended for up to `ns` nanoseconds before it reports failure (the default limit is a few
+// tens of cycles, so a waiting warp otherwise keeps issuing)
+__device__ __forceinline__ bool mbar_try_wait_for(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+                 "selp.u32 %0, 1, 0, P1;\n"
+                 "}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+                 : "memory");
+    return ok != 0;
+}
+
 __device__ __forceinline__ uint64_t global_timer_ns()
 {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+
+#ifndef CVVP_MBAR_SUSPEND_NS
+#define CVVP_MBAR_SUSPEND_NS 2000u
+#endif
 
 // Wait for the phase with the given parity.  NOTE (parity aliasing): a waiter may only start waiting
 // for fill q of a slot once fill q-1 of that slot has completed, otherwise the test passes early.
@@ -63,10 +83,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity))
         return;
+    // The spin loop is kept to try_wait + counter: a waiting warp shares its scheduler (and the integer pipe) with
+    // warps that have work, and reading the timer in every iteration made the waiters of median_pipe_kernel issue
+    // as many integer instructions as the workers.  The timer is read once per 4096 failed tries.
     const uint64_t t0 = global_timer_ns();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > 2000000000ull)
+    for (;;) {
+#pragma unroll 1
+        for (uint32_t spins = 0; spins < 4096u; ++spins)
+            if (mbar_try_wait_for(bar, parity, CVVP_MBAR_SUSPEND_NS))
+                return;
+        if (global_timer_ns() - t0 > 2000000000ull)
             __trap();
     }
 }
