@@ -161,6 +161,11 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     // P == 128: the stage lies in shared memory with TMA's 128-byte swizzle and is read with transposing matrix loads
     // (the byte stages of the transpose happen in the load path instead of 64 PRMTs per lane and stage)
     constexpr bool kLdsm = (LOG2S == 0);
+    // MODE 0 with the single plane buffer: the buffer is a pool of 64 half-stage slots (2 KB = the four planes of one
+    // nibble of one stage) handed back in two steps, see "half-slot pool" below
+    constexpr bool kHalf = (MODE == 0 && NSELW == 16);
+    constexpr uint32_t kCap = G * JT;      // stages the plane buffer holds = half-slots per nibble
+    constexpr uint32_t kFirst = kCap / 2u; // stages [0, kFirst) of a tile go into the slots that are released first
     static_assert(G == 2 || G == 4, "8 or 16 select warps");
     static_assert((1 << kColBits) >= int(G), "stage classes are encoded in the low column bits");
 
@@ -293,6 +298,44 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
             // r[8*p + b] = bit plane b of this lane's p-th element (elem_of(lane, p)) over its 32 frame slots.
             // Selectors must be done with the previous fill of this buffer.  Pre-check (almost always already
             // true): the fill before that one is finished, which makes the parity wait at most one phase away.
+            if constexpr (kHalf) {
+                // Half-slot pool.  The selectors of a tile hand back its 32 high-nibble slots as soon as those planes
+                // are in their registers (right after planes_full) and the 32 low-nibble slots four passes later.
+                // The first half of the NEXT tile's stages (both nibbles) goes into the former, the second half into
+                // the latter, so (at 32 stages) 16 stages are stored and 12 more wait transposed in registers while
+                // the selectors still work on the current tile.  With C = kCap slots per nibble and F = C / 2 the slot
+                // sets repeat with period two:
+                //   even tiles: high(s) = s, low(s) = C + s;   odd tiles: s < F: high = s, low = F + s;
+                //                                                           s >= F: high = F + s, low = C + s.
+                // rows_free[0] / [1] count the select warps that released the high / low slots (monotonic).
+                if (ti >= 1u) {
+                    if (lane == 0) {
+                        const uint32_t need = NSELW * ti;
+                        const uint32_t *cnt = rows_free + (st < kFirst ? 0 : 1);
+                        if (ld_acquire_shared(cnt) < need) {
+                            const uint64_t t0 = global_timer_ns();
+                            uint32_t spins = 0;
+                            while (ld_acquire_shared(cnt) < need) {
+                                __nanosleep(32);
+                                if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > 2000000000ull)
+                                    __trap();
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                const uint32_t odd = ti & 1u;
+                const uint32_t hi_slot = st + ((odd && st >= kFirst) ? kFirst : 0u);
+                const uint32_t lo_slot = st + ((odd && st < kFirst) ? kFirst : kCap);
+                const uint32_t col = lane ^ (st & (G - 1u));
+                uint4 *hi = reinterpret_cast<uint4 *>(planes) + hi_slot * 128u + col;
+                uint4 *lo = reinterpret_cast<uint4 *>(planes) + lo_slot * 128u + col;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    lo[p * 32] = make_uint4(r[8 * p + 0], r[8 * p + 1], r[8 * p + 2], r[8 * p + 3]);
+                    hi[p * 32] = make_uint4(r[8 * p + 4], r[8 * p + 5], r[8 * p + 6], r[8 * p + 7]);
+                }
+            } else {
             if constexpr (MODE == 3) {
                 // every select warp holds row st / G of the previous tile in registers (monotonic counter: no parity)
                 if (q >= 1u) {
@@ -326,6 +369,7 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
                     dst[(p * 2 + 0) * 32] = make_uint4(r[8 * p + 0], r[8 * p + 1], r[8 * p + 2], r[8 * p + 3]);
                 dst[(p * 2 + 1) * 32] = make_uint4(r[8 * p + 4], r[8 * p + 5], r[8 * p + 6], r[8 * p + 7]);
             }
+            } // !kHalf
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&planes_full[buf]);
@@ -650,15 +694,30 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
 #pragma unroll
         for (int bh = 1; bh >= 0; --bh) {
             uint4 w4[JT];
+            if constexpr (kHalf) {
+                // half-slot pool (see the transposers): this tile's high / low slots of stage 4j + g, then hand them back
+                const uint32_t odd = it & 1u;
+                const uint4 *hb = reinterpret_cast<const uint4 *>(planes) + s_g * 128u + s_p * 32u + s_col;
 #pragma unroll
-            for (int j = 0; j < JT; ++j)
-                w4[j] = base[j * (G * 256) + bh * 32]; // stage G*j+g, nibble bh: 4 planes in one LDS.128
-            if (bh == 0) {
-                // every plane word this thread needs is now in registers: hand the buffer back to the transposers
+                for (int j = 0; j < JT; ++j) {
+                    const bool first = uint32_t(G * j) + s_g < kFirst;
+                    const uint32_t off = bh ? ((odd && !first) ? kFirst : 0u) : ((odd && first) ? kFirst : kCap);
+                    w4[j] = hb[(uint32_t(G * j) + off) * 128u];
+                }
                 __syncwarp();
-                if (lane == 0) {
-                    atomicAdd(const_cast<uint32_t *>(sel_done) + buf, 1u);
-                    mbar_arrive(&planes_empty[buf]);
+                if (lane == 0)
+                    red_release_shared_inc(rows_free + (bh ? 0 : 1));
+            } else {
+#pragma unroll
+                for (int j = 0; j < JT; ++j)
+                    w4[j] = base[j * (G * 256) + bh * 32]; // stage G*j+g, nibble bh: 4 planes in one LDS.128
+                if (bh == 0) {
+                    // every plane word this thread needs is now in registers: hand the buffer back to the transposers
+                    __syncwarp();
+                    if (lane == 0) {
+                        atomicAdd(const_cast<uint32_t *>(sel_done) + buf, 1u);
+                        mbar_arrive(&planes_empty[buf]);
+                    }
                 }
             }
 #pragma unroll
