@@ -521,7 +521,7 @@ def median_single(E: Env, cfg, steps, warmup, sampler, e2e_steps, with_cpu, row_
     job_mpxf = W * H * N / 1e6
     res = {"ms_per_step": ms, "value": job_mpxf / (ms * 1e-3), "gpu_launches": int(launches), "kernel_ms": kern_ms}
     res["roofline"] = roofline(float(N) * nelem + nelem, kern_ms,
-                               "median_pipe_kernel<MODE 0> (on-chip bit-sliced select)" if N <= 2048 else
+                               "median_pipe_kernel<MODE 0> (on-chip bit-sliced select)" if N <= 1024 else
                                "median_pipe_kernel<MODE 3> x ceil(N/1024) launches + shard_window_final_kernel (one pass of window "
                                "counting; the gated two-pass fallback returns at once)",
                                "median_ncu_summary.json" if (N, W, H, E.world) == (1000, 1920, 1080, 1) else None)

@@ -34,16 +34,20 @@ int median_launch(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, siz
 {
     if (!d_out)
         return fail(ctx, CVVP_ERR_INVALID, "median: null output pointer");
-    // Up to 2048 frames the on-chip select reads every byte once at 128- or 64-byte tiles.  Longer stacks would need
-    // 32- / 16-byte tiles (1.5 TB/s and less): two counting passes in chunks of 1024 frames at full tile width are
-    // faster there, and reach 16 x 65535 frames (median_shard.cu).  CVVP_MEDIAN_TWO_PASS=0/1 forces either path (tests).
+    // Up to 1024 frames the on-chip select reads every byte once at 128-byte tiles.  Up to 2048 frames it still fits at
+    // 64-byte tiles, but TMA boxes of 64-byte rows cap the chip near 3 TB/s (one request per row: about 48 G requests/s
+    // whatever the row length, profiles/r1_median_probe_tiles.txt), and a frame stride well beyond a 2 MiB page costs
+    // another third there (profiles/r2_median_stride_probe.txt).  Counting passes in chunks of <= 1024 frames at full
+    // tile width are faster from about 1300 frames on (1080p x 1500: 0.91 against 1.03 ms; 4K x 1200: 3.1 against
+    // 4.3 ms) and reach 16 x 65535 frames (median_shard.cu).  CVVP_MEDIAN_TWO_PASS=0/1 forces either path (tests).
     // Long stacks first try ONE pass of window counting (median_pipe_kernel MODE 3: every 1024-frame launch counts
     // its frames in an 8-value window around its own pilot median; the owner kernel names the median wherever it
     // lies inside every launch's window) and run the two counting passes only over the 128-element tiles that hold an
     // undecided element -- the tile list is built on the device, so the call stays asynchronous.
     // CVVP_MEDIAN_WINDOW=0 skips the window pass (tests hold both to the oracle).
     const char *force = getenv("CVVP_MEDIAN_TWO_PASS");
-    const bool two_pass = force ? force[0] == '1' : nframes > 2048;
+    const bool long_stride = frame_stride > (5u << 19); // 2.5 MiB
+    const bool two_pass = force ? force[0] == '1' : (nframes > 1280 || (nframes > 1024 && long_stride));
     if (two_pass || nframes > median_max_frames()) {
         if (nframes > median_two_pass_max_frames())
             return fail(ctx, CVVP_ERR_UNSUPPORTED, "median: %lld frames exceed the supported maximum (%lld)", nframes,

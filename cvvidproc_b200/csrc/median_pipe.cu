@@ -95,7 +95,7 @@ __device__ __forceinline__ void red_release_shared_inc(uint32_t *p)
 
 // One transposing matrix load: two 16 x 16 BYTE tiles (lanes 0..15 / 16..31 name the 16-byte rows of the first / second
 // tile) arrive transposed -- lane T holds, of each tile, column T / 4 and column T / 4 + 8, rows 4 (T % 4) .. + 3 packed
-// into one register each (layout measured with tools/scratch/ldsm_probe.cu).  SASS: LDSM.8.MT1616.
+// into one register each (layout measured with tools/ldsm_probe.cu).  SASS: LDSM.8.MT1616.
 __device__ __forceinline__ void ldsm_t_b8_x2(uint32_t &a0, uint32_t &a1, uint32_t &b0, uint32_t &b1, uint32_t addr)
 {
     asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0, %1, %2, %3}, [%4];"

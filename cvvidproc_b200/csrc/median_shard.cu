@@ -686,7 +686,7 @@ int median_long_stack(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes,
             return rc;
     }
     if ((reinterpret_cast<uintptr_t>(d_out) & 3u) != 0) // the owner kernels store four result bytes at a time
-        return fail(ctx, CVVP_ERR_INVALID, "median: the result pointer of a stack of more than 2048 frames must be 4-byte aligned");
+        return fail(ctx, CVVP_ERR_INVALID, "median: the result pointer of a stack that takes the counting path (more than 1024 frames) must be 4-byte aligned");
     if (window) {
         for (int phase = 4; phase <= 5; ++phase) {
             const int rc = shard_phase(ctx, ctx->big, phase, d_frames, nframes, frame_stride, d_out, stream);

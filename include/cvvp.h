@@ -118,9 +118,9 @@ CVVP_API int cvvp_median_abort(cvvp_ctx *ctx);
  * d_frames + f*frame_stride (frame_stride % 16 == 0 and d_frames 16-byte aligned, the TMA
  * tensor-map constraints), d_out a DEVICE pointer to nelem bytes (4-byte aligned).  Runs on
  * `stream` (a cudaStream_t, NULL = the context's compute stream) and does not synchronize.
- * Up to 2048 frames the select happens on chip in one pass over the frames; longer stacks (up to
- * 16 x 65535 = 1048560 frames; more fails with CVVP_ERR_UNSUPPORTED) are counted in chunks of 1024
- * frames: one pass of window counting around per-chunk pilot medians, and -- only if that leaves an
+ * Up to 1280 frames (1024 when frame_stride exceeds 2.5 MiB) the select happens on chip in one pass
+ * over the frames; longer stacks (up to 16 x 65535 = 1048560 frames; more fails with
+ * CVVP_ERR_UNSUPPORTED) are counted in chunks of at most 1024 frames: one pass of window counting around per-chunk pilot medians, and -- only if that leaves an
  * element undecided, checked on the device -- two passes of nibble counting, 16-bit counts per
  * 65535 frames summed in 32 bits: the reference's analogue of widening its histogram bins with the
  * frame count (cv_vid_bg_helpers.cpp:232-253). */

@@ -115,7 +115,8 @@ def test_c5_long_stack_columns_and_both_device_forms(gpu_ctx, oracle_median, mon
     a = torch.empty(w * h, dtype=torch.uint8, device="cuda:0")
     b = torch.empty_like(a)
     c = torch.empty_like(a)
-    gpu_ctx.median_device(stack.data_ptr(), m, w * h, w * h, a.data_ptr())  # on-chip select (<= 2048 frames)
+    monkeypatch.setenv("CVVP_MEDIAN_TWO_PASS", "0")
+    gpu_ctx.median_device(stack.data_ptr(), m, w * h, w * h, a.data_ptr())  # on-chip select at 64-byte tiles
     monkeypatch.setenv("CVVP_MEDIAN_TWO_PASS", "1")
     gpu_ctx.median_device(stack.data_ptr(), m, w * h, w * h, b.data_ptr())  # long-stack path, window form
     monkeypatch.setenv("CVVP_MEDIAN_WINDOW", "0")

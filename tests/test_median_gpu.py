@@ -192,9 +192,9 @@ def test_too_many_frames_is_a_loud_error(gpu_ctx):
     assert ei.value.code == -5
 
 
-@pytest.mark.parametrize("n", [2049, 3000, 5000, 8193, 10000, 20001, 65535, 65536, 70001, 140000])
+@pytest.mark.parametrize("n", [1281, 2049, 3000, 5000, 8193, 10000, 20001, 65535, 65536, 70001, 140000])
 def test_long_stacks_take_the_two_pass_path(gpu_ctx, oracle_median, n):
-    """more than 2048 frames: two counting passes in chunks of <= 1024 frames (csrc/median_shard.cu, one rank)"""
+    """more than 1280 frames: counting passes in chunks of <= 1024 frames (csrc/median_shard.cu, one rank)"""
     rng = np.random.default_rng(n)
     nelem = 300 if n < 20000 else 130
     frames = rng.integers(60, 200, (n, 1, nelem), dtype=np.uint8)
@@ -215,7 +215,7 @@ def test_two_pass_forced_on_short_stacks(gpu_ctx, oracle_median, n, monkeypatch)
     assert np.array_equal(gpu_ctx.median(frames, chunk=512), oracle_median(frames))
 
 
-@pytest.mark.parametrize("n", [2049, 4096, 4097, 8192])
+@pytest.mark.parametrize("n", [1281, 1500, 2048, 2049, 4096, 4097, 8192])
 def test_single_pass_forced_on_long_stacks(gpu_ctx, oracle_median, n, monkeypatch):
     """CVVP_MEDIAN_TWO_PASS=0 keeps the on-chip select with its narrow tile variants covered"""
     monkeypatch.setenv("CVVP_MEDIAN_TWO_PASS", "0")

@@ -248,7 +248,7 @@ def test_window_form_reports_what_it_cannot_decide(oracle_median):
 @pytest.mark.parametrize("window", ["0", "1"])
 @pytest.mark.parametrize("n", [2049, 3000, 5001])
 def test_long_stack_on_one_gpu_both_forms(oracle_median, gpu_ctx, monkeypatch, window, n):
-    """cvvp_median_device beyond 2048 frames: window counting with the device-gated two-pass fallback behind it
+    """cvvp_median_device beyond 1280 frames: window counting with the device-gated two-pass fallback behind it
     (default) and the two passes alone (CVVP_MEDIAN_WINDOW=0) give the oracle's image; half of the elements are
     uniform noise over the whole range, which the one pass cannot decide, so the gated rounds really run"""
     monkeypatch.setenv("CVVP_MEDIAN_WINDOW", window)

@@ -1,4 +1,6 @@
-// Probe: fragment layout and throughput of ldmatrix.m16n16.trans.b8 on sm_100a.
+// Probe: fragment layout and throughput of ldmatrix.m16n16.trans.b8 on sm_100a.  Build and run on a B200:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -o /tmp/ldsm_probe tools/ldsm_probe.cu && /tmp/ldsm_probe
+// (result: profiles/r2_ldsm_probe.txt)
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -9,7 +9,7 @@ import subprocess
 from pathlib import Path
 
 REPO = Path(__file__).resolve().parent.parent
-PATTERNS = ["UTMALDG", r"SYNCS\.PHASECHK\.TRANS64\.TRYWAIT", r"SYNCS\.ARRIVE\.TRANS64", "POPC", "LOP3", "PRMT", "ATOMS", "MEMBAR"]
+PATTERNS = ["UTMALDG", r"LDSM\.8\.MT1616", r"SYNCS\.PHASECHK\.TRANS64\.TRYWAIT", r"SYNCS\.ARRIVE\.TRANS64", "POPC", "LOP3", "PRMT", "ATOMS", "MEMBAR"]
 
 
 def main():
