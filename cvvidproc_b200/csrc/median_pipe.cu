@@ -93,6 +93,27 @@ __device__ __forceinline__ void red_release_shared_inc(uint32_t *p)
     asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
 }
 
+// Every lane of the warp polls a monotonic shared-memory counter until it reaches `need` (acquire).  The loop is
+// load + compare + sleep: a polling warp shares its scheduler with working warps, and with one polling lane, a warp
+// barrier behind it and the watchdog's timer read in every iteration the pollers issued a tenth of the window
+// kernel's instructions.  The watchdog (2 s, trap instead of a hung GPU) looks at the timer once per 4096 polls.
+__device__ __forceinline__ void wait_counter(const uint32_t *cnt, uint32_t need)
+{
+    if (ld_acquire_shared(cnt) >= need)
+        return;
+    const uint64_t t0 = global_timer_ns();
+    for (;;) {
+#pragma unroll 1
+        for (uint32_t spins = 0; spins < 4096u; ++spins) {
+            __nanosleep(32);
+            if (ld_acquire_shared(cnt) >= need)
+                return;
+        }
+        if (global_timer_ns() - t0 > 2000000000ull)
+            __trap();
+    }
+}
+
 // One transposing matrix load: two 16 x 16 BYTE tiles (lanes 0..15 / 16..31 name the 16-byte rows of the first / second
 // tile) arrive transposed -- lane T holds, of each tile, column T / 4 and column T / 4 + 8, rows 4 (T % 4) .. + 3 packed
 // into one register each (layout measured with tools/ldsm_probe.cu).  SASS: LDSM.8.MT1616.
@@ -308,22 +329,8 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
                 //   even tiles: high(s) = s, low(s) = C + s;   odd tiles: s < F: high = s, low = F + s;
                 //                                                           s >= F: high = F + s, low = C + s.
                 // rows_free[0] / [1] count the select warps that released the high / low slots (monotonic).
-                if (ti >= 1u) {
-                    if (lane == 0) {
-                        const uint32_t need = NSELW * ti;
-                        const uint32_t *cnt = rows_free + (st < kFirst ? 0 : 1);
-                        if (ld_acquire_shared(cnt) < need) {
-                            const uint64_t t0 = global_timer_ns();
-                            uint32_t spins = 0;
-                            while (ld_acquire_shared(cnt) < need) {
-                                __nanosleep(32);
-                                if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > 2000000000ull)
-                                    __trap();
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
+                if (ti >= 1u)
+                    wait_counter(rows_free + (st < kFirst ? 0 : 1), NSELW * ti);
                 const uint32_t odd = ti & 1u;
                 const uint32_t hi_slot = st + ((odd && st >= kFirst) ? kFirst : 0u);
                 const uint32_t lo_slot = st + ((odd && st < kFirst) ? kFirst : kCap);
@@ -338,22 +345,8 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
             } else {
             if constexpr (MODE == 3) {
                 // every select warp holds row st / G of the previous tile in registers (monotonic counter: no parity)
-                if (q >= 1u) {
-                    if (lane == 0) {
-                        const uint32_t need = NSELW * q;
-                        const uint32_t *cnt = rows_free + st / G;
-                        if (ld_acquire_shared(cnt) < need) {
-                            const uint64_t t0 = global_timer_ns();
-                            uint32_t spins = 0;
-                            while (ld_acquire_shared(cnt) < need) {
-                                __nanosleep(32);
-                                if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > 2000000000ull)
-                                    __trap();
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
+                if (q >= 1u)
+                    wait_counter(rows_free + st / G, NSELW * q);
             } else {
                 if (q >= 2u) {
                     while (sel_done[buf] < NSELW * (q - 1u))
