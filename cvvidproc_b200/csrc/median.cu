@@ -11,11 +11,12 @@
 //               producer warp: each of the 12 transposer warps owns two private ring slots and re-issues the TMA
 //               load of its own next stage as soon as its lanes have read a slot (median_pipe.cu), so no "empty"
 //               barriers exist and every mbarrier wait is for the direct successor of a fill the warp consumed;
-//   transpose = each transposer warp takes one 4 KB stage, every lane reads 32 words (4 elements x
-//               32 frame slots) and bit-transposes them in registers (32x32 bit matrix:
-//               2 PRMT stages + 3 shift/LOP3 stages) into 4 elements x 8 bit planes, one word =
-//               32 frames of one bit of one element; planes go to shared memory (swizzled so both
-//               the stores and the select loads are bank-conflict free);
+//   transpose = each transposer warp takes one 4 KB stage and turns 4 elements x 32 frame slots per lane into
+//               4 elements x 8 bit planes, one word = 32 frames of one bit of one element (a 32x32 bit transpose per
+//               lane).  At 128-byte tiles the two byte stages happen in the load: the stage lies 128B-swizzled in
+//               shared memory and eight ldmatrix.m16n16.x2.trans.b8 (LDSM.8.MT1616) hand every lane registers that
+//               hold four frame slots of ONE element; three shift/LOP3 stages remain.  Planes go to shared memory
+//               (swizzled so both the stores and the select loads are bank-conflict free);
 //   select    = 8 passes, MSB first: count = popc(alive & ~plane) summed over the element's frame
 //               blocks (4..32 threads per element, warp shuffles), compare with the remaining
 //               rank, keep the matching half (alive &= plane or ~plane).

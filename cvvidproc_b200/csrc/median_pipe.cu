@@ -2,9 +2,12 @@
 // (Algorithm and reference citations: see median.cu.)
 //
 //   SELECT warps     (8 or 16)  tile t      : 8 MSB-first passes of popc over bit planes held in shared memory
-//   TRANSPOSE warps  (12)       tile t+1    : wait for a 4 KB TMA stage, 32x32 bit-transpose it in registers, store
-//                                             the planes, and immediately RE-ISSUE the TMA load of their own next
-//                                             stage into the slot they just drained
+//   TRANSPOSE warps  (12)       tile t+1    : wait for a 4 KB TMA stage, turn it into bit planes (128-byte tiles: eight
+//                                             transposing matrix loads, LDSM.8.MT1616, do the byte stages of the 32x32
+//                                             bit transpose in the load path and three shift/LOP3 stages remain;
+//                                             narrower tiles: plain loads, two PRMT stages more), store the planes, and
+//                                             immediately RE-ISSUE the TMA load of their own next stage into the slot
+//                                             they just drained
 //
 // There is no producer warp: a single thread issuing every TMA box costs ~290 cycles per stage (dependent
 // try_wait -> expect_tx -> issue chain) and caps the whole chip near 4 TB/s.  With 12 self-service warps the issue
@@ -15,11 +18,14 @@
 //
 // Two buffering modes, chosen by the stage count per tile (nst):
 //   nst <= 16 : two plane buffers, 8 select warps  (stages split by parity, JT = ceil(nst/2) <= 8 per thread)
-//   nst <= 32 : one plane buffer, 16 select warps  (stages split mod 4,      JT = ceil(nst/4) <= 8 per thread);
-//               the buffer is released as soon as the low-nibble planes are in registers, so the last four
-//               passes overlap the next tile's transposition; the 24 ring slots keep HBM streaming meanwhile.
+//   nst <= 32 : one plane buffer, 16 select warps  (stages split mod 4,      JT = ceil(nst/4) <= 8 per thread).
+//               MODE 0 treats the buffer as a pool of half-stage slots (the four planes of one nibble of one stage):
+//               the high-nibble slots of a tile are handed back as soon as those planes are in the selectors'
+//               registers, the low-nibble slots four passes later, and the next tile's first / second half of stages
+//               goes into them (see "half-slot pool" in the kernel); the 24 ring slots keep HBM streaming meanwhile.
 //
-// Plane layout per buffer: [stage][byte p][nibble bh][column phi][4 words = bits 4bh..4bh+3]: a transposer lane
+// Plane layout per buffer (half-slot pool: per 2 KB slot [byte p][column phi][4 words]):
+// [stage][byte p][nibble bh][column phi][4 words = bits 4bh..4bh+3]: a transposer lane
 // stores uint4, a select thread loads the four planes of a nibble with one LDS.128.  phi = lane ^ (stage % G)
 // (G = 2 or 4 stage classes); the select thread for logical lane L and stage class g reads column L ^ g, which is
 // its own lane id ^ (low column bits held in its warp id).  Both patterns touch 8 distinct 16-byte columns per
