@@ -232,90 +232,129 @@ __global__ void __launch_bounds__(32) shard_final_listed_kernel(const __grid_con
 // slot is empty and is skipped).
 __global__ void __launch_bounds__(256) shard_window_final_kernel(const __grid_constant__ OwnerArgs A)
 {
-    __shared__ uint32_t delta[9][256]; // per thread: frames whose value first counts at window position i
+    // The records are read ONCE, coalesced: a group's 256 records of a source are 5120 contiguous bytes, fetched 16 bytes
+    // per thread (the next source's while this one is evaluated) and handed out through shared memory.  Windows that
+    // intersect lie within 7 values of each other, so counts are kept by position relative to the FIRST source's window
+    // (value v at v - base0 + 7, 23 positions); a source further away means an empty intersection.  A block walks over
+    // many groups of 256 elements and fences its peer stores once, at the end (one system-wide fence per 256 elements
+    // was most of this kernel's time).
+    __shared__ uint32_t hist[23][256];
+    __shared__ __align__(16) uint32_t stage[2][1280];
     __shared__ uint32_t unresolved;
-    if (threadIdx.x == 0)
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0)
         unresolved = 0;
-    __syncthreads();
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool mine = i < A.owned;
-    uint32_t med = 0;
-    bool ok = true;
-    if (mine) {
-        ok = false;
-        // pass 1: N, and the intersection [lo, hi] of the sources' windows
-        uint32_t total = 0, lo = 0, hi = 255;
-        for (uint32_t src = 0; src < A.world; ++src) {
-            const size_t slot = src_slot(A, src);
-            const uint32_t nfr = __ldg(A.src_frames + slot);
-            if (nfr == 0u)
-                continue;
-            const uint32_t base = __ldg(A.counts + slot * A.slice * 8u + size_t(i) * 5u + 4u) >> 16;
-            total += nfr;
-            lo = max(lo, base);
-            hi = min(hi, base + 7u);
-        }
-        const uint32_t k = total / 2u; // halfway rank: first value with cumulative count > N / 2  (:160-166)
-        if (total != 0u && lo <= hi) {
+    // next source slot with frames at or after s (uniform over the block)
+    auto next_source = [&](uint32_t s) {
+        while (s < A.world && __ldg(A.src_frames + src_slot(A, s)) == 0u)
+            ++s;
+        return s;
+    };
+    const uint32_t ngroups = (A.owned + 255u) / 256u;
+    for (uint32_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        __syncthreads(); // the previous group's stage buffers and histogram are no longer read (and `unresolved` is set)
 #pragma unroll
-            for (int c = 0; c < 9; ++c)
-                delta[c][threadIdx.x] = 0;
-            uint32_t cum = 0; // G(lo - 1), then G(lo - 1 + c)
-            for (uint32_t src = 0; src < A.world; ++src) {
-                const size_t slot = src_slot(A, src);
-                if (__ldg(A.src_frames + slot) == 0u)
-                    continue;
-                const uint32_t *rec = A.counts + slot * A.slice * 8u + size_t(i) * 5u;
-                const uint32_t w[4] = {__ldg(rec), __ldg(rec + 1), __ldg(rec + 2), __ldg(rec + 3)};
-                const uint32_t t = __ldg(rec + 4);
-                const int o = int(lo - (t >> 16)); // window position of lo in this source (0..7)
-                cum += t & 0xFFFFu;
+        for (int c = 0; c < 23; ++c)
+            hist[c][tid] = 0;
+        const uint32_t i0 = g * 256u;
+        const uint32_t i = i0 + tid;
+        const bool mine = i < A.owned;
+        const uint32_t nw = min(256u, A.owned - i0) * 5u; // record words of this group per source
+        uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+        auto fetch = [&](uint32_t s) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(A.counts + src_slot(A, s) * A.slice * 8u + size_t(i0) * 5u);
+            if (4u * tid < nw)
+                ra = __ldcg(src + tid);
+            if (tid < 64u && 4u * (256u + tid) < nw)
+                rb = __ldcg(src + 256u + tid);
+        };
+        uint32_t total = 0, lo = 0, hi = 255, cum = 0, base0 = 0;
+        bool first = true, far = false;
+        uint32_t s = next_source(0);
+        if (s < A.world)
+            fetch(s);
+        for (uint32_t buf = 0; s < A.world; buf ^= 1u) {
+            uint4 *st4 = reinterpret_cast<uint4 *>(stage[buf]);
+            st4[tid] = ra;
+            if (tid < 64u)
+                st4[256u + tid] = rb;
+            __syncthreads(); // (the buffer written two sources ago was read before the previous barrier)
+            const uint32_t nfr = __ldg(A.src_frames + src_slot(A, s));
+            s = next_source(s + 1u);
+            if (s < A.world)
+                fetch(s);
+            if (mine) {
+                const uint32_t *rec = stage[buf] + tid * 5u;
+                const uint32_t w[4] = {rec[0], rec[1], rec[2], rec[3]};
+                const uint32_t t = rec[4];
+                const uint32_t base = t >> 16;
+                if (first) {
+                    base0 = base;
+                    first = false;
+                }
+                total += nfr;
+                lo = max(lo, base);
+                hi = min(hi, base + 7u);
+                cum += t & 0xFFFFu; // frames below this source's window
+                const int off = int(base) - int(base0) + 7;
+                if (off < 0 || off > 14) {
+                    far = true;
+                } else {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t cnt = (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xFFFFu);
-                    const int pos = c - o + 1; // value base + c is counted by G(lo - 1 + j) for every j >= pos
-                    delta[pos > 0 ? pos : 0][threadIdx.x] += cnt;
+                    for (int c = 0; c < 8; ++c)
+                        hist[off + c][tid] += (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xFFFFu);
                 }
             }
-            cum += delta[0][threadIdx.x];
-            const uint32_t span = hi - lo + 1u; // G is exact for positions 0 .. span
-            if (cum <= k) {
-                for (uint32_t c = 1; c <= span; ++c) {
-                    cum += delta[c][threadIdx.x];
-                    if (cum > k) {
-                        med = lo - 1u + c;
-                        ok = true;
-                        break;
+        }
+        uint32_t med = 0;
+        bool ok = true;
+        if (mine) {
+            ok = false;
+            const uint32_t k = total / 2u; // halfway rank: first value with cumulative count > N / 2  (:160-166)
+            if (total != 0u && !far && lo <= hi) {
+                // G(lo - 1) = frames below every window + the counted values <= lo - 1; G is exact up to hi
+                const uint32_t p0 = lo - base0 + 7u; // position of value lo
+                for (uint32_t pos = 0; pos < p0; ++pos)
+                    cum += hist[pos][tid];
+                const uint32_t span = hi - lo + 1u;
+                if (cum <= k) {
+                    for (uint32_t c = 0; c < span; ++c) {
+                        cum += hist[p0 + c][tid];
+                        if (cum > k) {
+                            med = lo + c;
+                            ok = true;
+                            break;
+                        }
                     }
                 }
             }
         }
-    }
-    // four lanes -> one word (owned slices start at multiples of 128 elements, so element i & ~3 is word aligned)
-    uint32_t packed = med << (8u * (threadIdx.x & 3u));
-    packed |= __shfl_xor_sync(0xFFFFFFFFu, packed, 1);
-    packed |= __shfl_xor_sync(0xFFFFFFFFu, packed, 2);
-    if (mine && (threadIdx.x & 3u) == 0u) {
-        const size_t e0 = size_t(A.rank) * A.slice + i;
-        const uint32_t n = min(4u, A.owned - i);
-        for (uint32_t r = 0; r < A.nranks; ++r) {
-            uint8_t *dst = A.result[r] + e0;
-            if (n == 4u) {
-                *reinterpret_cast<uint32_t *>(dst) = packed;
-            } else {
-                for (uint32_t q = 0; q < n; ++q)
-                    dst[q] = uint8_t(packed >> (8u * q));
+        // four lanes -> one word (owned slices start at multiples of 128 elements, so element i & ~3 is word aligned)
+        uint32_t packed = med << (8u * (tid & 3u));
+        packed |= __shfl_xor_sync(0xFFFFFFFFu, packed, 1);
+        packed |= __shfl_xor_sync(0xFFFFFFFFu, packed, 2);
+        if (mine && (tid & 3u) == 0u) {
+            const size_t e0 = size_t(A.rank) * A.slice + i;
+            const uint32_t n = min(4u, A.owned - i);
+            for (uint32_t r = 0; r < A.nranks; ++r) {
+                uint8_t *dst = A.result[r] + e0;
+                if (n == 4u) {
+                    *reinterpret_cast<uint32_t *>(dst) = packed;
+                } else {
+                    for (uint32_t q = 0; q < n; ++q)
+                        dst[q] = uint8_t(packed >> (8u * q));
+                }
             }
         }
-    }
-    if (!ok) {
-        atomicAdd(&unresolved, 1u);
-        const size_t tile = (size_t(A.rank) * A.slice + i) >> 7; // the 128-element tile of the counting kernels
-        for (uint32_t r = 0; r < A.nranks; ++r)
-            A.tflag[r][tile] = 1u;
+        if (!ok) {
+            atomicAdd(&unresolved, 1u);
+            const size_t tile = (size_t(A.rank) * A.slice + i) >> 7; // the 128-element tile of the counting kernels
+            for (uint32_t r = 0; r < A.nranks; ++r)
+                A.tflag[r][tile] = 1u;
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && unresolved != 0u)
+    if (tid == 0 && unresolved != 0u)
         for (uint32_t r = 0; r < A.nranks; ++r)
             atomicAdd_system(A.flag[r], unresolved);
     __threadfence_system();
@@ -653,7 +692,11 @@ static int shard_phase(cvvp_ctx *ctx, MedianShard *sh, int phase, const uint8_t 
         else if (phase == 3)
             shard_final_kernel<<<((A.owned + 3) / 4 + 255) / 256, 256, 0, s>>>(A);
         else
-            shard_window_final_kernel<<<(A.owned + 255) / 256, 256, 0, s>>>(A);
+            {
+                const uint32_t groups = (A.owned + 255u) / 256u; // persistent blocks: six fit an SM
+                const uint32_t grid = std::min<uint32_t>(groups, uint32_t(ctx->sm_count) * 6u);
+                shard_window_final_kernel<<<grid, 256, 0, s>>>(A);
+            }
         CVVP_CUDA_OK(ctx, cudaGetLastError());
         ctx->launches++;
         return CVVP_OK;
