@@ -99,6 +99,21 @@ __device__ __forceinline__ void red_release_shared_inc(uint32_t *p)
     asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
 }
 
+// A select warp hands plane slots back as soon as it has LOADED them -- and "loaded" must mean that the data sits in its
+// registers.  Issuing the loads is not enough: nothing orders a later store of another warp (a transposer woken by
+// the hand-back) behind loads that are still queued in this warp's path to shared memory, and on an SM whose
+// transposers already wait with the next tile in registers (the first tile of a CTA) the store did overtake them:
+// wrong medians in a few tiles per launch at 769 .. 896 frames, found by
+// tests/test_median_gpu.py::test_every_cta_walks_several_tiles_of_the_single_buffer_mode.  So every hand-back depends
+// on the loaded data: `fold` is the XOR of one word of every load, ANDed with a zero the compiler cannot see; the
+// instruction cannot issue before the registers are written, and its result (0) is added to the signalled address.
+__device__ __forceinline__ uint32_t landed(uint32_t fold, uint32_t opaque_zero)
+{
+    uint32_t z;
+    asm volatile("and.b32 %0, %1, %2;" : "=r"(z) : "r"(fold), "r"(opaque_zero));
+    return z;
+}
+
 // Every lane of the warp polls a monotonic shared-memory counter until it reaches `need` (acquire).  The loop is
 // load + compare + sleep: a polling warp shares its scheduler with working warps, and with one polling lane, a warp
 // barrier behind it and the watchdog's timer read in every iteration the pollers issued a tenth of the window
@@ -247,11 +262,12 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
         const uint32_t w = warp - NSELW;
         const uint32_t total_stages = my_tiles * nst; // global stage sequence of this CTA
         // issue the TMA load of the stage at (tile iteration t, stage s) into this warp's slot for its k-th stage
-        auto issue = [&](uint32_t k, uint32_t t, uint32_t s) {
+        // (z: 0, see landed() -- a refill must not be issued before the slot's previous content has been read)
+        auto issue = [&](uint32_t k, uint32_t t, uint32_t s, uint32_t z) {
             const uint32_t slot = w + kTrWarps * (k & 1u);
             const uint32_t tile = tile_at(t);
             mbar_arrive_expect_tx(&ring_full[slot], kStageBytes);
-            tma_load_2d(ring + size_t(slot) * kStageWords, &tmap, &ring_full[slot], int32_t(tile * P),
+            tma_load_2d(ring + size_t(slot) * kStageWords + z, &tmap, &ring_full[slot], int32_t(tile * P),
                         int32_t(s * kSlotsPerStage), l2_policy);
         };
         auto advance = [&](uint32_t &t, uint32_t &s) { // next stage of this warp: global stage number += 12
@@ -269,10 +285,10 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
         }
         uint32_t ti2 = ti, st2 = st; // look-ahead cursor: the stage that is (re)issued next
         if (lane == 0 && w < total_stages)
-            issue(0, ti2, st2);
+            issue(0, ti2, st2, 0u);
         advance(ti2, st2);
         if (lane == 0 && w + kTrWarps < total_stages)
-            issue(1, ti2, st2);
+            issue(1, ti2, st2, 0u);
         advance(ti2, st2);
 
         // byte offsets of this lane's tile row in a swizzled stage, for even and odd loads (see below)
@@ -307,9 +323,19 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
                 for (int i = 0; i < 32; ++i)
                     r[i] = src[i * 32];
             }
-            __syncwarp(); // every lane has read the slot: refill it with this warp's stage k+2 (same slot)
+            // Every lane has read the slot -- i.e. the data is in registers, not merely requested: the TMA unit writes
+            // through another path than the loads take, and a refill from L2 did overtake loads that were still queued
+            // behind the shared-memory traffic of a CTA's first tile (one stage of stale data in a few tiles per launch).
+            // The refill's destination therefore depends on the loaded words (landed()); the loads of a warp complete
+            // as a whole, so lane 0's dependency covers every lane.
+            uint32_t fold = 0;
+#pragma unroll
+            for (int i = 0; i < (kLdsm ? 8 : 32); ++i)
+                fold ^= r[i];
+            const uint32_t z = landed(fold, nst >> 8);
+            __syncwarp(); // refill the slot with this warp's stage k+2
             if (lane == 0 && gs + 2 * kTrWarps < total_stages)
-                issue(k, ti2, st2);
+                issue(k, ti2, st2, z);
             advance(ti2, st2);
             if constexpr (kLdsm) {
                 if (MODE == 1)
@@ -390,6 +416,7 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
     const uint32_t s_elem = kLdsm ? 64u * (s_p >> 1) + 16u * (s_c & 3u) + 8u * (s_p & 1u) + (s_c >> 2) : 4u * s_c + s_p;
     const bool s_writer = (s_g == 0u) && ((lane >> kColBits) == 0u);
     const uint32_t k0 = nframes / 2u + (nst * kSlotsPerStage - nframes); // wanted rank incl. zero pad slots
+    const uint32_t zero = nst >> 8; // 0 (nst <= 32), but not to the compiler: see landed()
 
     for (uint32_t it = 0; it < my_tiles; ++it) {
         const uint32_t tile = tile_at(it);
@@ -409,11 +436,18 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
                 plo[i] = base[pilot_row(i) * (G * 256)];
                 phi[i] = base[pilot_row(i) * (G * 256) + 32];
             }
-            __syncwarp();
-            if (lane == 0) {
+            {
+                uint32_t fold = 0;
 #pragma unroll
                 for (int i = 0; i < JP; ++i)
-                    red_release_shared_inc(rows_free + pilot_row(i));
+                    fold ^= plo[i].x ^ phi[i].x;
+                const uint32_t z = landed(fold, zero);
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < JP; ++i)
+                        red_release_shared_inc(rows_free + pilot_row(i) + z);
+                }
             }
             // pilot rank: the pilot stages are G*j .. G*j + G-1 of the pilot rows; their real frames and pad slots
             uint32_t p_real = 0, p_slots = 0;
@@ -488,9 +522,10 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
                         nlo = base[row_of(r + 1) * (G * 256)];
                         nhi = base[row_of(r + 1) * (G * 256) + 32];
                     }
+                    const uint32_t z = landed(clo.x ^ chi.x, zero);
                     __syncwarp();
                     if (lane == 0)
-                        red_release_shared_inc(rows_free + j); // row j was loaded one iteration ago
+                        red_release_shared_inc(rows_free + j + z); // row j was loaded one iteration ago
                     window_row(acc, below, clo, chi, fb, (G * uint32_t(j) + s_g) < nst ? 0xFFFFFFFFu : 0u);
                 }
             }
@@ -571,10 +606,15 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
 #pragma unroll
                 for (int j = 0; j < JT; ++j)
                     w4[j] = base[j * (G * 256) + 32]; // high-nibble planes
+                uint32_t fold = 0;
+#pragma unroll
+                for (int j = 0; j < JT; ++j)
+                    fold ^= w4[j].x;
+                const uint32_t z = landed(fold, zero);
                 __syncwarp();
                 if (lane == 0) {
-                    atomicAdd(const_cast<uint32_t *>(sel_done) + buf, 1u);
-                    mbar_arrive(&planes_empty[buf]);
+                    atomicAdd(const_cast<uint32_t *>(sel_done) + buf + z, 1u);
+                    mbar_arrive(&planes_empty[buf + z]);
                 }
 #pragma unroll
                 for (int j = 0; j < JT; ++j)
@@ -595,10 +635,15 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
 #pragma unroll
                 for (int j = 0; j < JT; ++j)
                     w4[j] = base[j * (G * 256)]; // low-nibble planes
+                uint32_t fold = 0;
+#pragma unroll
+                for (int j = 0; j < JT; ++j)
+                    fold ^= w4[j].x ^ eq[j];
+                const uint32_t z = landed(fold, zero);
                 __syncwarp();
                 if (lane == 0) {
-                    atomicAdd(const_cast<uint32_t *>(sel_done) + buf, 1u);
-                    mbar_arrive(&planes_empty[buf]);
+                    atomicAdd(const_cast<uint32_t *>(sel_done) + buf + z, 1u);
+                    mbar_arrive(&planes_empty[buf + z]);
                 }
 #pragma unroll
                 for (int j = 0; j < JT; ++j)
@@ -703,19 +748,29 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
                     const uint32_t off = bh ? ((odd && !first) ? kFirst : 0u) : ((odd && first) ? kFirst : kCap);
                     w4[j] = hb[(uint32_t(G * j) + off) * 128u];
                 }
+                uint32_t fold = 0;
+#pragma unroll
+                for (int j = 0; j < JT; ++j)
+                    fold ^= w4[j].x;
+                const uint32_t z = landed(fold, zero);
                 __syncwarp();
                 if (lane == 0)
-                    red_release_shared_inc(rows_free + (bh ? 0 : 1));
+                    red_release_shared_inc(rows_free + (bh ? 0 : 1) + z);
             } else {
 #pragma unroll
                 for (int j = 0; j < JT; ++j)
                     w4[j] = base[j * (G * 256) + bh * 32]; // stage G*j+g, nibble bh: 4 planes in one LDS.128
                 if (bh == 0) {
                     // every plane word this thread needs is now in registers: hand the buffer back to the transposers
+                    uint32_t fold = 0;
+#pragma unroll
+                    for (int j = 0; j < JT; ++j)
+                        fold ^= w4[j].x;
+                    const uint32_t z = landed(fold, zero);
                     __syncwarp();
                     if (lane == 0) {
-                        atomicAdd(const_cast<uint32_t *>(sel_done) + buf, 1u);
-                        mbar_arrive(&planes_empty[buf]);
+                        atomicAdd(const_cast<uint32_t *>(sel_done) + buf + z, 1u);
+                        mbar_arrive(&planes_empty[buf + z]);
                     }
                 }
             }

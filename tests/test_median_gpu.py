@@ -168,6 +168,20 @@ def test_device_resident_full_size_property(gpu_ctx):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("n", [513, 530, 641, 650, 769, 780, 897, 900, 1000, 1024])
+def test_every_cta_walks_several_tiles_of_the_single_buffer_mode(gpu_ctx, oracle_median, n):
+    """One plane buffer (more than 512 frames), every stage count per select thread (5 .. 8, odd ones split a plane row
+    between the slots released first and second), and 469 tiles for 148 CTAs: every CTA goes through even and odd tiles of
+    the half-slot pool (csrc/median_pipe.cu), whose slot sets alternate."""
+    rng = np.random.default_rng(n * 3 + 1)
+    frames = _rand(rng, n, 60, 1000, 60, 200)
+    frames[:, 0, :7] = 0                 # value 0 coincides with the zero-filled pad slots
+    frames[: n // 2, 1, :5] = 9          # exact split: the upper median
+    frames[n // 2 :, 1, :5] = 250
+    got = gpu_ctx.median(frames, chunk=256)
+    assert np.array_equal(got, oracle_median(frames, nthreads=8))
+
+
 def test_uhd_geometry_matches_oracle(gpu_ctx, oracle_median):
     """BASELINE configs[4] geometry (3840x2160) at a reduced frame count: full compare against the oracle"""
     from cvvidproc_b200 import synth
