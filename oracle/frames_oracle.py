@@ -14,10 +14,16 @@ and of the crop-rectangle rule
 The arithmetic of cvtColor lives in OpenCV, which is NOT vendored under /root/reference (CMakeLists.txt:52 states
 `OpenCV >= 4.2.0`); each statement below is the cv2 4.13.0 call of the cited line.
 
-PARITY UNPINNED BY THE REFERENCE (no tests or fixtures).  The pins we add:
+PARITY PINNED BY THE REFERENCE'S OWN SOURCE RUN HERE.  The reference has no tests or fixtures for this path
+(SURVEY.md section 4); the pin is its generator itself: oracle/Makefile (target ref_frames) compiles
+cv_vid_frames_generator_algo.h UNMODIFIED from /root/reference against oracle/shim_cv2 (cv::VideoCapture,
+cv::extractChannel, cv::cvtColor forward to the cv2 wheel) into oracle/_ref/cvvp_frames_ref, and
+tests/test_oracle_frames.py holds `prepare_frames` to the tokens GetTokenSet() emits for lossless videos (frame range,
+crop, all three channel modes); tests/golden/frames_golden.json holds hashes of the reference's tokens wherever a video
+can carry the case (tests/golden/make_frames_golden.py).  GetCroppedFrameDims lives in a file that needs the whole
+AsyncTokens/cv_util build and is restated only (twenty lines of integer logic).  Beyond that:
 `rgb2gray_fixed_point` below (the closed form of OpenCV's 8-bit RGB2GRAY) is held to cv2 on ALL 2^24 colour triples
-by tests/test_oracle_frames.py, and tests/golden/frames_golden.json holds hashes of this oracle on seeded inputs
-(tests/golden/make_frames_golden.py).
+by tests/test_oracle_frames.py.
 """
 from __future__ import annotations
 

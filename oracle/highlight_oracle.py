@@ -16,10 +16,16 @@ this image, but the Python wheel `cv2` 4.13.0 exposes every function the referen
 and the reference source itself carries the original Python lines as comments (:26, :34, :38, :116-140, :159-173,
 :197-217), so each statement below is the cv2 call of the cited reference line.
 
-PARITY UNPINNED BY THE REFERENCE: it ships no tests, golden vectors or fixtures for this path.
-The pins we add: tests/golden/highlight_golden.json (hashes of this oracle's outputs on seeded inputs, generated by
-tests/golden/make_highlight_golden.py) and the independent label-based model oracle/highlight_model.py, which must
-agree with this file on random and adversarial images (tests/test_oracle_highlight.py).
+PARITY PINNED BY THE REFERENCE'S OWN SOURCE RUN HERE.  The reference ships no tests, golden vectors or fixtures for
+this path, so the pin is the reference itself: oracle/Makefile (target ref_highlight) compiles
+highlight_objects_algo.{h,cpp} UNMODIFIED from /root/reference against oracle/shim_cv2 -- a stand-in for
+<opencv2/opencv.hpp> whose cv:: functions forward to the cv2 wheel, i.e. to OpenCV's real core/imgproc code -- into
+oracle/_ref/cvvp_highlight_ref (oracle/highlight_ref_driver.cpp drives the class through Insert / HasResults /
+TryGetResult).  tests/test_oracle_highlight.py holds every function below to the reference function it restates
+(whole pipeline on 120 random + every adversarial case + full-size C3/C4 frames; ThresholdImage incl. Otsu,
+ThresholdImageWithHysteresis, RemoveSmallObjects, FillHoles one by one), and tests/golden/highlight_golden.json holds
+hashes of the REFERENCE's outputs (tests/golden/make_highlight_golden.py).  What the pin cannot cover is an OpenCV
+other than the wheel's 4.13.0.  The independent label-based model oracle/highlight_model.py stays as a second opinion.
 """
 from __future__ import annotations
 

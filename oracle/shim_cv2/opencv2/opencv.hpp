@@ -1,0 +1,354 @@
+// TEST INFRASTRUCTURE ONLY.
+// Stand-in for <opencv2/opencv.hpp> that lets the reference's own
+//     /root/reference/Sources/ProcessorAlgos/highlight_objects_algo.{h,cpp}
+//     /root/reference/Sources/ProcessorTokenHandlers/cv_vid_frames_generator_algo.h
+// be compiled UNMODIFIED where OpenCV's C++ headers and libraries are absent (this image): every cv:: function the
+// file calls is forwarded to the function of the same name in the Python wheel `cv2` (OpenCV 4.13), which IS
+// installed and runs OpenCV's real core/imgproc code.  cv::Mat wraps a numpy array; `rows`, `cols` and `data` are
+// kept as public fields because the reference reads them directly (highlight_objects_algo.h:63, .cpp:26, :201-208).
+//
+// This is not OpenCV and not reference code.  What it must get right, and how:
+//   * `Mat = Mat - Mat` (.cpp:27): a MatExpr assigned to a Mat evaluates cv::subtract(a, b, dst) with dtype -1, i.e.
+//     the destination takes the operands' depth (CV_8U, saturating) whatever it was declared as  -> cv2.subtract.
+//   * OutputArray: Mat::create() keeps the buffer when size and type already match, else allocates  -> shim::output().
+//   * a Mat copy shares its pixels (reference-counted header)  -> the copies share one numpy array.
+//   * cv::drawContours with an empty contour list is a no-op in C++; cv2's binding rejects the empty list -> skipped.
+//   * cv::VideoCapture is cv2.VideoCapture (same FFmpeg backend, same property numbers); `vid >> frame` leaves an
+//     empty Mat at the end of the stream.
+// Built into oracle/_ref/cvvp_highlight_ref*.so and oracle/_ref/cvvp_frames_ref*.so by oracle/Makefile (targets
+// ref_highlight, ref_frames); used by tests/ and by the tests/golden/make_*_golden.py scripts only.
+#ifndef CVVP_ORACLE_OPENCV_CV2_SHIM_HPP
+#define CVVP_ORACLE_OPENCV_CV2_SHIM_HPP
+
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+
+#include <cassert>
+#include <climits>
+#include <cstddef>
+#include <cstdint>
+#include <iostream> // the real header brings it in; cv_vid_frames_generator_algo.h:164 relies on that
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#define CV_8U 0
+#define CV_8S 1
+#define CV_16U 2
+#define CV_16S 3
+#define CV_32S 4
+#define CV_32F 5
+#define CV_64F 6
+#define CV_CN_SHIFT 3
+#define CV_MAT_DEPTH(type) ((type) & ((1 << CV_CN_SHIFT) - 1))
+#define CV_MAT_CN(type) (((type) >> CV_CN_SHIFT) + 1)
+#define CV_MAKETYPE(depth, cn) (CV_MAT_DEPTH(depth) + (((cn)-1) << CV_CN_SHIFT))
+#define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_8UC2 CV_MAKETYPE(CV_8U, 2)
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
+
+namespace cv
+{
+namespace py = pybind11;
+typedef unsigned char uchar;
+
+enum ThresholdTypes { THRESH_BINARY = 0, THRESH_BINARY_INV = 1, THRESH_TRUNC = 2, THRESH_TOZERO = 3, THRESH_TOZERO_INV = 4,
+                      THRESH_OTSU = 8 };
+enum MorphTypes { MORPH_ERODE = 0, MORPH_DILATE = 1, MORPH_OPEN = 2, MORPH_CLOSE = 3 };
+enum RetrievalModes { RETR_EXTERNAL = 0, RETR_LIST = 1, RETR_CCOMP = 2, RETR_TREE = 3 };
+enum ContourApproximationModes { CHAIN_APPROX_NONE = 1, CHAIN_APPROX_SIMPLE = 2 };
+enum FloodFillFlags { FLOODFILL_FIXED_RANGE = 1 << 16, FLOODFILL_MASK_ONLY = 1 << 17 };
+enum LineTypes { FILLED = -1, LINE_4 = 4, LINE_8 = 8 };
+enum VideoCaptureProperties { CAP_PROP_POS_MSEC = 0, CAP_PROP_POS_FRAMES = 1, CAP_PROP_FRAME_WIDTH = 3, CAP_PROP_FRAME_HEIGHT = 4,
+                              CAP_PROP_FPS = 5, CAP_PROP_FOURCC = 6, CAP_PROP_FRAME_COUNT = 7, CAP_PROP_FORMAT = 8,
+                              CAP_PROP_CONVERT_RGB = 16 };
+enum ColorConversionCodes { COLOR_BGR2GRAY = 6, COLOR_RGB2GRAY = 7 };
+
+struct Size {
+    int width{0}, height{0};
+    Size() = default;
+    Size(int w, int h) : width{w}, height{h} {}
+};
+struct Point {
+    int x{0}, y{0};
+    Point() = default;
+    Point(int x_, int y_) : x{x_}, y{y_} {}
+};
+struct Rect {
+    int x{0}, y{0}, width{0}, height{0};
+    Rect() = default;
+    Rect(int x_, int y_, int w, int h) : x{x_}, y{y_}, width{w}, height{h} {}
+};
+struct Scalar {
+    double val[4]{0, 0, 0, 0};
+    Scalar() = default;
+    Scalar(double v0) : val{v0, 0, 0, 0} {}
+    Scalar(double v0, double v1, double v2 = 0, double v3 = 0) : val{v0, v1, v2, v3} {}
+};
+
+namespace shim
+{
+inline py::module_ cv2() { return py::module_::import("cv2"); }
+inline py::module_ np() { return py::module_::import("numpy"); }
+inline py::tuple tup(const Scalar &s) { return py::make_tuple(s.val[0], s.val[1], s.val[2], s.val[3]); }
+inline py::tuple tup(const Point &p) { return py::make_tuple(p.x, p.y); }
+inline const char *dtype_name(int depth)
+{
+    static const char *names[] = {"uint8", "int8", "uint16", "int16", "int32", "float32", "float64"};
+    if (depth < 0 || depth > CV_64F)
+        throw std::invalid_argument("opencv shim: unsupported depth");
+    return names[depth];
+}
+inline int depth_of(const py::array &a)
+{
+    const std::string n = py::str(a.dtype().attr("name"));
+    for (int d = 0; d <= CV_64F; ++d)
+        if (n == dtype_name(d))
+            return d;
+    throw std::invalid_argument("opencv shim: unsupported dtype " + n);
+}
+} // namespace shim
+
+class Mat;
+struct MatExpr { // only `a - b` is needed (.cpp:27)
+    const Mat &a;
+    const Mat &b;
+};
+
+class Mat
+{
+public:
+    int rows{0};
+    int cols{0};
+    uchar *data{nullptr};
+
+    Mat() = default;
+    Mat(Size s, int type) { create(s.height, s.width, type); }
+    Mat(int rows_, int cols_, int type) { create(rows_, cols_, type); }
+    Mat(int rows_, int cols_, int type, const Scalar &s)
+    {
+        create(rows_, cols_, type);
+        *this = s;
+    }
+    explicit Mat(py::array a) { adopt(std::move(a)); }
+    Mat(const Mat &) = default; // shares the pixels, like a reference-counted cv::Mat header
+    Mat(Mat &&) = default;
+    Mat &operator=(const Mat &) = default;
+    Mat &operator=(Mat &&) = default;
+    inline Mat &operator=(const MatExpr &e);
+    Mat &operator=(const Scalar &s) // setTo over every channel
+    {
+        if (!m_arr.is_none()) {
+            if (channels() == 1)
+                m_arr.attr("fill")(s.val[0]);
+            else
+                m_arr[py::ellipsis()] = shim::tup(s)[py::slice(0, channels(), 1)];
+        }
+        return *this;
+    }
+
+    void create(int rows_, int cols_, int type)
+    {
+        const int cn = CV_MAT_CN(type);
+        py::tuple shape = cn == 1 ? py::tuple(py::make_tuple(rows_, cols_)) : py::tuple(py::make_tuple(rows_, cols_, cn));
+        adopt(shim::np().attr("zeros")(shape, shim::dtype_name(CV_MAT_DEPTH(type))).cast<py::array>());
+    }
+    void adopt(py::array a)
+    {
+        if (a.ndim() != 2 && a.ndim() != 3)
+            throw std::invalid_argument("opencv shim: a Mat wraps a 2-D or 3-D array");
+        m_arr = std::move(a);
+        py::array v = array();
+        rows = int(v.shape(0));
+        cols = int(v.shape(1));
+        data = static_cast<uchar *>(v.mutable_data());
+    }
+    py::array array() const { return m_arr.is_none() ? py::array() : m_arr.cast<py::array>(); }
+    bool has_array() const { return !m_arr.is_none(); }
+
+    int channels() const { return has_array() && array().ndim() == 3 ? int(array().shape(2)) : 1; }
+    int depth() const { return has_array() ? shim::depth_of(array()) : CV_8U; }
+    int type() const { return CV_MAKETYPE(depth(), channels()); }
+    bool empty() const { return data == nullptr || total() == 0; }
+    std::size_t total() const { return std::size_t(rows) * std::size_t(cols); }
+    Size size() const { return Size{cols, rows}; }
+
+    Mat clone() const { return has_array() ? Mat{m_arr.attr("copy")().cast<py::array>()} : Mat{}; }
+    inline void convertTo(Mat &dst, int rtype) const;
+    void copyTo(const Mat &dst) const // destination of the same size (a region of interest): pixels are copied into it
+    {
+        if (!dst.has_array() || dst.rows != rows || dst.cols != cols)
+            throw std::invalid_argument("opencv shim: copyTo needs an allocated destination of the same size");
+        shim::np().attr("copyto")(dst.m_arr, m_arr);
+    }
+    Mat operator()(const Rect &r) const // a view of the same pixels
+    {
+        assert(r.x >= 0 && r.y >= 0 && r.x + r.width <= cols && r.y + r.height <= rows);
+        return Mat{m_arr[py::make_tuple(py::slice(r.y, r.y + r.height, 1), py::slice(r.x, r.x + r.width, 1))].cast<py::array>()};
+    }
+
+private:
+    py::object m_arr{py::none()};
+};
+
+namespace shim
+{
+// what an OutputArray does with a result: Mat::create() keeps a buffer of the right size and type and the function
+// writes into it; otherwise the destination header gets a new buffer
+inline void output(Mat &dst, py::object result)
+{
+    py::array r = result.cast<py::array>();
+    if (dst.has_array()) {
+        py::array d = dst.array();
+        if (d.is(r))
+            return;
+        bool same = d.ndim() == r.ndim() && d.dtype().is(r.dtype());
+        for (py::ssize_t k = 0; same && k < d.ndim(); ++k)
+            same = d.shape(k) == r.shape(k);
+        if (same) {
+            np().attr("copyto")(d, r);
+            return;
+        }
+    }
+    dst.adopt(std::move(r));
+}
+inline py::array contour_array(const std::vector<Point> &c)
+{
+    py::array_t<std::int32_t> a({py::ssize_t(c.size()), py::ssize_t(1), py::ssize_t(2)});
+    auto w = a.mutable_unchecked<3>();
+    for (std::size_t i = 0; i < c.size(); ++i) {
+        w(py::ssize_t(i), 0, 0) = c[i].x;
+        w(py::ssize_t(i), 0, 1) = c[i].y;
+    }
+    return std::move(a);
+}
+} // namespace shim
+
+inline MatExpr operator-(const Mat &a, const Mat &b) { return MatExpr{a, b}; }
+
+inline Mat &Mat::operator=(const MatExpr &e)
+{
+    shim::output(*this, shim::cv2().attr("subtract")(e.a.array(), e.b.array())); // dtype = -1: the operands' depth
+    return *this;
+}
+
+inline void Mat::convertTo(Mat &dst, int rtype) const
+{
+    const int d = rtype < 0 ? depth() : CV_MAT_DEPTH(rtype);
+    py::object out;
+    if (d == depth()) {
+        out = m_arr.attr("copy")();
+    } else if (d >= CV_32F) {
+        out = m_arr.attr("astype")(shim::dtype_name(d));
+    } else { // saturate_cast: round to nearest even, clamp to the target's range
+        py::module_ np = shim::np();
+        py::object info = np.attr("iinfo")(shim::dtype_name(d));
+        out = np.attr("clip")(np.attr("rint")(m_arr), info.attr("min"), info.attr("max")).attr("astype")(shim::dtype_name(d));
+    }
+    shim::output(dst, out);
+}
+
+inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, int type)
+{
+    py::tuple r = shim::cv2().attr("threshold")(src.array(), thresh, maxval, type);
+    shim::output(dst, r[1]);
+    return r[0].cast<double>();
+}
+
+inline void morphologyEx(const Mat &src, Mat &dst, int op, const Mat &kernel)
+{
+    // defaults of the C++ signature: anchor (-1,-1), 1 iteration, BORDER_CONSTANT with morphologyDefaultBorderValue()
+    shim::output(dst, shim::cv2().attr("morphologyEx")(src.array(), op, kernel.array()));
+}
+
+inline void findContours(const Mat &image, std::vector<std::vector<Point>> &contours, int mode, int method)
+{
+    py::tuple r = shim::cv2().attr("findContours")(image.array(), mode, method);
+    contours.clear();
+    for (py::handle h : r[0]) {
+        py::array_t<std::int32_t, py::array::c_style | py::array::forcecast> a = py::reinterpret_borrow<py::object>(h);
+        auto v = a.unchecked<3>();
+        std::vector<Point> c;
+        c.reserve(std::size_t(v.shape(0)));
+        for (py::ssize_t i = 0; i < v.shape(0); ++i)
+            c.emplace_back(v(i, 0, 0), v(i, 0, 1));
+        contours.push_back(std::move(c));
+    }
+}
+
+inline double contourArea(const std::vector<Point> &contour, bool oriented = false)
+{
+    return shim::cv2().attr("contourArea")(shim::contour_array(contour), oriented).cast<double>();
+}
+
+inline void drawContours(Mat &image, const std::vector<std::vector<Point>> &contours, int contourIdx, const Scalar &color,
+                         int thickness = 1, int lineType = LINE_8)
+{
+    if (contours.empty())
+        return; // C++ loops over nothing; the Python binding refuses an empty list
+    py::list cs;
+    for (const auto &c : contours)
+        cs.append(shim::contour_array(c));
+    shim::output(image, shim::cv2().attr("drawContours")(image.array(), cs, contourIdx, shim::tup(color), thickness, lineType));
+}
+
+inline int floodFill(Mat &image, Point seedPoint, Scalar newVal, Rect *rect = nullptr, Scalar loDiff = Scalar(),
+                     Scalar upDiff = Scalar(), int flags = 4)
+{
+    py::tuple r = shim::cv2().attr("floodFill")(image.array(), py::none(), shim::tup(seedPoint), shim::tup(newVal),
+                                                 shim::tup(loDiff), shim::tup(upDiff), flags);
+    shim::output(image, r[1]);
+    if (rect) {
+        py::tuple b = r[3];
+        *rect = Rect{b[0].cast<int>(), b[1].cast<int>(), b[2].cast<int>(), b[3].cast<int>()};
+    }
+    return r[0].cast<int>();
+}
+
+inline void extractChannel(const Mat &src, Mat &dst, int coi)
+{
+    shim::output(dst, shim::cv2().attr("extractChannel")(src.array(), coi));
+}
+
+inline void cvtColor(const Mat &src, Mat &dst, int code) { shim::output(dst, shim::cv2().attr("cvtColor")(src.array(), code)); }
+
+class VideoCapture
+{
+public:
+    VideoCapture() = default;
+    explicit VideoCapture(const std::string &filename) : m_cap{shim::cv2().attr("VideoCapture")(filename)} {}
+    bool isOpened() const { return !m_cap.is_none() && m_cap.attr("isOpened")().cast<bool>(); }
+    double get(int prop) const { return m_cap.is_none() ? 0.0 : m_cap.attr("get")(prop).cast<double>(); }
+    bool set(int prop, double value) { return !m_cap.is_none() && m_cap.attr("set")(prop, value).cast<bool>(); }
+    bool read(Mat &image)
+    {
+        image = Mat{}; // a failed read releases the destination
+        if (m_cap.is_none())
+            return false;
+        py::tuple r = m_cap.attr("read")();
+        if (!r[0].cast<bool>() || r[1].is_none())
+            return false;
+        image = Mat{r[1].cast<py::array>()};
+        return true;
+    }
+    VideoCapture &operator>>(Mat &image)
+    {
+        read(image);
+        return *this;
+    }
+
+private:
+    py::object m_cap{py::none()};
+};
+
+inline void bitwise_not(const Mat &src, Mat &dst) { shim::output(dst, shim::cv2().attr("bitwise_not")(src.array())); }
+
+inline void bitwise_or(const Mat &a, const Mat &b, Mat &dst)
+{
+    shim::output(dst, shim::cv2().attr("bitwise_or")(a.array(), b.array()));
+}
+} // namespace cv
+
+#endif

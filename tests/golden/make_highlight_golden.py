@@ -1,6 +1,8 @@
-"""Generates tests/golden/highlight_golden.json: SHA-256 of the cv2 restatement's output (oracle/highlight_oracle.py,
-cv2 4.13.0) on every adversarial case, 40 random cases and reduced synthetic-stream frames.  The reference has no
-fixtures for this path; these hashes pin the oracle (and through it the CUDA path) against drift.
+"""Generates tests/golden/highlight_golden.json: SHA-256 of the REFERENCE's output -- HighlightObjectsAlgo compiled
+unmodified from /root/reference against the cv2-forwarding shim (oracle/_ref/cvvp_highlight_ref, OpenCV 4.13.0 through
+the cv2 wheel) -- on every adversarial case, 40 random cases and reduced synthetic-stream frames.  The reference has no
+fixtures of its own for this path; these are outputs of the reference itself run here.  The cv2 restatement
+(oracle/highlight_oracle.py) must produce the same bytes, or the script stops.  Run where /root/reference is mounted:
 
     python tests/golden/make_highlight_golden.py
 """
@@ -14,12 +16,16 @@ sys.path.insert(0, str(REPO))
 sys.path.insert(0, str(REPO / "tests"))
 import hl_cases  # noqa: E402
 from oracle import highlight_oracle as ho  # noqa: E402
+from oracle import highlight_ref as href  # noqa: E402
 
 
 def entry(kind, name, frame, p, **extra):
-    out = ho.highlight_objects(frame.copy(), p)
+    out = href.highlight_objects(frame, p)
+    if not (out == ho.highlight_objects(frame.copy(), p)).all():
+        raise SystemExit(f"{name}: the restatement differs from the compiled reference")
     e = dict(kind=kind, name=name, shape=list(frame.shape), input_sha256=hashlib.sha256(frame.tobytes()).hexdigest(),
-             output_sha256=hashlib.sha256(out.tobytes()).hexdigest(), white_fraction=float((out == 255).mean()))
+             output_sha256=hashlib.sha256(out.tobytes()).hexdigest(), white_fraction=float((out == 255).mean()),
+             source="reference (oracle/_ref/cvvp_highlight_ref)")
     e.update(extra)
     return e
 

@@ -1,6 +1,8 @@
-"""CPU tests of the frame-source oracle (oracle/frames_oracle.py): the closed form of OpenCV's 8-bit RGB2GRAY against
-cv2 on ALL 2^24 colour triples, the crop-rectangle rule incl. its quirk, the committed golden hashes, and the ctypes
-view of struct cvvp_frame_format.  No GPU."""
+"""CPU tests of the frame-source oracle (oracle/frames_oracle.py): against the reference's own generator compiled
+unmodified (oracle/_ref/cvvp_frames_ref, see oracle/frames_ref.py) on lossless videos; the closed form of OpenCV's
+8-bit RGB2GRAY against cv2 on ALL 2^24 colour triples; the crop-rectangle rule incl. its quirk; the committed golden
+hashes (outputs of the reference where a video can carry the case); and the ctypes view of struct cvvp_frame_format.
+No GPU."""
 import ctypes
 import hashlib
 import json
@@ -11,8 +13,12 @@ import numpy as np
 import pytest
 
 import frame_cases
+import video_util
 from cvvidproc_b200 import _cabi
 from oracle import frames_oracle as fo
+from oracle import frames_ref as fref
+
+needs_ref = pytest.mark.skipif(not fref.available(), reason="oracle/_ref/cvvp_frames_ref was not built (no /root/reference)")
 
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "frames_golden.json").read_text())
 
@@ -68,6 +74,46 @@ def test_oracle_matches_golden_and_closed_form(case):
     else:
         want = c
     assert np.array_equal(res, want)
+
+
+VIDEO_CASES = [c for c in CASES if c[1].ndim == 4 and c[1].shape[3] == 3 and c[1].shape[1] % 2 == 0]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", VIDEO_CASES, ids=[c[0] for c in VIDEO_CASES])
+def test_restatement_matches_the_compiled_reference_generator(case, tmp_path):
+    """CvVidFramesGeneratorAlgo::GetTokenSet (cv_vid_frames_generator_algo.h:119-189) on a lossless video of the case's
+    frames == oracle.prepare_frames on the decoded frames, and == the golden hash"""
+    name, frames, crop, mode = case
+    vid = video_util.write_lossless(tmp_path / "v.avi", frames)
+    assert np.array_equal(video_util.read_all(vid), frames)
+    toks = fref.tokens(vid, 0, len(frames), crop, mode, frames_in_batch=3)
+    want = fo.prepare_frames(frames, crop, mode)
+    assert len(toks) == len(want)
+    got = np.stack(toks)
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+    g = next(e for e in GOLDEN if e["name"] == name)
+    assert g["source"].startswith("reference")
+    assert hashlib.sha256(got.tobytes()).hexdigest() == g["output_sha256"]
+
+
+@needs_ref
+def test_reference_generator_frame_range_and_batches(tmp_path):
+    """start_frame / last_frame (:97-104, :128-129), a last_frame beyond the stream, batches of any size, and the
+    generator's own assertion on a crop rectangle that leaves the frame (:92-93)"""
+    frames = np.random.default_rng(3).integers(0, 256, (11, 36, 50, 3), dtype=np.uint8)
+    vid = video_util.write_lossless(tmp_path / "v.avi", frames)
+    crop = (3, 2, 41, 30)
+    for start, last, batch in ((0, 11, 4), (2, 9, 3), (5, 6, 1), (4, 500, 5), (10, 11, 2)):
+        for mode in (fo.RGB2GRAY, fo.CHANNEL0, fo.AS_IS):
+            toks = fref.tokens(vid, start, last, crop, mode, frames_in_batch=batch)
+            want = fo.prepare_frames(frames[start:min(last, len(frames))], crop, mode)
+            assert len(toks) == len(want), (start, last, batch, mode)
+            assert np.array_equal(np.stack(toks), want), (start, last, batch, mode)
+    with pytest.raises(RuntimeError, match="crop_rectangle"):
+        fref.tokens(vid, 0, 11, (10, 0, 41, 36), fo.RGB2GRAY)
+    with pytest.raises(RuntimeError, match="start_frame"):
+        fref.tokens(vid, 11, 12, crop, fo.RGB2GRAY)
 
 
 def test_frame_format_struct_layout():
