@@ -99,14 +99,17 @@ __device__ __forceinline__ void red_release_shared_inc(uint32_t *p)
     asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
 }
 
-// A select warp hands plane slots back as soon as it has LOADED them -- and "loaded" must mean that the data sits in its
-// registers.  Issuing the loads is not enough: nothing orders a later store of another warp (a transposer woken by
-// the hand-back) behind loads that are still queued in this warp's path to shared memory, and on an SM whose
-// transposers already wait with the next tile in registers (the first tile of a CTA) the store did overtake them:
-// wrong medians in a few tiles per launch at 769 .. 896 frames, found by
-// tests/test_median_gpu.py::test_every_cta_walks_several_tiles_of_the_single_buffer_mode.  So every hand-back depends
-// on the loaded data: `fold` is the XOR of one word of every load, ANDed with a zero the compiler cannot see; the
-// instruction cannot issue before the registers are written, and its result (0) is added to the signalled address.
+// A select warp hands plane slots back as soon as it has LOADED them, a transposer warp refills its ring slot as soon
+// as it has read it.  The hand-backs are release operations behind a warp barrier, which by the memory model already
+// orders the warp's loads before them; the TMA refill, however, is an asynchronous-proxy write issued by one lane
+// after generic-proxy reads of all lanes, with only the warp barrier in between.  As a hardening that costs nothing
+// measurable (1080p x 1000 frames: 0.363 ms with and without), every hand-back also carries a DATA dependency on the
+// loads: `fold` is the XOR of one word of every load, ANDed with a zero the compiler cannot see; the instruction cannot
+// issue before the registers are written, and its result (0) is added to the signalled address / the refill's
+// destination.  (History: wrong medians once seen at 769 .. 896 frames came from a probe that launched this kernel on
+// the library's stream while torch was still generating the input on another; the kernel before this change passes
+// tests/test_median_gpu.py::test_every_cta_walks_several_tiles_of_the_single_buffer_mode and tools/stress_median.py
+// as well.)
 __device__ __forceinline__ uint32_t landed(uint32_t fold, uint32_t opaque_zero)
 {
     uint32_t z;
@@ -323,11 +326,9 @@ __global__ void __launch_bounds__((NSELW + kTrWarps) * 32, 1)
                 for (int i = 0; i < 32; ++i)
                     r[i] = src[i * 32];
             }
-            // Every lane has read the slot -- i.e. the data is in registers, not merely requested: the TMA unit writes
-            // through another path than the loads take, and a refill from L2 did overtake loads that were still queued
-            // behind the shared-memory traffic of a CTA's first tile (one stage of stale data in a few tiles per launch).
-            // The refill's destination therefore depends on the loaded words (landed()); the loads of a warp complete
-            // as a whole, so lane 0's dependency covers every lane.
+            // Every lane has read the slot.  The refill is an asynchronous-proxy write issued by lane 0; its destination
+            // carries a data dependency on the loaded words (landed()) so that it cannot be issued before the loads of
+            // the whole warp have completed (a warp's load instruction completes for all lanes at once).
             uint32_t fold = 0;
 #pragma unroll
             for (int i = 0; i < (kLdsm ? 8 : 32); ++i)

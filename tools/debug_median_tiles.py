@@ -17,6 +17,7 @@ def main():
             g = torch.Generator(device="cuda:0").manual_seed(n)
             stack = torch.randint(60, 200, (n, nelem), dtype=torch.uint8, device="cuda:0", generator=g)
             out = torch.empty(nelem, dtype=torch.uint8, device="cuda:0")
+            torch.cuda.synchronize()  # the library launches on its own stream: the generator must be done
             ctx.median_device(stack.data_ptr(), n, nelem, nelem, out.data_ptr())
             ctx.synchronize()
             want = torch.sort(stack, dim=0).values[n // 2]
