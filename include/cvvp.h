@@ -117,7 +117,8 @@ CVVP_API int cvvp_median_abort(cvvp_ctx *ctx);
 /* Device-resident form: d_frames is a DEVICE pointer to nframes frames, frame f at
  * d_frames + f*frame_stride (frame_stride % 16 == 0 and d_frames 16-byte aligned, the TMA
  * tensor-map constraints), d_out a DEVICE pointer to nelem bytes (4-byte aligned).  Runs on
- * `stream` (a cudaStream_t, NULL = the context's compute stream) and does not synchronize.
+ * `stream` (a cudaStream_t, NULL = the context's compute stream) and does not synchronize: frames
+ * written on ANOTHER stream must be complete (or ordered by an event) before the call.
  * Up to 1280 frames (1024 when frame_stride exceeds 2.5 MiB) the select happens on chip in one pass
  * over the frames; longer stacks (up to 16 x 65535 = 1048560 frames; more fails with
  * CVVP_ERR_UNSUPPORTED) are counted in chunks of at most 1024 frames: one pass of window counting around per-chunk pilot medians, and -- only if that leaves an
