@@ -172,6 +172,7 @@ public:
     int depth() const { return has_array() ? shim::depth_of(array()) : CV_8U; }
     int type() const { return CV_MAKETYPE(depth(), channels()); }
     bool empty() const { return data == nullptr || total() == 0; }
+    bool isContinuous() const { return !has_array() || array().attr("flags").attr("c_contiguous").cast<bool>(); }
     std::size_t total() const { return std::size_t(rows) * std::size_t(cols); }
     Size size() const { return Size{cols, rows}; }
 
