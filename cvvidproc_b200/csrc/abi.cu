@@ -4,6 +4,8 @@
 #include "context.hpp"
 #include "pool.hpp"
 
+#include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -57,6 +59,7 @@ void release_median(cvvp_ctx *ctx)
     MedianJob &m = ctx->med;
     m.active = false;
     m.count = 0;
+    m.folded = 0;
     // device buffers are kept for reuse by the next job of the same context
 }
 
@@ -112,6 +115,88 @@ int ensure_stack(cvvp_ctx *ctx, long long frames_needed)
     return CVVP_OK;
 }
 
+
+// CVVP_MEDIAN_RESIDENT_MAX=<frames> (development switch, tests): the resident stack holds at most that many frames, so
+// that small jobs exercise the constant-memory form
+long long resident_limit()
+{
+    const char *e = getenv("CVVP_MEDIAN_RESIDENT_MAX");
+    if (!e || !*e)
+        return LLONG_MAX;
+    const long long v = atoll(e);
+    return v >= 1 ? v : 1;
+}
+
+// The resident frames go into the value histograms (median_hist.cu) and the stack is free again.
+int spill_resident(cvvp_ctx *ctx)
+{
+    MedianJob &m = ctx->med;
+    if (m.count == 0)
+        return CVVP_OK;
+    const size_t bytes = median_hist_bytes(m.stride);
+    if (m.d_hist_bytes != bytes) {
+        if (m.d_hist)
+            cudaFree(m.d_hist);
+        m.d_hist = nullptr;
+        m.d_hist_bytes = 0;
+        if (cudaMalloc(&m.d_hist, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, CVVP_ERR_NOMEM,
+                        "median: the frame stack cannot grow beyond %lld frames and the %zu bytes of value histograms that "
+                        "would take their place do not fit the device either",
+                        m.capacity, bytes);
+        }
+        m.d_hist_bytes = bytes;
+    }
+    if (m.folded == 0)
+        CVVP_CUDA_OK(ctx, cudaMemsetAsync(m.d_hist, 0, bytes, ctx->compute));
+    // uploads still in flight on the copy stream (and preparation kernels on the compute stream) come first
+    CVVP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy));
+    CVVP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->compute, ctx->ev_copy, 0));
+    const int rc = median_hist_fold(ctx, m.d_stack, m.count, m.stride, m.d_hist, ctx->compute);
+    if (rc != CVVP_OK)
+        return rc;
+    // the stack is rewritten by the copy stream next
+    CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->compute));
+    m.folded += m.count;
+    m.count = 0;
+    return CVVP_OK;
+}
+
+// Room for the next frames of a push: *take <- how many of `want` frames fit behind the resident ones right now
+// (at least one).  The stack grows as ensure_stack() allows; when it cannot, the resident frames are folded into the
+// value histograms and the stack is reused -- from there on the job's memory no longer depends on the frame count,
+// like the reference's (histogram_median_algo.h:123-126).
+int reserve_frames(cvvp_ctx *ctx, long long want, long long *take)
+{
+    MedianJob &m = ctx->med;
+    const long long limit = resident_limit();
+    long long need = m.count + want;
+    if (need > limit)
+        need = limit;
+    int rc = ensure_stack(ctx, need);
+    if (rc == CVVP_ERR_NOMEM && m.capacity == 0) {
+        // not even the first allocation fits: take half of what is free beside the histograms
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        cudaGetLastError();
+        const size_t hist = median_hist_bytes(m.stride);
+        const long long frames = free_b > hist ? (long long)((free_b - hist) / 2 / m.stride) : 0;
+        if (frames >= 16)
+            rc = ensure_stack(ctx, frames);
+    }
+    if (rc != CVVP_OK && !(rc == CVVP_ERR_NOMEM && m.capacity > 0))
+        return rc;
+    long long room = (m.capacity < limit ? m.capacity : limit) - m.count;
+    if (room <= 0) {
+        if ((rc = spill_resident(ctx)) != CVVP_OK)
+            return rc;
+        room = m.capacity < limit ? m.capacity : limit;
+    }
+    *take = want < room ? want : room;
+    return CVVP_OK;
+}
+
 int ensure_staging(cvvp_ctx *ctx)
 {
     if (!ctx->staging.empty())
@@ -141,6 +226,76 @@ bool is_pinned(const void *p)
 } // namespace cvvp
 
 using namespace cvvp;
+
+namespace cvvp
+{
+namespace
+{
+// n frames behind the resident ones (room has been reserved)
+int push_piece(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride)
+{
+    MedianJob &m = ctx->med;
+    int rc = CVVP_OK;
+    uint8_t *dst = m.d_stack + size_t(m.count) * m.stride;
+    if (is_pinned(frames)) {
+        // DMA straight from the caller's pinned buffer
+        if (frame_stride == m.stride && m.stride == m.nelem) {
+            CVVP_CUDA_OK(ctx, cudaMemcpyAsync(dst, frames, size_t(n) * m.stride, cudaMemcpyHostToDevice, ctx->copy));
+        } else {
+            CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst, m.stride, frames, frame_stride, m.nelem, size_t(n),
+                                                cudaMemcpyHostToDevice, ctx->copy));
+        }
+    } else {
+        // pageable source: stage through the pinned ring, copies overlap the next memcpy
+        rc = ensure_staging(ctx);
+        if (rc != CVVP_OK)
+            return rc;
+        const long long per_buf = (long long)(kStagingBytes / m.nelem);
+        auto next_buf = [&]() -> StagingBuf * {
+            StagingBuf &b = ctx->staging[ctx->staging_next];
+            ctx->staging_next = (ctx->staging_next + 1) % ctx->staging.size();
+            if (b.in_flight) {
+                if (cudaEventSynchronize(b.done) != cudaSuccess)
+                    return nullptr;
+                b.in_flight = false;
+            }
+            return &b;
+        };
+        if (per_buf == 0) {
+            // a single frame is larger than a staging buffer (an 8K frame, a 4K colour frame): pieces of the frame
+            for (long long i = 0; i < n; ++i) {
+                for (size_t off = 0; off < m.nelem; off += kStagingBytes) {
+                    const size_t piece = m.nelem - off < kStagingBytes ? m.nelem - off : kStagingBytes;
+                    StagingBuf *b = next_buf();
+                    if (!b)
+                        return fail(ctx, CVVP_ERR_CUDA, "median: waiting for a staging buffer failed");
+                    std::memcpy(b->host, frames + size_t(i) * frame_stride + off, piece);
+                    CVVP_CUDA_OK(ctx, cudaMemcpyAsync(dst + size_t(i) * m.stride + off, b->host, piece, cudaMemcpyHostToDevice, ctx->copy));
+                    CVVP_CUDA_OK(ctx, cudaEventRecord(b->done, ctx->copy));
+                    b->in_flight = true;
+                }
+            }
+        }
+        for (long long done = 0; per_buf > 0 && done < n;) {
+            const long long chunk = (n - done) < per_buf ? (n - done) : per_buf;
+            StagingBuf *bp = next_buf();
+            if (!bp)
+                return fail(ctx, CVVP_ERR_CUDA, "median: waiting for a staging buffer failed");
+            StagingBuf &b = *bp;
+            for (long long i = 0; i < chunk; ++i)
+                std::memcpy(b.host + size_t(i) * m.nelem, frames + size_t(done + i) * frame_stride, m.nelem);
+            CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst + size_t(done) * m.stride, m.stride, b.host, m.nelem, m.nelem,
+                                                size_t(chunk), cudaMemcpyHostToDevice, ctx->copy));
+            CVVP_CUDA_OK(ctx, cudaEventRecord(b.done, ctx->copy));
+            b.in_flight = true;
+            done += chunk;
+        }
+    }
+    m.count += n;
+    return CVVP_OK;
+}
+} // namespace
+} // namespace cvvp
 
 extern "C" {
 
@@ -240,6 +395,8 @@ void cvvp_ctx_destroy(cvvp_ctx *ctx)
     median_shard_release(ctx);
     if (ctx->med.d_stack)
         cudaFree(ctx->med.d_stack);
+    if (ctx->med.d_hist)
+        cudaFree(ctx->med.d_hist);
     if (ctx->med.d_out)
         cudaFree(ctx->med.d_out);
     if (ctx->ev_start)
@@ -358,10 +515,16 @@ int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint)
         m.d_stack = nullptr;
         m.d_stack_bytes = 0;
     }
+    if (m.d_hist && m.d_hist_bytes != median_hist_bytes(stride)) {
+        cudaFree(m.d_hist);
+        m.d_hist = nullptr;
+        m.d_hist_bytes = 0;
+    }
     m.capacity = 0;
     m.nelem = nelem;
     m.stride = stride;
     m.count = 0;
+    m.folded = 0;
     if (m.d_out_bytes < stride) {
         if (m.d_out)
             cudaFree(m.d_out);
@@ -375,12 +538,15 @@ int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint)
     }
     if (m.d_stack_bytes >= stride)
         m.capacity = (long long)(m.d_stack_bytes / stride);
-    const int rc = ensure_stack(ctx, nframes_hint > 0 ? nframes_hint : 64);
+    // a hint that does not fit leaves a smaller stack: the job then folds frames into value histograms as it goes
+    long long room = 0;
+    const int rc = reserve_frames(ctx, nframes_hint > 0 ? nframes_hint : 64, &room);
     if (rc != CVVP_OK)
         return rc;
     m.active = true;
     return CVVP_OK;
 }
+
 
 int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride)
 {
@@ -394,71 +560,22 @@ int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t f
     if (!frames || n < 0 || frame_stride < m.nelem)
         return fail(ctx, CVVP_ERR_INVALID, "median: bad push arguments");
     DeviceGuard guard(ctx->device);
-    int rc = ensure_stack(ctx, m.count + n);
-    if (rc != CVVP_OK)
-        return rc;
-    uint8_t *dst = m.d_stack + size_t(m.count) * m.stride;
-    if (is_pinned(frames)) {
-        // DMA straight from the caller's pinned buffer
-        if (frame_stride == m.stride && m.stride == m.nelem) {
-            CVVP_CUDA_OK(ctx, cudaMemcpyAsync(dst, frames, size_t(n) * m.stride, cudaMemcpyHostToDevice, ctx->copy));
-        } else {
-            CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst, m.stride, frames, frame_stride, m.nelem, size_t(n),
-                                                cudaMemcpyHostToDevice, ctx->copy));
-        }
-    } else {
-        // pageable source: stage through the pinned ring, copies overlap the next memcpy
-        rc = ensure_staging(ctx);
+    while (n > 0) {
+        long long take = 0;
+        int rc = reserve_frames(ctx, n, &take);
         if (rc != CVVP_OK)
             return rc;
-        const long long per_buf = (long long)(kStagingBytes / m.nelem);
-        auto next_buf = [&]() -> StagingBuf * {
-            StagingBuf &b = ctx->staging[ctx->staging_next];
-            ctx->staging_next = (ctx->staging_next + 1) % ctx->staging.size();
-            if (b.in_flight) {
-                if (cudaEventSynchronize(b.done) != cudaSuccess)
-                    return nullptr;
-                b.in_flight = false;
-            }
-            return &b;
-        };
-        if (per_buf == 0) {
-            // a single frame is larger than a staging buffer (an 8K frame, a 4K colour frame): pieces of the frame
-            for (long long i = 0; i < n; ++i) {
-                for (size_t off = 0; off < m.nelem; off += kStagingBytes) {
-                    const size_t piece = m.nelem - off < kStagingBytes ? m.nelem - off : kStagingBytes;
-                    StagingBuf *b = next_buf();
-                    if (!b)
-                        return fail(ctx, CVVP_ERR_CUDA, "median: waiting for a staging buffer failed");
-                    std::memcpy(b->host, frames + size_t(i) * frame_stride + off, piece);
-                    CVVP_CUDA_OK(ctx, cudaMemcpyAsync(dst + size_t(i) * m.stride + off, b->host, piece, cudaMemcpyHostToDevice, ctx->copy));
-                    CVVP_CUDA_OK(ctx, cudaEventRecord(b->done, ctx->copy));
-                    b->in_flight = true;
-                }
-            }
-        }
-        for (long long done = 0; per_buf > 0 && done < n;) {
-            const long long chunk = (n - done) < per_buf ? (n - done) : per_buf;
-            StagingBuf *bp = next_buf();
-            if (!bp)
-                return fail(ctx, CVVP_ERR_CUDA, "median: waiting for a staging buffer failed");
-            StagingBuf &b = *bp;
-            for (long long i = 0; i < chunk; ++i)
-                std::memcpy(b.host + size_t(i) * m.nelem, frames + size_t(done + i) * frame_stride, m.nelem);
-            CVVP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst + size_t(done) * m.stride, m.stride, b.host, m.nelem, m.nelem,
-                                                size_t(chunk), cudaMemcpyHostToDevice, ctx->copy));
-            CVVP_CUDA_OK(ctx, cudaEventRecord(b.done, ctx->copy));
-            b.in_flight = true;
-            done += chunk;
-        }
+        if ((rc = push_piece(ctx, frames, take, frame_stride)) != CVVP_OK)
+            return rc;
+        frames += size_t(take) * frame_stride;
+        n -= take;
     }
-    m.count += n;
     return CVVP_OK;
 }
 
 long long cvvp_median_count(const cvvp_ctx *ctx)
 {
-    return ctx ? ctx->med.count : 0;
+    return ctx ? ctx->med.count + ctx->med.folded : 0;
 }
 
 int cvvp_median_stack_device(cvvp_ctx *ctx, const uint8_t **d_frames, size_t *frame_stride, long long *nframes)
@@ -468,6 +585,9 @@ int cvvp_median_stack_device(cvvp_ctx *ctx, const uint8_t **d_frames, size_t *fr
     MedianJob &m = ctx->med;
     if (!m.active)
         return fail(ctx, CVVP_ERR_STATE, "median: no job is running");
+    if (m.folded > 0)
+        return fail(ctx, CVVP_ERR_STATE, "median: %lld frames of this job were folded into value histograms (the stack did "
+                                         "not fit the device); the frame stack is no longer complete", m.folded);
     DeviceGuard guard(ctx->device);
     // everything pushed so far is ordered before whatever the caller queues on the compute stream next
     CVVP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy));
@@ -489,7 +609,7 @@ int cvvp_median_finish(cvvp_ctx *ctx, uint8_t *out)
         release_median(ctx);
         return fail(ctx, CVVP_ERR_INVALID, "median: out is NULL");
     }
-    if (m.count == 0) {
+    if (m.count + m.folded == 0) {
         // the reference publishes an empty Mat when no token was inserted; report it as a state error
         release_median(ctx);
         return fail(ctx, CVVP_ERR_STATE, "median: no frames were pushed");
@@ -504,7 +624,14 @@ int cvvp_median_finish(cvvp_ctx *ctx, uint8_t *out)
             rc = fail(ctx, CVVP_ERR_CUDA, "median: stream setup failed: %s", cudaGetErrorString(e));
             break;
         }
-        rc = median_launch(ctx, m.d_stack, m.count, m.nelem, m.stride, m.d_out, ctx->compute);
+        if (m.folded > 0) {
+            // constant-memory form: the rest of the stack joins the histograms, the median is read off them
+            if ((rc = spill_resident(ctx)) != CVVP_OK)
+                break;
+            rc = median_hist_select(ctx, m.d_hist, m.stride, m.nelem, m.folded, m.d_out, ctx->compute);
+        } else {
+            rc = median_launch(ctx, m.d_stack, m.count, m.nelem, m.stride, m.d_out, ctx->compute);
+        }
         if (rc != CVVP_OK)
             break;
         if ((e = cudaEventRecord(ctx->ev_stop, ctx->compute)) != cudaSuccess ||
@@ -540,14 +667,19 @@ int cvvp_median_push_source(cvvp_ctx *ctx, const uint8_t *frames, long long n, s
     if (!frames || n < 0 || frame_stride < src_frame)
         return fail(ctx, CVVP_ERR_INVALID, "median: bad push arguments");
     DeviceGuard guard(ctx->device);
-    if ((rc = ensure_stack(ctx, m.count + n)) != CVVP_OK)
-        return rc;
-    if ((rc = frames_upload_prepare(ctx, frames, n, frame_stride, *fmt, m.d_stack + size_t(m.count) * m.stride, m.stride)) != CVVP_OK)
-        return rc;
+    while (n > 0) {
+        long long take = 0;
+        if ((rc = reserve_frames(ctx, n, &take)) != CVVP_OK)
+            return rc;
+        if ((rc = frames_upload_prepare(ctx, frames, take, frame_stride, *fmt, m.d_stack + size_t(m.count) * m.stride, m.stride)) != CVVP_OK)
+            return rc;
+        m.count += take;
+        frames += size_t(take) * frame_stride;
+        n -= take;
+    }
     // the caller may reuse `frames` on return: wait for the uploads (not for the kernels) -- a pageable source is
     // already staged at this point, a pinned one is still being read by the copy engine
     CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy));
-    m.count += n;
     return CVVP_OK;
 }
 

@@ -35,6 +35,10 @@ struct MedianJob {
     uint8_t *d_out{nullptr};
     size_t d_out_bytes{0};
     size_t d_stack_bytes{0};
+    // constant-memory form (median_hist.cu): frames folded into value histograms when the stack cannot grow
+    uint32_t *d_hist{nullptr}; // [256][stride] counts, or nullptr
+    size_t d_hist_bytes{0};
+    long long folded{0};       // frames that live in d_hist only (count = the frames resident in d_stack)
 };
 struct HighlightState; // highlight_state.hpp
 
@@ -141,6 +145,12 @@ int median_launch_mode(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes
 long long median_max_frames();
 int median_pipe_launch(cvvp_ctx *ctx, const CUtensorMap &tmap, int log2s, uint8_t *d_out, uint32_t nelem, uint32_t nframes,
                        uint32_t nst, int mode, const ShardPush &push, cudaStream_t stream);
+// median_hist.cu
+size_t median_hist_bytes(size_t frame_stride);
+int median_hist_fold(cvvp_ctx *ctx, const uint8_t *d_stack, long long nframes, size_t frame_stride, uint32_t *d_hist,
+                     cudaStream_t stream);
+int median_hist_select(cvvp_ctx *ctx, const uint32_t *d_hist, size_t frame_stride, size_t nelem, long long total, uint8_t *d_out,
+                       cudaStream_t stream);
 // median_shard.cu
 void median_shard_release(cvvp_ctx *ctx);
 int median_long_stack(cvvp_ctx *ctx, const uint8_t *d_frames, long long nframes, size_t nelem, size_t frame_stride,

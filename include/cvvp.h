@@ -91,9 +91,12 @@ CVVP_API int cvvp_ctx_copy_to_host(cvvp_ctx *ctx, void *host_dst, const void *de
 
 /* Start a median job on frames of `nelem` bytes.  nframes_hint > 0 sizes the device stack for exactly that many
  * frames (rounded up to 16; it grows by half if more are pushed, and the old and new stacks coexist while it does).
- * The job keeps every pushed frame resident in device memory -- frames x round_up(nelem, 128) bytes must fit the
- * device, unlike the reference's histograms, whose size is independent of the frame count
- * (histogram_median_algo.h:123-126); a stack that does not fit fails with CVVP_ERR_NOMEM. */
+ * While they fit, the job keeps every pushed frame resident in device memory (frames x round_up(nelem, 128) bytes) and
+ * selects the median on chip.  When the stack cannot be allocated or grown any further, the resident frames are folded
+ * into per-element value histograms (256 x round_up(nelem, 128) x 4 bytes, 32-bit counts) and the stack is reused for
+ * the frames that follow: from there on the job's memory is independent of the frame count, like the reference's
+ * histograms (histogram_median_algo.h:123-126), and the result is the same upper median of ALL frames.
+ * CVVP_ERR_NOMEM only when neither a stack of 16 frames nor the histograms fit. */
 CVVP_API int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint);
 /* Append n frames from HOST memory; frame i starts at frames + i*frame_stride and holds nelem
  * contiguous bytes.  The copy is asynchronous when `frames` is pinned (cvvp_host_alloc or

@@ -7,6 +7,8 @@ UPPER median rule of histogram_median_algo.h:160-166), ragged widths, every tile
 import numpy as np
 import pytest
 
+from cvvidproc_b200 import _cabi
+
 pytestmark = pytest.mark.gpu
 
 
@@ -257,3 +259,67 @@ def test_cuda_reproduces_reference_golden(gpu_ctx):
         frames = mg.case_input(case)
         got = gpu_ctx.median(frames)
         assert hashlib.sha256(got.tobytes()).hexdigest() == case["output_sha256"], case["name"]
+
+
+# ---- constant-memory form: a stack that cannot grow folds into value histograms (csrc/median_hist.cu) -------------------
+@pytest.mark.parametrize("n,cap,chunk", [(1000, 256, 100), (300, 16, 7), (65, 64, 64), (64, 64, 10), (2100, 1000, 512),
+                                         (5000, 333, 1024)])
+def test_stack_that_cannot_grow_folds_into_value_histograms(gpu_ctx, oracle_median, monkeypatch, n, cap, chunk):
+    """CVVP_MEDIAN_RESIDENT_MAX caps the resident stack the way a full device does: the job folds the resident frames
+    into per-element value histograms and goes on -- memory independent of the frame count, like the reference's
+    HistogramMedianAlgo (histogram_median_algo.h:116-193) -- and the result stays the upper median of ALL frames"""
+    monkeypatch.setenv("CVVP_MEDIAN_RESIDENT_MAX", str(cap))
+    rng = np.random.default_rng(n * 7 + cap)
+    frames = rng.integers(80, 150, (n, 9, 131), dtype=np.uint8)
+    frames[:, 0, :5] = 0                       # constant columns at both ends of the value range
+    frames[:, 0, 5:9] = 255
+    frames[: n // 2, 1, :6] = 9                # exact split: the upper median
+    frames[n // 2 :, 1, :6] = 250
+    frames[:, 2, :] = rng.integers(0, 256, (n, 131), dtype=np.uint8)   # the whole value range
+    nelem = 9 * 131
+    gpu_ctx.median_begin(nelem, n)
+    for i in range(0, n, chunk):
+        gpu_ctx.median_push(frames[i:i + chunk])
+        assert gpu_ctx.median_count() == min(i + chunk, n)
+    if n > cap:
+        with pytest.raises(_cabi.CvvpError) as ei:   # the stack no longer holds every frame
+            gpu_ctx.median_stack_device()
+        assert ei.value.code == -4 and "folded" in str(ei.value)
+    got = gpu_ctx.median_finish(nelem=nelem).reshape(9, 131)
+    want = oracle_median(frames)
+    assert np.array_equal(got, want)
+    assert (got[1, :6] == 250).all()
+    # the context goes back to resident jobs afterwards
+    monkeypatch.delenv("CVVP_MEDIAN_RESIDENT_MAX")
+    assert np.array_equal(gpu_ctx.median(frames[:100]), oracle_median(frames[:100]))
+
+
+def test_folding_with_device_prepared_colour_frames_and_pinned_sources(gpu_ctx, oracle_median, monkeypatch):
+    """the same through cvvp_median_push_source (decoded colour frames, cropped and converted on the device) and from
+    page-locked host memory"""
+    from oracle import frames_oracle as fo
+
+    monkeypatch.setenv("CVVP_MEDIAN_RESIDENT_MAX", "40")
+    rng = np.random.default_rng(77)
+    n, h, w = 203, 50, 70
+    base = rng.integers(0, 256, (h, w, 3), dtype=np.int16)
+    frames = np.clip(base[None] + rng.integers(-25, 26, (n, h, w, 3)), 0, 255).astype(np.uint8)
+    crop = (3, 4, 61, 40)
+    for mode in (fo.RGB2GRAY, fo.AS_IS):
+        fmt = _cabi.FrameFormat.of((h, w, 3), mode, crop)
+        prepared = fo.prepare_frames(frames, crop, mode)
+        nelem = int(np.prod(prepared.shape[1:]))
+        gpu_ctx.median_begin(nelem, n)
+        for i in range(0, n, 33):
+            gpu_ctx.median_push_source(frames[i:i + 33], fmt)
+        assert gpu_ctx.median_count() == n
+        got = gpu_ctx.median_finish(nelem=nelem).reshape(prepared.shape[1:])
+        assert np.array_equal(got, oracle_median(prepared)), mode
+    pinned = _cabi.PinnedBuffer(n * h * w * 3)
+    host = pinned.array[: n * h * w * 3].reshape(n, h, w, 3)
+    host[:] = frames
+    gpu_ctx.median_begin(h * w * 3, n)
+    gpu_ctx.median_push(host[:150])
+    gpu_ctx.median_push(host[150:])
+    got = gpu_ctx.median_finish(nelem=h * w * 3).reshape(h, w, 3)
+    assert np.array_equal(got, oracle_median(frames))
