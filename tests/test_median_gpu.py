@@ -323,3 +323,19 @@ def test_folding_with_device_prepared_colour_frames_and_pinned_sources(gpu_ctx, 
     gpu_ctx.median_push(host[150:])
     got = gpu_ctx.median_finish(nelem=h * w * 3).reshape(h, w, 3)
     assert np.array_equal(got, oracle_median(frames))
+
+
+def test_a_hint_beyond_the_device_leaves_a_smaller_stack(oracle_median):
+    """GetVideoBackground announces frames_to_analyze; a video longer than the device is wide (200 000 frames of 1080p:
+    415 GB) must not fail at cvvp_median_begin: the job takes a stack that fits and folds as it goes"""
+    from cvvidproc_b200 import synth
+
+    p = synth.CONFIG_PARAMS["C2"]
+    frames = synth.synth_frames(0, 40, p["width"], p["height"], p["seed"], p["ndisks"])
+    with _cabi.Context(0) as ctx:
+        ctx.median_begin(p["width"] * p["height"], 200_000)
+        ctx.median_push(frames[:25])
+        ctx.median_push(frames[25:])
+        assert ctx.median_count() == 40
+        got = ctx.median_finish(nelem=p["width"] * p["height"]).reshape(p["height"], p["width"])
+    assert np.array_equal(got, oracle_median(frames, nthreads=8))
