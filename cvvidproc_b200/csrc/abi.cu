@@ -63,12 +63,13 @@ void release_median(cvvp_ctx *ctx)
     // device buffers are kept for reuse by the next job of the same context
 }
 
-// Device frame stack of the streaming median job.  The job keeps EVERY pushed frame resident (the select needs all of
-// them at once), so a job is limited to  frames x round_up(nelem, 128)  bytes of free HBM -- unlike the reference's
-// histograms, whose size does not depend on the frame count (histogram_median_algo.h:123-126).  To make that limit
-// the real one, the stack is sized EXACTLY to what is asked for (the hint of cvvp_median_begin, rounded up to a
-// granule of 16 frames) and grows by half only when more frames arrive than were announced; while it grows the old
-// and the new stack coexist, which an exact hint avoids altogether.
+// Device frame stack of the streaming median job.  While they fit, the job keeps EVERY pushed frame resident (the
+// on-chip select needs all of them at once): frames x round_up(nelem, 128) bytes.  The stack is sized EXACTLY to what
+// is asked for (the hint of cvvp_median_begin, rounded up to a granule of 16 frames) and grows by half only when more
+// frames arrive than were announced; while it grows the old and the new stack coexist, which an exact hint avoids
+// altogether.  CVVP_ERR_NOMEM from here is not the end of the job: reserve_frames() below then folds the resident
+// frames into value histograms and reuses the stack (the reference's histograms do not depend on the frame count
+// either, histogram_median_algo.h:123-126).
 int ensure_stack(cvvp_ctx *ctx, long long frames_needed)
 {
     MedianJob &m = ctx->med;
@@ -114,7 +115,6 @@ int ensure_stack(cvvp_ctx *ctx, long long frames_needed)
     m.capacity = (long long)(m.d_stack_bytes / m.stride);
     return CVVP_OK;
 }
-
 
 // CVVP_MEDIAN_RESIDENT_MAX=<frames> (development switch, tests): the resident stack holds at most that many frames, so
 // that small jobs exercise the constant-memory form
@@ -546,7 +546,6 @@ int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint)
     m.active = true;
     return CVVP_OK;
 }
-
 
 int cvvp_median_push(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_stride)
 {
