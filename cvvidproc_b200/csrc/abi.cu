@@ -60,6 +60,9 @@ void release_median(cvvp_ctx *ctx)
     m.active = false;
     m.count = 0;
     m.folded = 0;
+    m.split = false;
+    m.half = 0;
+    m.base = 0;
     // device buffers are kept for reuse by the next job of the same context
 }
 
@@ -127,7 +130,9 @@ long long resident_limit()
     return v >= 1 ? v : 1;
 }
 
-// The resident frames go into the value histograms (median_hist.cu) and the stack is free again.
+// The frames of the region being filled go into the value histograms (median_hist.cu), asynchronously, and the job
+// moves on to the other half of the stack: uploads into one half overlap the fold of the other.  The first fold reads
+// the whole stack (it was filled as one region); the halves start behind it.
 int spill_resident(cvvp_ctx *ctx)
 {
     MedianJob &m = ctx->med;
@@ -148,18 +153,35 @@ int spill_resident(cvvp_ctx *ctx)
         }
         m.d_hist_bytes = bytes;
     }
+    for (auto &ev : m.ev_fold)
+        if (!ev)
+            CVVP_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (m.folded == 0)
         CVVP_CUDA_OK(ctx, cudaMemsetAsync(m.d_hist, 0, bytes, ctx->compute));
-    // uploads still in flight on the copy stream (and preparation kernels on the compute stream) come first
+    // uploads still in flight on the copy stream come first (preparation kernels run on the compute stream itself)
     CVVP_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy));
     CVVP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->compute, ctx->ev_copy, 0));
-    const int rc = median_hist_fold(ctx, m.d_stack, m.count, m.stride, m.d_hist, ctx->compute);
+    const int rc = median_hist_fold(ctx, m.d_stack + size_t(m.base) * m.stride, m.count, m.stride, m.d_hist, ctx->compute);
     if (rc != CVVP_OK)
         return rc;
-    // the stack is rewritten by the copy stream next
-    CVVP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->compute));
+    if (m.split) {
+        CVVP_CUDA_OK(ctx, cudaEventRecord(m.ev_fold[m.half], ctx->compute));
+        m.half ^= 1;
+    } else {
+        // the whole stack was one region: both halves are free once this fold is done
+        CVVP_CUDA_OK(ctx, cudaEventRecord(m.ev_fold[0], ctx->compute));
+        CVVP_CUDA_OK(ctx, cudaEventRecord(m.ev_fold[1], ctx->compute));
+        const long long limit = resident_limit();
+        const long long eff = m.capacity < limit ? m.capacity : limit;
+        m.split = eff >= 2;
+        m.half_cap = m.split ? eff / 2 : eff;
+        m.half = 0;
+    }
+    m.base = m.split ? (long long)m.half * m.half_cap : 0;
     m.folded += m.count;
     m.count = 0;
+    // the copy stream may write the next region only after the fold that last read it
+    CVVP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy, m.ev_fold[m.half], 0));
     return CVVP_OK;
 }
 
@@ -170,11 +192,20 @@ int spill_resident(cvvp_ctx *ctx)
 int reserve_frames(cvvp_ctx *ctx, long long want, long long *take)
 {
     MedianJob &m = ctx->med;
+    int rc = CVVP_OK;
+    if (m.folded > 0) {
+        // constant-memory form: the region being filled is a half of the stack (or all of a one-frame stack)
+        if (m.half_cap - m.count <= 0 && (rc = spill_resident(ctx)) != CVVP_OK)
+            return rc;
+        const long long room = m.half_cap - m.count;
+        *take = want < room ? want : room;
+        return CVVP_OK;
+    }
     const long long limit = resident_limit();
     long long need = m.count + want;
     if (need > limit)
         need = limit;
-    int rc = ensure_stack(ctx, need);
+    rc = ensure_stack(ctx, need);
     if (rc == CVVP_ERR_NOMEM && m.capacity == 0) {
         // not even the first allocation fits: take half of what is free beside the histograms
         size_t free_b = 0, total_b = 0;
@@ -191,7 +222,7 @@ int reserve_frames(cvvp_ctx *ctx, long long want, long long *take)
     if (room <= 0) {
         if ((rc = spill_resident(ctx)) != CVVP_OK)
             return rc;
-        room = m.capacity < limit ? m.capacity : limit;
+        room = m.half_cap;
     }
     *take = want < room ? want : room;
     return CVVP_OK;
@@ -236,7 +267,7 @@ int push_piece(cvvp_ctx *ctx, const uint8_t *frames, long long n, size_t frame_s
 {
     MedianJob &m = ctx->med;
     int rc = CVVP_OK;
-    uint8_t *dst = m.d_stack + size_t(m.count) * m.stride;
+    uint8_t *dst = m.d_stack + size_t(m.base + m.count) * m.stride;
     if (is_pinned(frames)) {
         // DMA straight from the caller's pinned buffer
         if (frame_stride == m.stride && m.stride == m.nelem) {
@@ -397,6 +428,9 @@ void cvvp_ctx_destroy(cvvp_ctx *ctx)
         cudaFree(ctx->med.d_stack);
     if (ctx->med.d_hist)
         cudaFree(ctx->med.d_hist);
+    for (auto &ev : ctx->med.ev_fold)
+        if (ev)
+            cudaEventDestroy(ev);
     if (ctx->med.d_out)
         cudaFree(ctx->med.d_out);
     if (ctx->ev_start)
@@ -525,6 +559,9 @@ int cvvp_median_begin(cvvp_ctx *ctx, size_t nelem, long long nframes_hint)
     m.stride = stride;
     m.count = 0;
     m.folded = 0;
+    m.split = false;
+    m.half = 0;
+    m.base = 0;
     if (m.d_out_bytes < stride) {
         if (m.d_out)
             cudaFree(m.d_out);
@@ -670,7 +707,7 @@ int cvvp_median_push_source(cvvp_ctx *ctx, const uint8_t *frames, long long n, s
         long long take = 0;
         if ((rc = reserve_frames(ctx, n, &take)) != CVVP_OK)
             return rc;
-        if ((rc = frames_upload_prepare(ctx, frames, take, frame_stride, *fmt, m.d_stack + size_t(m.count) * m.stride, m.stride)) != CVVP_OK)
+        if ((rc = frames_upload_prepare(ctx, frames, take, frame_stride, *fmt, m.d_stack + size_t(m.base + m.count) * m.stride, m.stride)) != CVVP_OK)
             return rc;
         m.count += take;
         frames += size_t(take) * frame_stride;

@@ -39,6 +39,12 @@ struct MedianJob {
     uint32_t *d_hist{nullptr}; // [256][stride] counts, or nullptr
     size_t d_hist_bytes{0};
     long long folded{0};       // frames that live in d_hist only (count = the frames resident in d_stack)
+    // after the first fold the stack is used as two halves: one is filled while the other is being folded
+    bool split{false};
+    int half{0};
+    long long half_cap{0};     // frames per half
+    long long base{0};         // first frame slot of the region being filled (0 or half_cap)
+    cudaEvent_t ev_fold[2]{nullptr, nullptr}; // the fold that last read half h is complete
 };
 struct HighlightState; // highlight_state.hpp
 

@@ -13,8 +13,8 @@
 //   fold   : one thread per four elements walks the resident frames (a 32-bit load per frame, coalesced over the
 //            warp) and bumps hist[v][e] -- plain read-modify-write, the thread owns its elements.  A run of equal
 //            values costs one update.  Neighbouring elements of a video background have neighbouring values, so the
-//            updates of a warp land in few planes.  HBM/L2-bound integer work; it runs once per spill, at a rate of
-//            the same order as the PCIe link that feeds the job.
+//            updates of a warp land in few planes.  HBM/L2-bound integer work at about three times the rate of the
+//            PCIe link that feeds the job; abi.cu overlaps it with the uploads (two stack halves).
 //   select : one thread per element accumulates the 256 planes (coalesced) until the count exceeds N/2.
 #include "context.hpp"
 

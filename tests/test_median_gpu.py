@@ -263,7 +263,7 @@ def test_cuda_reproduces_reference_golden(gpu_ctx):
 
 # ---- constant-memory form: a stack that cannot grow folds into value histograms (csrc/median_hist.cu) -------------------
 @pytest.mark.parametrize("n,cap,chunk", [(1000, 256, 100), (300, 16, 7), (65, 64, 64), (64, 64, 10), (2100, 1000, 512),
-                                         (5000, 333, 1024)])
+                                         (5000, 333, 1024), (40, 1, 3), (200, 3, 50)])
 def test_stack_that_cannot_grow_folds_into_value_histograms(gpu_ctx, oracle_median, monkeypatch, n, cap, chunk):
     """CVVP_MEDIAN_RESIDENT_MAX caps the resident stack the way a full device does: the job folds the resident frames
     into per-element value histograms and goes on -- memory independent of the frame count, like the reference's
