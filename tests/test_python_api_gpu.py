@@ -38,6 +38,18 @@ def test_background_of_gray_video(gray_video, oracle_median, capfd):
     assert np.array_equal(bg_all, bg)
 
 
+def test_background_of_a_video_longer_than_the_device_holds(gray_video, color_video, oracle_median, monkeypatch):
+    """GetVideoBackground with the resident stack capped (what a video beyond the device's memory does): frames are
+    folded into value histograms as they arrive (csrc/median_hist.cu); same background"""
+    monkeypatch.setenv("CVVP_MEDIAN_RESIDENT_MAX", "16")
+    path, frames = gray_video
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True))
+    assert np.array_equal(bg, oracle_median(frames))
+    path, frames = color_video
+    bg = cvp.GetVideoBackground(cvp.VidBgPack(path, crop_x=5, crop_y=3, crop_width=30, crop_height=20))
+    assert np.array_equal(bg, oracle_median(np.ascontiguousarray(frames[:, 3:23, 5:35])))
+
+
 def test_background_crop_and_color_modes(color_video, oracle_median, capfd):
     path, frames = color_video  # BGR as stored
     # no grayscale flag: element-wise median over all three channels, result (H, W, 3) (ndarray_converter.cpp:141-142)
