@@ -20,8 +20,9 @@ cv_vid_frames_generator_algo.h UNMODIFIED from /root/reference against oracle/sh
 cv::extractChannel, cv::cvtColor forward to the cv2 wheel) into oracle/_ref/cvvp_frames_ref, and
 tests/test_oracle_frames.py holds `prepare_frames` to the tokens GetTokenSet() emits for lossless videos (frame range,
 crop, all three channel modes); tests/golden/frames_golden.json holds hashes of the reference's tokens wherever a video
-can carry the case (tests/golden/make_frames_golden.py).  GetCroppedFrameDims lives in a file that needs the whole
-AsyncTokens/cv_util build and is restated only (twenty lines of integer logic).  Beyond that:
+can carry the case (tests/golden/make_frames_golden.py).  GetCroppedFrameDims is held to the reference's own function, and the crop +
+frame range + channel mode chain to the reference's GetVideoBackground entry point (oracle/_ref/cvvp_background_ref,
+tests/test_oracle_background.py).  Beyond that:
 `rgb2gray_fixed_point` below (the closed form of OpenCV's 8-bit RGB2GRAY) is held to cv2 on ALL 2^24 colour triples
 by tests/test_oracle_frames.py.
 """

@@ -2,6 +2,8 @@
 // Stand-in for <opencv2/opencv.hpp> that lets the reference's own
 //     /root/reference/Sources/ProcessorAlgos/highlight_objects_algo.{h,cpp}
 //     /root/reference/Sources/ProcessorTokenHandlers/cv_vid_frames_generator_algo.h
+//     /root/reference/Sources/cv_vid_bg_helpers.cpp, Sources/Utility/cv_util.cpp (+ the AsyncTokens headers and
+//     histogram_median_algo.h they drive)
 // be compiled UNMODIFIED where OpenCV's C++ headers and libraries are absent (this image): every cv:: function the
 // file calls is forwarded to the function of the same name in the Python wheel `cv2` (OpenCV 4.13), which IS
 // installed and runs OpenCV's real core/imgproc code.  cv::Mat wraps a numpy array; `rows`, `cols` and `data` are
@@ -15,8 +17,12 @@
 //   * cv::drawContours with an empty contour list is a no-op in C++; cv2's binding rejects the empty list -> skipped.
 //   * cv::VideoCapture is cv2.VideoCapture (same FFmpeg backend, same property numbers); `vid >> frame` leaves an
 //     empty Mat at the end of the stream.
-// Built into oracle/_ref/cvvp_highlight_ref*.so and oracle/_ref/cvvp_frames_ref*.so by oracle/Makefile (targets
-// ref_highlight, ref_frames); used by tests/ and by the tests/golden/make_*_golden.py scripts only.
+//   * threads: the reference's pipelines (AsyncTokens) create, copy and drop Mats on worker threads.  Every function here
+//     that talks to Python takes the GIL itself, and a Mat holds its array through shim::PyRef, whose copies and
+//     destructor take it too; the fields `rows`, `cols`, `step`, `data` are plain and need none.  A driver that calls
+//     into threaded reference code releases the GIL around the call.
+// Built into oracle/_ref/cvvp_{highlight,frames,background,binding}_ref*.so by oracle/Makefile (targets ref_highlight,
+// ref_frames, ref_background, ref_binding); used by tests/ and by the tests/golden/make_*_golden.py scripts only.
 #ifndef CVVP_ORACLE_OPENCV_CV2_SHIM_HPP
 #define CVVP_ORACLE_OPENCV_CV2_SHIM_HPP
 
@@ -25,12 +31,16 @@
 
 #include <cassert>
 #include <climits>
+#include <cstdarg>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
 #include <iostream> // the real header brings it in; cv_vid_frames_generator_algo.h:164 relies on that
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #define CV_8U 0
@@ -53,6 +63,8 @@ namespace cv
 {
 namespace py = pybind11;
 typedef unsigned char uchar;
+typedef std::string String;
+class CommandLineParser; // only named in a declaration of the reference's main.h
 
 enum ThresholdTypes { THRESH_BINARY = 0, THRESH_BINARY_INV = 1, THRESH_TRUNC = 2, THRESH_TOZERO = 3, THRESH_TOZERO_INV = 4,
                       THRESH_OTSU = 8 };
@@ -90,6 +102,54 @@ struct Scalar {
 
 namespace shim
 {
+typedef py::gil_scoped_acquire Gil; // re-entrant: harmless where the caller already holds the GIL
+
+// A Python reference that may be copied, moved and dropped on any thread.
+class PyRef
+{
+public:
+    PyRef() = default;
+    explicit PyRef(py::object o)
+    {
+        Gil gil;
+        m_p = o.release().ptr();
+    }
+    PyRef(const PyRef &o)
+    {
+        if (o.m_p) {
+            Gil gil;
+            m_p = o.m_p;
+            Py_INCREF(m_p);
+        }
+    }
+    PyRef(PyRef &&o) noexcept : m_p{o.m_p} { o.m_p = nullptr; }
+    PyRef &operator=(const PyRef &o)
+    {
+        if (this != &o) {
+            PyRef tmp{o};
+            std::swap(m_p, tmp.m_p);
+        }
+        return *this;
+    }
+    PyRef &operator=(PyRef &&o) noexcept
+    {
+        std::swap(m_p, o.m_p);
+        return *this;
+    }
+    ~PyRef()
+    {
+        if (m_p) {
+            Gil gil;
+            Py_DECREF(m_p);
+        }
+    }
+    bool empty() const { return m_p == nullptr; }
+    py::object get() const { return m_p ? py::reinterpret_borrow<py::object>(m_p) : py::object(py::none()); } // GIL held
+
+private:
+    PyObject *m_p{nullptr};
+};
+
 inline py::module_ cv2() { return py::module_::import("cv2"); }
 inline py::module_ np() { return py::module_::import("numpy"); }
 inline py::tuple tup(const Scalar &s) { return py::make_tuple(s.val[0], s.val[1], s.val[2], s.val[3]); }
@@ -122,6 +182,7 @@ class Mat
 public:
     int rows{0};
     int cols{0};
+    std::size_t step{0}; // bytes from one row to the next
     uchar *data{nullptr};
 
     Mat() = default;
@@ -133,71 +194,159 @@ public:
         *this = s;
     }
     explicit Mat(py::array a) { adopt(std::move(a)); }
+    // a column vector over the bytes of a std::vector (cv_util.cpp:291; the shim always copies)
+    Mat(const std::vector<uchar> &vec, bool copy_data)
+    {
+        (void)copy_data;
+        shim::Gil gil;
+        py::array_t<uchar> a({py::ssize_t(vec.size()), py::ssize_t(1)});
+        if (!vec.empty())
+            std::memcpy(a.mutable_data(), vec.data(), vec.size());
+        adopt(std::move(a));
+    }
     Mat(const Mat &) = default; // shares the pixels, like a reference-counted cv::Mat header
-    Mat(Mat &&) = default;
+    Mat(Mat &&o) noexcept : rows{o.rows}, cols{o.cols}, step{o.step}, data{o.data}, m_arr{std::move(o.m_arr)} { o.forget(); }
     Mat &operator=(const Mat &) = default;
-    Mat &operator=(Mat &&) = default;
+    Mat &operator=(Mat &&o) noexcept
+    {
+        if (this != &o) {
+            rows = o.rows;
+            cols = o.cols;
+            step = o.step;
+            data = o.data;
+            m_arr = std::move(o.m_arr);
+            o.m_arr = shim::PyRef{};
+            o.forget();
+        }
+        return *this;
+    }
     inline Mat &operator=(const MatExpr &e);
     Mat &operator=(const Scalar &s) // setTo over every channel
     {
-        if (!m_arr.is_none()) {
+        if (has_array()) {
+            shim::Gil gil;
             if (channels() == 1)
-                m_arr.attr("fill")(s.val[0]);
+                array().attr("fill")(s.val[0]);
             else
-                m_arr[py::ellipsis()] = shim::tup(s)[py::slice(0, channels(), 1)];
+                array()[py::ellipsis()] = shim::tup(s)[py::slice(0, channels(), 1)];
         }
         return *this;
     }
 
     void create(int rows_, int cols_, int type)
     {
+        shim::Gil gil;
         const int cn = CV_MAT_CN(type);
         py::tuple shape = cn == 1 ? py::tuple(py::make_tuple(rows_, cols_)) : py::tuple(py::make_tuple(rows_, cols_, cn));
         adopt(shim::np().attr("zeros")(shape, shim::dtype_name(CV_MAT_DEPTH(type))).cast<py::array>());
     }
     void adopt(py::array a)
     {
+        shim::Gil gil;
         if (a.ndim() != 2 && a.ndim() != 3)
             throw std::invalid_argument("opencv shim: a Mat wraps a 2-D or 3-D array");
-        m_arr = std::move(a);
-        py::array v = array();
-        rows = int(v.shape(0));
-        cols = int(v.shape(1));
-        data = static_cast<uchar *>(v.mutable_data());
+        rows = int(a.shape(0));
+        cols = int(a.shape(1));
+        step = std::size_t(a.strides(0));
+        data = static_cast<uchar *>(a.mutable_data());
+        m_arr = shim::PyRef{std::move(a)};
     }
-    py::array array() const { return m_arr.is_none() ? py::array() : m_arr.cast<py::array>(); }
-    bool has_array() const { return !m_arr.is_none(); }
+    py::array array() const { return has_array() ? m_arr.get().cast<py::array>() : py::array(); } // GIL held by the caller
+    bool has_array() const { return !m_arr.empty(); }
 
-    int channels() const { return has_array() && array().ndim() == 3 ? int(array().shape(2)) : 1; }
-    int depth() const { return has_array() ? shim::depth_of(array()) : CV_8U; }
+    int channels() const
+    {
+        if (!has_array())
+            return 1;
+        shim::Gil gil;
+        py::array a = array();
+        return a.ndim() == 3 ? int(a.shape(2)) : 1;
+    }
+    int depth() const
+    {
+        if (!has_array())
+            return CV_8U;
+        shim::Gil gil;
+        return shim::depth_of(array());
+    }
     int type() const { return CV_MAKETYPE(depth(), channels()); }
     bool empty() const { return data == nullptr || total() == 0; }
-    bool isContinuous() const { return !has_array() || array().attr("flags").attr("c_contiguous").cast<bool>(); }
+    bool isContinuous() const
+    {
+        if (!has_array())
+            return true;
+        shim::Gil gil;
+        return array().attr("flags").attr("c_contiguous").cast<bool>();
+    }
     std::size_t total() const { return std::size_t(rows) * std::size_t(cols); }
     Size size() const { return Size{cols, rows}; }
+    template <typename T>
+    T *ptr(int r)
+    {
+        return reinterpret_cast<T *>(data + std::size_t(r) * step);
+    }
+    template <typename T>
+    const T *ptr(int r) const
+    {
+        return reinterpret_cast<const T *>(data + std::size_t(r) * step);
+    }
 
-    Mat clone() const { return has_array() ? Mat{m_arr.attr("copy")().cast<py::array>()} : Mat{}; }
+    Mat clone() const
+    {
+        if (!has_array())
+            return Mat{};
+        shim::Gil gil;
+        return Mat{array().attr("copy")().cast<py::array>()};
+    }
+    // same bytes, new channel count and row count (columns inferred), cv_util.cpp:291
+    Mat reshape(int cn, int new_rows = 0) const
+    {
+        if (!has_array())
+            return Mat{};
+        shim::Gil gil;
+        py::array a = array();
+        const int old_cn = a.ndim() == 3 ? int(a.shape(2)) : 1;
+        if (cn <= 0)
+            cn = old_cn;
+        if (new_rows <= 0)
+            new_rows = rows;
+        const std::size_t elems = total() * std::size_t(old_cn);
+        if (elems % (std::size_t(cn) * std::size_t(new_rows)) != 0)
+            throw std::invalid_argument("opencv shim: reshape does not divide the elements");
+        const py::ssize_t new_cols = py::ssize_t(elems / (std::size_t(cn) * std::size_t(new_rows)));
+        py::tuple shape = cn == 1 ? py::tuple(py::make_tuple(new_rows, new_cols)) : py::tuple(py::make_tuple(new_rows, new_cols, cn));
+        return Mat{a.attr("reshape")(shape).cast<py::array>()};
+    }
     inline void convertTo(Mat &dst, int rtype) const;
     void copyTo(const Mat &dst) const // destination of the same size (a region of interest): pixels are copied into it
     {
         if (!dst.has_array() || dst.rows != rows || dst.cols != cols)
             throw std::invalid_argument("opencv shim: copyTo needs an allocated destination of the same size");
-        shim::np().attr("copyto")(dst.m_arr, m_arr);
+        shim::Gil gil;
+        shim::np().attr("copyto")(dst.array(), array());
     }
     Mat operator()(const Rect &r) const // a view of the same pixels
     {
-        assert(r.x >= 0 && r.y >= 0 && r.x + r.width <= cols && r.y + r.height <= rows);
-        return Mat{m_arr[py::make_tuple(py::slice(r.y, r.y + r.height, 1), py::slice(r.x, r.x + r.width, 1))].cast<py::array>()};
+        if (r.x < 0 || r.y < 0 || r.width < 0 || r.height < 0 || r.x + r.width > cols || r.y + r.height > rows)
+            throw std::out_of_range("opencv shim: region of interest outside the Mat");
+        shim::Gil gil;
+        return Mat{array()[py::make_tuple(py::slice(r.y, r.y + r.height, 1), py::slice(r.x, r.x + r.width, 1))].cast<py::array>()};
     }
 
 private:
-    py::object m_arr{py::none()};
+    void forget()
+    {
+        rows = cols = 0;
+        step = 0;
+        data = nullptr;
+    }
+    shim::PyRef m_arr{};
 };
 
 namespace shim
 {
 // what an OutputArray does with a result: Mat::create() keeps a buffer of the right size and type and the function
-// writes into it; otherwise the destination header gets a new buffer
+// writes into it; otherwise the destination header gets a new buffer  (GIL held by the caller)
 inline void output(Mat &dst, py::object result)
 {
     py::array r = result.cast<py::array>();
@@ -231,28 +380,42 @@ inline MatExpr operator-(const Mat &a, const Mat &b) { return MatExpr{a, b}; }
 
 inline Mat &Mat::operator=(const MatExpr &e)
 {
+    shim::Gil gil;
     shim::output(*this, shim::cv2().attr("subtract")(e.a.array(), e.b.array())); // dtype = -1: the operands' depth
     return *this;
 }
 
 inline void Mat::convertTo(Mat &dst, int rtype) const
 {
+    shim::Gil gil;
     const int d = rtype < 0 ? depth() : CV_MAT_DEPTH(rtype);
+    py::object src = array();
     py::object out;
     if (d == depth()) {
-        out = m_arr.attr("copy")();
+        out = src.attr("copy")();
     } else if (d >= CV_32F) {
-        out = m_arr.attr("astype")(shim::dtype_name(d));
+        out = src.attr("astype")(shim::dtype_name(d));
     } else { // saturate_cast: round to nearest even, clamp to the target's range
         py::module_ np = shim::np();
         py::object info = np.attr("iinfo")(shim::dtype_name(d));
-        out = np.attr("clip")(np.attr("rint")(m_arr), info.attr("min"), info.attr("max")).attr("astype")(shim::dtype_name(d));
+        out = np.attr("clip")(np.attr("rint")(src), info.attr("min"), info.attr("max")).attr("astype")(shim::dtype_name(d));
     }
     shim::output(dst, out);
 }
 
+inline std::string format(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    return std::string{buf};
+}
+
 inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, int type)
 {
+    shim::Gil gil;
     py::tuple r = shim::cv2().attr("threshold")(src.array(), thresh, maxval, type);
     shim::output(dst, r[1]);
     return r[0].cast<double>();
@@ -261,11 +424,13 @@ inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, 
 inline void morphologyEx(const Mat &src, Mat &dst, int op, const Mat &kernel)
 {
     // defaults of the C++ signature: anchor (-1,-1), 1 iteration, BORDER_CONSTANT with morphologyDefaultBorderValue()
+    shim::Gil gil;
     shim::output(dst, shim::cv2().attr("morphologyEx")(src.array(), op, kernel.array()));
 }
 
 inline void findContours(const Mat &image, std::vector<std::vector<Point>> &contours, int mode, int method)
 {
+    shim::Gil gil;
     py::tuple r = shim::cv2().attr("findContours")(image.array(), mode, method);
     contours.clear();
     for (py::handle h : r[0]) {
@@ -281,6 +446,7 @@ inline void findContours(const Mat &image, std::vector<std::vector<Point>> &cont
 
 inline double contourArea(const std::vector<Point> &contour, bool oriented = false)
 {
+    shim::Gil gil;
     return shim::cv2().attr("contourArea")(shim::contour_array(contour), oriented).cast<double>();
 }
 
@@ -289,6 +455,7 @@ inline void drawContours(Mat &image, const std::vector<std::vector<Point>> &cont
 {
     if (contours.empty())
         return; // C++ loops over nothing; the Python binding refuses an empty list
+    shim::Gil gil;
     py::list cs;
     for (const auto &c : contours)
         cs.append(shim::contour_array(c));
@@ -298,6 +465,7 @@ inline void drawContours(Mat &image, const std::vector<std::vector<Point>> &cont
 inline int floodFill(Mat &image, Point seedPoint, Scalar newVal, Rect *rect = nullptr, Scalar loDiff = Scalar(),
                      Scalar upDiff = Scalar(), int flags = 4)
 {
+    shim::Gil gil;
     py::tuple r = shim::cv2().attr("floodFill")(image.array(), py::none(), shim::tup(seedPoint), shim::tup(newVal),
                                                  shim::tup(loDiff), shim::tup(upDiff), flags);
     shim::output(image, r[1]);
@@ -310,25 +478,53 @@ inline int floodFill(Mat &image, Point seedPoint, Scalar newVal, Rect *rect = nu
 
 inline void extractChannel(const Mat &src, Mat &dst, int coi)
 {
+    shim::Gil gil;
     shim::output(dst, shim::cv2().attr("extractChannel")(src.array(), coi));
 }
 
-inline void cvtColor(const Mat &src, Mat &dst, int code) { shim::output(dst, shim::cv2().attr("cvtColor")(src.array(), code)); }
+inline void cvtColor(const Mat &src, Mat &dst, int code)
+{
+    shim::Gil gil;
+    shim::output(dst, shim::cv2().attr("cvtColor")(src.array(), code));
+}
 
 class VideoCapture
 {
 public:
     VideoCapture() = default;
-    explicit VideoCapture(const std::string &filename) : m_cap{shim::cv2().attr("VideoCapture")(filename)} {}
-    bool isOpened() const { return !m_cap.is_none() && m_cap.attr("isOpened")().cast<bool>(); }
-    double get(int prop) const { return m_cap.is_none() ? 0.0 : m_cap.attr("get")(prop).cast<double>(); }
-    bool set(int prop, double value) { return !m_cap.is_none() && m_cap.attr("set")(prop, value).cast<bool>(); }
+    explicit VideoCapture(const std::string &filename)
+    {
+        shim::Gil gil;
+        m_cap = shim::PyRef{shim::cv2().attr("VideoCapture")(filename)};
+    }
+    bool isOpened() const
+    {
+        if (m_cap.empty())
+            return false;
+        shim::Gil gil;
+        return m_cap.get().attr("isOpened")().cast<bool>();
+    }
+    double get(int prop) const
+    {
+        if (m_cap.empty())
+            return 0.0;
+        shim::Gil gil;
+        return m_cap.get().attr("get")(prop).cast<double>();
+    }
+    bool set(int prop, double value)
+    {
+        if (m_cap.empty())
+            return false;
+        shim::Gil gil;
+        return m_cap.get().attr("set")(prop, value).cast<bool>();
+    }
     bool read(Mat &image)
     {
         image = Mat{}; // a failed read releases the destination
-        if (m_cap.is_none())
+        if (m_cap.empty())
             return false;
-        py::tuple r = m_cap.attr("read")();
+        shim::Gil gil;
+        py::tuple r = m_cap.get().attr("read")();
         if (!r[0].cast<bool>() || r[1].is_none())
             return false;
         image = Mat{r[1].cast<py::array>()};
@@ -341,13 +537,18 @@ public:
     }
 
 private:
-    py::object m_cap{py::none()};
+    shim::PyRef m_cap{};
 };
 
-inline void bitwise_not(const Mat &src, Mat &dst) { shim::output(dst, shim::cv2().attr("bitwise_not")(src.array())); }
+inline void bitwise_not(const Mat &src, Mat &dst)
+{
+    shim::Gil gil;
+    shim::output(dst, shim::cv2().attr("bitwise_not")(src.array()));
+}
 
 inline void bitwise_or(const Mat &a, const Mat &b, Mat &dst)
 {
+    shim::Gil gil;
     shim::output(dst, shim::cv2().attr("bitwise_or")(a.array(), b.array()));
 }
 } // namespace cv

@@ -140,3 +140,42 @@ def test_median_c_abi_against_the_reference_class_on_generator_tokens(gpu_ctx, c
             gpu_ctx.median_push_source(decoded[i:i + 11], fmt)
         got = gpu_ctx.median_finish(nelem=nelem).reshape(want.shape)
         assert np.array_equal(got, want), (crop, mode)
+
+
+def test_get_video_background_equals_the_reference_entry_point(colour_stream, tmp_path, capfd):
+    """The drop-in claim at the public entry point: the reference's own GetVideoBackground -- cv_vid_bg_helpers.cpp with
+    the whole AsyncTokens pipeline behind it, compiled unmodified (oracle/_ref/cvvp_background_ref) -- and this
+    module's GetVideoBackground get the same VidBgPack fields and must return the same image and print the same
+    video-information line"""
+    from oracle import background_ref as bgref
+
+    if not bgref.available():
+        pytest.skip("oracle/_ref/cvvp_background_ref was not built")
+    path, frames = colour_stream
+    rng = np.random.default_rng(21)
+    portrait = np.clip(rng.integers(0, 256, (60, 40, 3), dtype=np.int16)[None] + rng.integers(-30, 31, (33, 60, 40, 3)), 0,
+                       255).astype(np.uint8)
+    ppath = video_util.write_lossless(tmp_path / "portrait.avi", portrait)
+    packs = [
+        (path, dict()),
+        (path, dict(grayscale=True)),
+        (path, dict(vid_is_grayscale=True, max_threads=3)),
+        (path, dict(grayscale=True, crop_x=8, crop_y=6, crop_width=150, crop_height=90, max_threads=5)),
+        (path, dict(frame_limit=17, crop_x=100, crop_width=500)),            # width clamped to the frame
+        (path, dict(frame_limit=10_000, vid_is_grayscale=True, crop_y=50)),   # limit beyond the stream
+        (ppath, dict(vid_is_grayscale=True, crop_y=30, crop_width=20, crop_height=25)),   # the :56 quirk: 30 rows come back
+        (ppath, dict(grayscale=True, max_threads=2, frame_limit=32)),
+    ]
+    for vid, kw in packs:
+        capfd.readouterr()
+        want = bgref.get_video_background(vid, **kw)
+        ref_out = capfd.readouterr().out
+        got = cvp.GetVideoBackground(cvp.VidBgPack(vid, **kw))
+        our_out = capfd.readouterr().out
+        assert want is not None and got.dtype == np.uint8 and got.shape == want.shape, kw
+        assert np.array_equal(got, want), kw
+        info = [ln for ln in ref_out.splitlines() if ln.startswith("Frames:")]
+        assert info and info[0] in our_out.splitlines(), (info, our_out)
+    # both report a missing video the same way: an empty result
+    assert bgref.get_video_background("/no/such/video.avi") is None
+    assert cvp.GetVideoBackground(cvp.VidBgPack("/no/such/video.avi")) is None
