@@ -16,6 +16,7 @@
 // to it; tests/test_reference_chain_gpu.py holds the drop-in module's GetVideoBackground to it, pack for pack.
 //
 // Built only where /root/reference is mounted, into oracle/_ref/ (git-ignored, travels with the snapshot).
+#include <iostream>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -69,6 +70,7 @@ PYBIND11_MODULE(cvvp_background_ref, m)
                 py::gil_scoped_release nogil; // the reference's threads call back into the shim, which takes the GIL
                 bg = GetVideoBackground(pack);
             }
+            std::cout.flush(); // the reference ends its report lines with '\n'; tests read them back at once
             if (!bg.has_array() || bg.empty())
                 return py::none();
             return bg.array();
