@@ -5,6 +5,7 @@ bin-width dispatch (8 / 16-bit histograms), strip split over any number of worke
 import numpy as np
 import pytest
 
+import report_format
 import video_util
 from oracle import background_ref as bgref
 from oracle import frames_oracle as fo
@@ -92,3 +93,14 @@ def test_entry_point_reports_and_failures(video, capfd):
     assert bgref.get_video_background(path, bg_algo="mean") is None  # unknown algorithm (:20-31, :262-266)
     bgref.get_video_background(path, max_threads=2, crop_x=3, crop_y=5, crop_width=33, crop_height=20)
     assert "Frames: 60; Res: 70x48(33x20 cropped); FPS: 30" in capfd.readouterr().out
+
+
+def test_timing_report_lines_of_the_reference(video, capfd):
+    """print_timing_report: what the reference really prints (async_token_process.h:273-414); the drop-in module's report
+    is held to the same expressions on the GPU (tests/test_python_api_gpu.py)"""
+    path, frames = video
+    capfd.readouterr()
+    bgref.get_video_background(path, max_threads=3, vid_is_grayscale=True, print_timing_report=True)
+    out = capfd.readouterr().out
+    report_format.check(out)
+    assert "(60 batches;" in out and "(60 tokens;" in out

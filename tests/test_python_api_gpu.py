@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import cvvidproc_b200 as cvp
+import report_format
 import video_util
 from cvvidproc_b200 import synth
 from oracle import highlight_oracle as ho
@@ -154,10 +155,7 @@ def test_timing_reports_follow_the_reference_format(gray_video, capfd):
     path, frames = gray_video
     bg = cvp.GetVideoBackground(cvp.VidBgPack(path, vid_is_grayscale=True, print_timing_report=True))
     out = capfd.readouterr().out
-    num = r"\d+ ms \(\d+ (batches|tokens); \d+ ms avg\)"
-    for head, tail in (("Batch loading", "on time between each generated batch"), ("Batch gen", "on generating batches"),
-                       ("Result consume", "on handling results"), (r"Unit \[1\]", "on ingesting tokens in workers")):
-        assert re.search(rf"^{head}: {num} {tail}$", out, re.M), (head, out)
+    report_format.check(out)  # the same expressions match the reference's own output (tests/test_oracle_background.py)
     assert "(60 batches;" in out and "(60 tokens;" in out
     p = ho.canonical_params(bg)
     hp = cvp.HighlightObjectsPack(bg, p.struct_element, p.threshold, p.threshold_lo, p.threshold_hi, p.min_size_hyst,
