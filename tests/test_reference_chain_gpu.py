@@ -179,3 +179,6 @@ def test_get_video_background_equals_the_reference_entry_point(colour_stream, tm
     # both report a missing video the same way: an empty result
     assert bgref.get_video_background("/no/such/video.avi") is None
     assert cvp.GetVideoBackground(cvp.VidBgPack("/no/such/video.avi")) is None
+    # ... and an unknown algorithm name (cv_vid_bg_helpers.cpp:20-31, :262-266)
+    assert bgref.get_video_background(path, bg_algo="mean") is None
+    assert cvp.GetVideoBackground(cvp.VidBgPack(path, bg_algo="mean")) is None
