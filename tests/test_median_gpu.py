@@ -304,9 +304,8 @@ def test_folding_with_device_prepared_colour_frames_and_pinned_sources(gpu_ctx, 
     n, h, w = 203, 50, 70
     base = rng.integers(0, 256, (h, w, 3), dtype=np.int16)
     frames = np.clip(base[None] + rng.integers(-25, 26, (n, h, w, 3)), 0, 255).astype(np.uint8)
-    crop = (3, 4, 61, 40)
-    for mode in (fo.RGB2GRAY, fo.AS_IS):
-        fmt = _cabi.FrameFormat.of((h, w, 3), mode, crop)
+    for mode, crop in ((fo.RGB2GRAY, (3, 4, 61, 40)), (fo.AS_IS, (3, 4, 61, 40)), (fo.AS_IS, (0, 6, 70, 31))):  # the last one:
+        fmt = _cabi.FrameFormat.of((h, w, 3), mode, crop)                          # full-width rows, copied without a kernel
         prepared = fo.prepare_frames(frames, crop, mode)
         nelem = int(np.prod(prepared.shape[1:]))
         gpu_ctx.median_begin(nelem, n)
