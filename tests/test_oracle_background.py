@@ -48,6 +48,15 @@ def test_entry_point_matches_the_chained_oracles(video, oracle_median, kw, mode)
             assert np.array_equal(bg, want), (crop, max_threads, frame_limit)
 
 
+def test_token_storage_limits_do_not_change_the_result(video, oracle_median):
+    """token_storage_limit bounds the reference's queues (token_queue.h:209-214): back-pressure, same image"""
+    path, frames = video
+    want = _want(frames, oracle_median, 60, (0, 0, 70, 48), fo.RGB2GRAY)
+    for limit in (1, 2, 10, -1):
+        bg = bgref.get_video_background(path, max_threads=6, grayscale=True, token_storage_limit=limit)
+        assert np.array_equal(bg, want), limit
+
+
 def test_bin_width_dispatch_beyond_255_frames(tmp_path, oracle_median):
     """more than 255 frames: the reference switches to 16-bit histograms (cv_vid_bg_helpers.cpp:232-253); with
     frame_limit <= 255 on the same video it uses 8-bit ones.  A pixel that is constant over 300 frames would saturate an
