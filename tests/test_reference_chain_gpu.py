@@ -142,6 +142,7 @@ def test_median_c_abi_against_the_reference_class_on_generator_tokens(gpu_ctx, c
         assert np.array_equal(got, want), (crop, mode)
 
 
+@pytest.mark.timeout(300, method="thread")  # the reference runs its own threads: a stalled pipeline must not hang the run
 def test_get_video_background_equals_the_reference_entry_point(colour_stream, tmp_path, capfd):
     """The drop-in claim at the public entry point: the reference's own GetVideoBackground -- cv_vid_bg_helpers.cpp with
     the whole AsyncTokens pipeline behind it, compiled unmodified (oracle/_ref/cvvp_background_ref) -- and this
