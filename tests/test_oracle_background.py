@@ -1,7 +1,10 @@
 """CPU tests against the reference's own GetVideoBackground ENTRY POINT, compiled unmodified with everything behind it
 (oracle/_ref/cvvp_background_ref, see oracle/background_ref.py): the oracles of the frame source and of the median,
 chained, must give what the reference's pipeline gives for the same VidBgPack -- crop rule and quirk, frame_limit,
-bin-width dispatch (8 / 16-bit histograms), strip split over any number of workers, the three channel modes."""
+bin-width dispatch (8 / 16-bit histograms), strip split over any number of workers, the three channel modes.
+
+The reference's calls run in a child process with a time limit (background_ref.run_isolated): its thread pipeline was
+seen to stall on a loaded machine, and a stall must cost a retry, not the test run."""
 import numpy as np
 import pytest
 
@@ -10,9 +13,7 @@ import video_util
 from oracle import background_ref as bgref
 from oracle import frames_oracle as fo
 
-# the reference runs its own threads: a stalled pipeline must end the run, not hang it
-pytestmark = [pytest.mark.skipif(not bgref.available(), reason="oracle/_ref/cvvp_background_ref was not built (no /root/reference)"),
-              pytest.mark.timeout(180, method="thread")]
+pytestmark = pytest.mark.skipif(not bgref.available(), reason="oracle/_ref/cvvp_background_ref was not built (no /root/reference)")
 
 
 def _stream(n, h, w, seed):
@@ -37,17 +38,19 @@ def _want(frames, oracle_median, n, crop, mode):
                                      ({"grayscale": True, "vid_is_grayscale": True}, fo.CHANNEL0)])
 def test_entry_point_matches_the_chained_oracles(video, oracle_median, kw, mode):
     path, frames = video
+    jobs, wants = [], []
     for crop in ((0, 0, 0, 0), (3, 5, 33, 20), (69, 47, 0, 0), (10, 0, 500, 0)):
         c = fo.get_cropped_frame_dims(*crop, 70, 48)
         for max_threads, frame_limit in ((1, -1), (2, 25), (5, -1), (8, 10_000), (3, 1)):
             if c[2] < 8 and max_threads > 2:
                 continue  # a crop narrower than the strip count makes the reference's own strip split fail (cv_util.cpp:52-56)
-            bg = bgref.get_video_background(path, max_threads=max_threads, frame_limit=frame_limit, crop_x=crop[0], crop_y=crop[1],
-                                            crop_width=crop[2], crop_height=crop[3], **kw)
+            jobs.append((path, dict(max_threads=max_threads, frame_limit=frame_limit, crop_x=crop[0], crop_y=crop[1],
+                                    crop_width=crop[2], crop_height=crop[3], **kw)))
             n = len(frames) if frame_limit <= 0 else min(frame_limit, len(frames))
-            want = _want(frames, oracle_median, n, c, mode)
-            assert bg is not None and bg.dtype == np.uint8 and bg.shape == want.shape, (crop, max_threads, frame_limit)
-            assert np.array_equal(bg, want), (crop, max_threads, frame_limit)
+            wants.append(_want(frames, oracle_median, n, c, mode))
+    for (_, pack), (bg, _, _), want in zip(jobs, bgref.run_isolated(jobs), wants):
+        assert bg is not None and bg.dtype == np.uint8 and bg.shape == want.shape, pack
+        assert np.array_equal(bg, want), pack
 
 
 def test_token_storage_limits_do_not_change_the_result(video, oracle_median):
@@ -56,9 +59,9 @@ def test_token_storage_limits_do_not_change_the_result(video, oracle_median):
     are not compared.)"""
     path, frames = video
     want = _want(frames, oracle_median, 60, (0, 0, 70, 48), fo.RGB2GRAY)
-    for limit in (3, 5, 10, -1):
-        bg = bgref.get_video_background(path, max_threads=3, grayscale=True, token_storage_limit=limit)
-        assert np.array_equal(bg, want), limit
+    jobs = [(path, dict(max_threads=3, grayscale=True, token_storage_limit=limit)) for limit in (3, 5, 10, -1)]
+    for (_, pack), (bg, _, _) in zip(jobs, bgref.run_isolated(jobs)):
+        assert np.array_equal(bg, want), pack
 
 
 def test_bin_width_dispatch_beyond_255_frames(tmp_path, oracle_median):
@@ -69,16 +72,17 @@ def test_bin_width_dispatch_beyond_255_frames(tmp_path, oracle_median):
     frames[:, 0, :4] = 200  # constant pixels
     path = video_util.write_lossless(tmp_path / "long.avi", frames)
     assert np.array_equal(video_util.read_all(path), frames)
-    for limit in (-1, 255, 256):
+    limits = (-1, 255, 256)
+    jobs = [(path, dict(max_threads=4, frame_limit=limit, grayscale=True)) for limit in limits]
+    for limit, (bg, _, _) in zip(limits, bgref.run_isolated(jobs)):
         n = 300 if limit <= 0 else limit
-        bg = bgref.get_video_background(path, max_threads=4, frame_limit=limit, grayscale=True)
         assert np.array_equal(bg, _want(frames, oracle_median, n, (0, 0, 26, 20), fo.RGB2GRAY)), limit
 
 
 def test_crop_rule_and_its_quirk_on_a_portrait_video(tmp_path, oracle_median):
     """GetCroppedFrameDims (:39-60) compares height + y against the WIDTH (:56): on a portrait frame a legal height is
     clamped as soon as it exceeds the width; followed by the restatement and by the drop-in module"""
-    ref = bgref.load().GetCroppedFrameDims
+    ref = bgref.load().GetCroppedFrameDims  # plain integer logic, no threads: called in this process
     for args in ((0, 0, 0, 0, 640, 480), (10, 20, 100, 50, 640, 480), (600, 0, 100, 0, 640, 480), (0, 200, 0, 300, 640, 480),
                  (0, 100, 0, 400, 480, 640), (5, 7, 1, 1, 9, 11), (0, 30, 20, 25, 40, 60), (39, 59, 5, 5, 40, 60)):
         assert tuple(ref(*args)) == fo.get_cropped_frame_dims(*args), args
@@ -94,26 +98,24 @@ def test_crop_rule_and_its_quirk_on_a_portrait_video(tmp_path, oracle_median):
     crop = (0, 30, 20, 25)
     c = fo.get_cropped_frame_dims(*crop, 40, 60)
     assert c == (0, 30, 20, 30)
-    bg = bgref.get_video_background(path, max_threads=2, vid_is_grayscale=True, crop_x=0, crop_y=30, crop_width=20, crop_height=25)
+    (bg, _, _), = bgref.run_isolated([(path, dict(max_threads=2, vid_is_grayscale=True, crop_x=0, crop_y=30, crop_width=20,
+                                                  crop_height=25))])
     assert bg.shape == (30, 20)
     assert np.array_equal(bg, _want(frames, oracle_median, 21, c, fo.CHANNEL0))
 
 
-def test_entry_point_reports_and_failures(video, capfd):
+def test_entry_point_reports_and_failures(video):
     path, frames = video
-    assert bgref.get_video_background("/no/such/video.avi") is None
-    assert "Video file not detected" in capfd.readouterr().err
-    assert bgref.get_video_background(path, bg_algo="mean") is None  # unknown algorithm (:20-31, :262-266)
-    bgref.get_video_background(path, max_threads=2, crop_x=3, crop_y=5, crop_width=33, crop_height=20)
-    assert "Frames: 60; Res: 70x48(33x20 cropped); FPS: 30" in capfd.readouterr().out
-
-
-def test_timing_report_lines_of_the_reference(video, capfd):
-    """print_timing_report: what the reference really prints (async_token_process.h:273-414); the drop-in module's report
-    is held to the same expressions on the GPU (tests/test_python_api_gpu.py)"""
-    path, frames = video
-    capfd.readouterr()
-    bgref.get_video_background(path, max_threads=3, vid_is_grayscale=True, print_timing_report=True)
-    out = capfd.readouterr().out
-    report_format.check(out)
-    assert "(60 batches;" in out and "(60 tokens;" in out
+    missing, unknown, cropped, timed = bgref.run_isolated([
+        ("/no/such/video.avi", {}),
+        (path, dict(bg_algo="mean")),  # unknown algorithm (:20-31, :262-266)
+        (path, dict(max_threads=2, crop_x=3, crop_y=5, crop_width=33, crop_height=20)),
+        (path, dict(max_threads=3, vid_is_grayscale=True, print_timing_report=True)),
+    ])
+    assert missing[0] is None and "Video file not detected" in missing[2]
+    assert unknown[0] is None and "Unknown background algorithm detected: mean" in unknown[2]
+    assert "Frames: 60; Res: 70x48(33x20 cropped); FPS: 30" in cropped[1]
+    # print_timing_report: what the reference really prints (async_token_process.h:273-414); the drop-in module's report
+    # is held to the same expressions on the GPU (tests/test_python_api_gpu.py)
+    report_format.check(timed[1])
+    assert "(60 batches;" in timed[1] and "(60 tokens;" in timed[1]
