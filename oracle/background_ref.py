@@ -6,10 +6,12 @@ UNMODIFIED from /root/reference against oracle/shim_cv2 (oracle/background_ref_d
 Only tests/ import this module.  It pins what no single class does: the crop rule and its quirk, frame_limit, the
 bin-width dispatch, the per-generator frame ranges, the strip split and re-assembly, batch sizes from max_threads.
 
-The reference's thread pipeline, run through the GIL-taking shim, was seen to stall now and then on a loaded machine
-(4 of 10 runs with six test processes on eight cores; never on an idle one; cause not established -- no debugger in this
-image).  `run_isolated` therefore runs the calls in a child process with a time limit and starts the unfinished ones again,
-so that a stall costs a retry instead of hanging the test run."""
+The reference's worker threads reach OpenCV through Python here.  With a Python thread state created and deleted around
+every call (what pybind11's gil_scoped_acquire does on threads Python did not start) the pipeline stalled now and then
+on a loaded machine; the shim now keeps one thread state per reference thread (shim::Gil) and 600 calls under heavy
+load completed.  `run_isolated` stays as a guard: it runs the calls in a child process with a progress watchdog and
+starts unfinished ones again, so that a stall of the reference's pipeline (token_storage_limit below its generator
+count does stall it, deterministically) costs a retry instead of hanging the test run."""
 from __future__ import annotations
 
 import importlib.util

@@ -102,7 +102,55 @@ struct Scalar {
 
 namespace shim
 {
-typedef py::gil_scoped_acquire Gil; // re-entrant: harmless where the caller already holds the GIL
+// Takes the GIL for the current scope; a no-op where the caller already holds it.  A thread the reference created keeps
+// ONE Python thread state for its whole life (made on its first call, dropped when the thread ends) and only hands the
+// GIL back between calls -- creating and deleting a thread state around every call, as PyGILState_Ensure / Release or
+// pybind11's gil_scoped_acquire do on such threads, is what the reference's worker threads would otherwise do thousands
+// of times per video.
+class Gil
+{
+public:
+    Gil()
+    {
+        if (PyGILState_Check())
+            return;
+        Slot &t = slot();
+        if (!t.made) {
+            t.state = PyGILState_Ensure();
+            t.made = true;
+        } else {
+            PyEval_RestoreThread(t.saved);
+        }
+        m_taken = true;
+    }
+    ~Gil()
+    {
+        if (m_taken)
+            slot().saved = PyEval_SaveThread();
+    }
+    Gil(const Gil &) = delete;
+    Gil &operator=(const Gil &) = delete;
+
+private:
+    struct Slot {
+        bool made{false};
+        PyGILState_STATE state{};
+        PyThreadState *saved{nullptr};
+        ~Slot()
+        {
+            if (made && saved && Py_IsInitialized()) {
+                PyEval_RestoreThread(saved);
+                PyGILState_Release(state);
+            }
+        }
+    };
+    static Slot &slot()
+    {
+        thread_local Slot s;
+        return s;
+    }
+    bool m_taken{false};
+};
 
 // A Python reference that may be copied, moved and dropped on any thread.
 class PyRef

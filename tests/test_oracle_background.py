@@ -3,8 +3,8 @@
 chained, must give what the reference's pipeline gives for the same VidBgPack -- crop rule and quirk, frame_limit,
 bin-width dispatch (8 / 16-bit histograms), strip split over any number of workers, the three channel modes.
 
-The reference's calls run in a child process with a time limit (background_ref.run_isolated): its thread pipeline was
-seen to stall on a loaded machine, and a stall must cost a retry, not the test run."""
+The reference's calls run in a child process with a progress watchdog (background_ref.run_isolated): a stall of its
+thread pipeline must cost a retry, not the test run."""
 import numpy as np
 import pytest
 
